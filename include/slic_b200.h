@@ -1,0 +1,186 @@
+/*
+ * slic_b200.h - C ABI of the B200-native FINCH / nearest-neighbour hot path.
+ *
+ * The reference (rvl-lab-utoronto/video_similarity_search) is pure Python: it has no FFI layer,
+ * its module-level functions are the boundary.  This header is what a binding for that path
+ * would call instead of numpy / scipy / scikit-learn; every entry point names the reference
+ * lines it replaces (paths relative to the reference root).  INTEGRATION.md shows the ctypes
+ * stub a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every function returns 0 (SLIC_OK) or a negative slic_status; the message for the last
+ *     failure on the calling thread is slic_last_error().  Nothing throws across the boundary.
+ *   - pointers named *_dev are device pointers on the current CUDA device; the *_host entry
+ *     points at the end take host buffers and do their own transfers.
+ *   - all device work is ordered on `stream` (a cudaStream_t passed as void*; NULL = the legacy
+ *     default stream); temporaries come from the stream-ordered allocator, so no call blocks the
+ *     host except where a result is returned through a host pointer (documented per call).
+ *   - dtype: SLIC_F32 or SLIC_F64 - the arithmetic type of the reference at that call site
+ *     (float32 at FINCH level 0, float64 at levels >= 1: clustering/finch.py:62,131).
+ *   - matrices are dense row-major; indices / labels on the device are int32.
+ *   - there is no CPU fallback: without an sm_100 device the calls fail with SLIC_ERR_NO_DEVICE.
+ */
+#ifndef SLIC_B200_H
+#define SLIC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLIC_ABI_VERSION 1
+
+#define SLIC_F32 0
+#define SLIC_F64 1
+
+#define SLIC_METRIC_COSINE 0
+#define SLIC_METRIC_EUCLIDEAN 1
+
+typedef enum slic_status {
+    SLIC_OK = 0,
+    SLIC_ERR_INVALID_ARG = -1,
+    SLIC_ERR_CUDA = -2,
+    SLIC_ERR_UNSUPPORTED = -3,
+    SLIC_ERR_NO_DEVICE = -4,
+    SLIC_ERR_OVERFLOW = -5
+} slic_status;
+
+typedef void* slic_stream_t; /* cudaStream_t */
+
+/* ---- library ---------------------------------------------------------------------------- */
+int slic_abi_version(void);
+const char* slic_last_error(void);
+/* SLIC_OK only if the current device is compute capability 10.x (B200 / sm_100a). */
+int slic_require_device(void);
+
+/* ---- K1 prep: row normalisation --------------------------------------------------------- */
+/* sklearn cosine_similarity's normalize step behind clustering/finch.py:27, evaluate.py:213,
+ * iic_retrieve_clips.py:295:  norm_i = sqrt(sum_k x_ik^2) (0 -> 1),  unit_i = x_i / norm_i in
+ * `dtype`.  Optionally also emits the bf16 copy (row stride d_pad, zero padded; d_pad % 64 == 0)
+ * that the tensor-core screen reads.  unit_dev / norms_dev / unit_bf16_dev may each be NULL. */
+int slic_normalize_rows(const void* x_dev, int64_t n, int32_t d, int32_t dtype,
+                        void* unit_dev, void* norms_dev,
+                        uint16_t* unit_bf16_dev, int32_t d_pad, slic_stream_t stream);
+
+/* ---- K1 exact: brute-force first neighbour in the reference dtype ------------------------ */
+/* clustering/finch.py:27-29 (pairwise_distances + fill_diagonal + argmin) without the n x n
+ * matrix: for query row r (database row r + self_offset when self_offset >= 0, which is then
+ * excluded) the column with the smallest clip(1 - <q_r, x_j>, 0, 2); ties -> lowest j.
+ * Products are accumulated in float64.  q_rows_dev (optional) lists the query rows to process
+ * (indices into q_unit_dev); outputs are indexed by position in that list.  */
+int slic_nn_exact_top1(const void* q_unit_dev, const int32_t* q_rows_dev, int64_t nq,
+                       const void* x_unit_dev, int64_t n, int32_t d, int32_t dtype,
+                       int64_t self_offset, int32_t* idx_out_dev, void* dist_out_dev,
+                       slic_stream_t stream);
+
+/* ---- K1 tensor-core screen + exact re-rank ------------------------------------------------ */
+/* The same first-neighbour search as slic_nn_exact_top1, done as a bf16 tcgen05 GEMM with a
+ * fused per-row candidate filter (scores never leave the SM) followed by an exact re-rank of
+ * the surviving candidates in `dtype`.  eps is the screen's error allowance: every column whose
+ * bf16 score is within eps of the row's best is re-ranked (eps <= 0 selects the provable
+ * default 2^-7).  Rows whose candidate list overflowed are finished by the exact kernel, so the
+ * result never depends on the screen's precision.  q_* may equal x_* (FINCH self-search). */
+int slic_nn_top1(const void* q_unit_dev, const uint16_t* q_bf16_dev, int64_t nq,
+                 const void* x_unit_dev, const uint16_t* x_bf16_dev, int64_t n,
+                 int32_t d, int32_t d_pad, int32_t dtype, int64_t self_offset, float eps,
+                 int32_t* idx_out_dev, void* dist_out_dev, int32_t* stats_out_dev /* [4] or NULL:
+                 candidates re-ranked, rows finished by the exact kernel, list compactions, 0 */,
+                 slic_stream_t stream);
+
+/* Debug / test hook: raw bf16-screen scores of one 128 x 256 tile region, written as float
+ * [nq, n] (small shapes only).  Lets the tests check the tcgen05 path element by element. */
+int slic_screen_scores_debug(const uint16_t* q_bf16_dev, int64_t nq, const uint16_t* x_bf16_dev,
+                             int64_t n, int32_t d_pad, float* out_dev, slic_stream_t stream);
+
+/* ---- K1 dense / top-k (retrieval) ------------------------------------------------------- */
+/* evaluate.py:208-223 (get_distance_matrix), iic_retrieve_clips.py:295: dense [nq, n] distance
+ * matrix in `dtype`.  cosine: inputs are unit rows, out = clip(1 - s, 0, 2); euclidean: inputs
+ * are raw rows, out = sqrt(max(|q|^2 + |x|^2 - 2 s, 0)) evaluated in float64 (as sklearn does).  same_matrix != 0
+ * zeroes the diagonal exactly as sklearn does for Y is None. */
+int slic_distance_matrix(const void* q_dev, int64_t nq, const void* x_dev, int64_t n,
+                         int32_t d, int32_t dtype, int32_t metric, int32_t same_matrix,
+                         void* out_dev, int64_t ld_out, slic_stream_t stream);
+
+/* evaluate.py:226-231 (get_closest_data_mat), iic_retrieve_clips.py:296: the k smallest entries
+ * of every row of a dense [nq, n] matrix, ascending (ties -> lowest column).  */
+int slic_rows_topk(const void* dist_dev, int64_t nq, int64_t n, int64_t ld, int32_t dtype,
+                   int32_t k, int32_t* idx_out_dev, void* val_out_dev, slic_stream_t stream);
+
+/* Fused form of the two calls above (no [nq, n] matrix in HBM beyond one row block):
+ * top-k cosine neighbours of unit query rows among unit database rows. */
+int slic_topk_cosine(const void* q_unit_dev, int64_t nq, const void* x_unit_dev, int64_t n,
+                     int32_t d, int32_t dtype, int32_t k, int64_t self_offset,
+                     int32_t* idx_out_dev, void* dist_out_dev, slic_stream_t stream);
+
+/* evaluate.py:287-307 (get_topk_acc), iic_retrieve_clips.py:298-306: hits[m] = number of query
+ * rows whose label occurs among the labels of their first ks[m] neighbours. */
+int slic_hit_at_k(const int32_t* topk_idx_dev, int64_t nq, int32_t k_stride,
+                  const int64_t* q_labels_dev, const int64_t* x_labels_dev,
+                  const int32_t* ks_dev, int32_t num_ks, int32_t* hits_out_dev,
+                  slic_stream_t stream);
+
+/* ---- K2: first-neighbour graph components ------------------------------------------------- */
+/* clustering/finch.py:40-47 + 50-55 (sparse (P+I)(P+I)^T, optional min_sim cut,
+ * scipy connected_components(directed, weak)) on the nn[] array itself.
+ * Labels are numbered by smallest member index, exactly as scipy numbers them.
+ *   use_filter == 0: plain components of {i - nn[i]}.
+ *   use_filter != 0: a link survives iff weight * distance <= min_sim, weight 2 for mutual first
+ *     neighbours, 1 otherwise; rows sharing a first neighbour are linked iff their own distance
+ *     <= min_sim (needs unit rows + dist_nn in `dtype`).
+ * num_clust_out_dev receives the component count (device int32). */
+int slic_finch_components(const int32_t* nn_dev, int64_t n, int32_t use_filter, double min_sim,
+                          const void* unit_dev, int32_t d, int32_t dtype, const void* dist_nn_dev,
+                          int32_t* labels_out_dev, int32_t* num_clust_out_dev,
+                          slic_stream_t stream);
+
+/* clustering/finch.py:142-144: min_sim = max(orig_dist * adj) evaluated on the explicit link
+ * list (direct links, weight 2 when mutual; sibling pairs, weight 1).  float32 result on device. */
+int slic_finch_min_sim(const int32_t* nn_dev, int64_t n, const void* unit_dev, int32_t d,
+                       int32_t dtype, const void* dist_nn_dev, float* min_sim_out_dev,
+                       slic_stream_t stream);
+
+/* clustering/finch.py:85-94 (update_adj, used by req_numclust): the linked pair (direct link or
+ * sibling pair) with the smallest distance; pair_out_dev[0] < pair_out_dev[1]. */
+int slic_finch_closest_link(const int32_t* nn_dev, int64_t n, const void* unit_dev, int32_t d,
+                            int32_t dtype, const void* dist_nn_dev, int32_t* pair_out_dev,
+                            slic_stream_t stream);
+
+/* ---- K3: label composition + per-cluster means -------------------------------------------- */
+/* clustering/finch.py:74-79 (get_merge): out[i] = u[prev[i]] (prev == NULL: out = u). */
+int slic_compose_labels(const int32_t* prev_dev, const int32_t* u_dev, int64_t n,
+                        int32_t* out_dev, slic_stream_t stream);
+
+/* clustering/finch.py:58-71 (cool_mean): float64 mean of the float32 rows of every cluster,
+ * labels dense 0..num_clust-1.  Deterministic: rows are summed in ascending index order. */
+int slic_segmented_mean(const float* data_dev, const int32_t* labels_dev, int64_t n, int32_t d,
+                        int32_t num_clust, double* out_dev, slic_stream_t stream);
+
+/* ---- K4: label-equality masks and grouping ------------------------------------------------ */
+/* models/infoNCE.py:281-283, loss/triplet_loss.py:136-142,254-261,291-297:
+ * out[i, prepend + j] = (a[i] == b[j]) ^ negate as one byte per entry (torch.bool layout),
+ * row stride nb + prepend; with prepend_ones the first column is 1 (the UberNCE self column). */
+int slic_label_mask_u8(const int64_t* a_dev, int64_t na, const int64_t* b_dev, int64_t nb,
+                       int32_t prepend_ones, int32_t negate, uint8_t* out_dev,
+                       slic_stream_t stream);
+/* Same mask, bit-packed: word w of row i holds columns 32w..32w+31 (bit j = column 32w + j),
+ * row stride words_per_row = ceil(nb / 32) uint32. */
+int slic_label_mask_bits(const int64_t* a_dev, int64_t na, const int64_t* b_dev, int64_t nb,
+                         int32_t negate, uint32_t* out_dev, slic_stream_t stream);
+
+/* datasets/triplets_dataset.py:99-104 (label_to_indices) as CSR: order[] lists the rows of label
+ * 0, then label 1, ... (ascending row index inside a label, what np.where yields);
+ * offsets[c]..offsets[c+1] delimit label c.  Labels must lie in [0, num_labels). */
+int slic_group_by_label(const int32_t* labels_dev, int64_t n, int32_t num_labels,
+                        int32_t* order_out_dev, int32_t* offsets_out_dev, slic_stream_t stream);
+
+/* ---- host-buffer entry points (do their own H2D / D2H; block until the result is in place) -- */
+/* clustering/finch.py:22-29 for a float32/float64 host matrix: first neighbour + distance. */
+int slic_first_neighbors_host(const void* x_host, int64_t n, int32_t d, int32_t dtype,
+                              int32_t* nn_out_host, void* dist_out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLIC_B200_H */

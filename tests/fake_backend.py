@@ -1,0 +1,175 @@
+"""numpy stand-in for backend.CudaBackend - TEST INFRASTRUCTURE ONLY.
+
+Lets the host-side logic (the FINCH level loop and exit rules, fit_cluster, the evaluate / iic
+wrappers, the row-sharded search under gloo) run on a box without a GPU.  It is never imported by the
+package; the product path constructs CudaBackend, which raises without a CUDA device.
+Each method follows the documented contract of the C-ABI call it stands in for.
+"""
+import numpy as np
+import torch
+from scipy.sparse import csr_matrix
+from scipy.sparse.csgraph import connected_components
+
+
+def _np(t):
+    return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+
+
+class FakeBackend:
+    name = "fake-numpy"
+    device = torch.device("cpu")
+
+    def __init__(self):
+        self.calls = []
+
+    def to_device(self, array, dtype=None):
+        t = torch.as_tensor(array)
+        return (t.to(dtype) if dtype is not None else t).contiguous()
+
+    def empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype)
+
+    def to_host(self, t):
+        return t.cpu().numpy()
+
+    # K1
+    def normalize_rows(self, x, want_bf16=True):
+        a = _np(x)
+        nrm = np.sqrt(np.einsum("ij,ij->i", a.astype(np.float64), a.astype(np.float64))).astype(a.dtype)
+        nrm[nrm == 0] = 1
+        unit = torch.from_numpy(a / nrm[:, None])
+        return unit, (unit.to(torch.bfloat16) if want_bf16 else None)
+
+    def _sims(self, q, x):
+        return _np(q).astype(np.float64) @ _np(x).astype(np.float64).T
+
+    def nn_exact_top1(self, q_unit, x_unit, self_offset=-1, q_rows=None):
+        q = _np(q_unit) if q_rows is None else _np(q_unit)[_np(q_rows)]
+        s = self._sims(q, x_unit)
+        if self_offset >= 0:
+            rows = np.arange(len(q)) if q_rows is None else _np(q_rows)
+            s[np.arange(len(q)), rows + self_offset] = -np.inf
+        j = np.argmax(s, axis=1)
+        dt = _np(x_unit).dtype
+        d = np.clip(dt.type(1) - s[np.arange(len(q)), j].astype(dt), 0, 2).astype(dt)
+        return torch.from_numpy(j.astype(np.int32)), torch.from_numpy(d)
+
+    def nn_top1(self, q_unit, q_bf16, x_unit, x_bf16, self_offset=-1, eps=0.0):
+        return self.nn_exact_top1(q_unit, x_unit, self_offset)
+
+    def first_neighbors(self, x, row_range=None):
+        self.calls.append(("first_neighbors", tuple(x.shape), str(x.dtype), row_range))
+        unit, _ = self.normalize_rows(x, want_bf16=False)
+        r0, r1 = (0, x.shape[0]) if row_range is None else row_range
+        nn, d = self.nn_exact_top1(unit[r0:r1], unit, self_offset=r0)
+        return nn, d, unit
+
+    def distance_matrix(self, q, x, metric="cosine", same=False):
+        dt = _np(x).dtype
+        if metric == "cosine":
+            m = np.clip(dt.type(1) - self._sims(q, x).astype(dt), 0, 2).astype(dt)
+        else:
+            qa, xa = _np(q).astype(np.float64), _np(x).astype(np.float64)
+            d2 = (qa * qa).sum(1)[:, None] + (xa * xa).sum(1)[None, :] - 2 * qa @ xa.T
+            m = np.sqrt(np.maximum(d2, 0)).astype(dt)
+        if same:
+            np.fill_diagonal(m, 0)
+        return torch.from_numpy(m)
+
+    def rows_topk(self, mat, k):
+        m = _np(mat)
+        order = np.lexsort((np.broadcast_to(np.arange(m.shape[1]), m.shape), m), axis=1)[:, :k]
+        return torch.from_numpy(order.astype(np.int32)), torch.from_numpy(np.take_along_axis(m, order, 1))
+
+    def topk_cosine(self, q_unit, x_unit, k, self_offset=-1):
+        m = _np(self.distance_matrix(q_unit, x_unit))
+        if self_offset >= 0:
+            m[np.arange(m.shape[0]), np.arange(m.shape[0]) + self_offset] = np.inf
+        return self.rows_topk(torch.from_numpy(m), k)
+
+    def hit_at_k(self, topk_idx, q_labels, x_labels, ks):
+        idx, ql, xl = _np(topk_idx), _np(q_labels), _np(x_labels)
+        return torch.tensor([int(((xl[idx[:, :k]] == ql[:, None]).any(1)).sum()) for k in ks], dtype=torch.int32)
+
+    # K2
+    def _links(self, nn, unit=None):
+        nn = _np(nn).astype(np.int64)
+        n = len(nn)
+        i = np.arange(n)
+        rows, cols, kind = [i], [nn], [np.zeros(n, int)]
+        order = np.argsort(nn, kind="stable")
+        s = nn[order]
+        for h in np.unique(s):
+            mem = order[s == h]
+            if len(mem) > 1:
+                a, b = np.triu_indices(len(mem), 1)
+                rows.append(mem[a]); cols.append(mem[b]); kind.append(np.ones(len(a), int))
+        return np.concatenate(rows), np.concatenate(cols), np.concatenate(kind)
+
+    def _pair_dist(self, unit, r, c):
+        u = _np(unit)
+        s = np.einsum("ij,ij->i", u[r].astype(np.float64), u[c].astype(np.float64))
+        return np.clip(u.dtype.type(1) - s.astype(u.dtype), 0, 2).astype(u.dtype)
+
+    def components(self, nn, min_sim=None, unit=None, dist=None):
+        nnv = _np(nn).astype(np.int64)
+        n = len(nnv)
+        if min_sim is None:
+            r, c = np.arange(n), nnv
+        else:
+            r, c, kind = self._links(nn)
+            d = np.where(kind == 0, _np(dist)[r].astype(np.float64), self._pair_dist(unit, r, c).astype(np.float64))
+            w = np.where((kind == 0) & (nnv[c] == r), 2.0, 1.0)
+            keep = ~(d * w > float(min_sim)) & (r != c)
+            r, c = r[keep], c[keep]
+        g = csr_matrix((np.ones(len(r)), (r, c)), shape=(n, n))
+        num, lab = connected_components(g, directed=True, connection="weak")
+        return torch.from_numpy(lab.astype(np.int32)), int(num)
+
+    def min_sim(self, nn, unit, dist):
+        nnv = _np(nn).astype(np.int64)
+        r, c, kind = self._links(nn)
+        d = np.where(kind == 0, _np(dist)[r], self._pair_dist(unit, r, c)).astype(np.float32)
+        w = np.where((kind == 0) & (nnv[c] == r), 2.0, 1.0).astype(np.float32)
+        keep = r != c
+        return np.float32(np.max(d[keep] * w[keep]))
+
+    def closest_link(self, nn, unit, dist):
+        r, c, kind = self._links(nn)
+        d = np.where(kind == 0, _np(dist)[r].astype(np.float64), self._pair_dist(unit, r, c).astype(np.float64))
+        d[r == c] = np.inf
+        m = d.min()
+        cand = [(min(a, b), max(a, b)) for a, b in zip(r[d == m], c[d == m])]
+        i, j = min(cand)
+        return int(i), int(j)
+
+    # K3
+    def compose_labels(self, prev, u):
+        return u.clone() if prev is None else torch.from_numpy(_np(u)[_np(prev).astype(np.int64)])
+
+    def segmented_mean(self, data, labels, num_clust):
+        a, lab = _np(data).astype(np.float64), _np(labels).astype(np.int64)
+        out = np.zeros((num_clust, a.shape[1]))
+        np.add.at(out, lab, a)
+        return torch.from_numpy(out / np.bincount(lab, minlength=num_clust)[:, None])
+
+    # K4
+    def label_mask(self, a, b, prepend_ones=False, negate=False):
+        m = (_np(a)[:, None] == _np(b)[None, :]) != negate
+        if prepend_ones:
+            m = np.concatenate([np.ones((m.shape[0], 1), bool), m], 1)
+        return torch.from_numpy(m)
+
+    def label_mask_bits(self, a, b, negate=False):
+        m = (_np(a)[:, None] == _np(b)[None, :]) != negate
+        pad = (-m.shape[1]) % 32
+        m = np.pad(m, ((0, 0), (0, pad)))
+        words = np.packbits(m.reshape(m.shape[0], -1, 32), axis=-1, bitorder="little").view(np.uint32)[..., 0]
+        return torch.from_numpy(words.astype(np.int64).astype(np.uint32).view(np.int32))
+
+    def group_by_label(self, labels, num_labels):
+        lab = _np(labels).astype(np.int64)
+        order = np.argsort(lab, kind="stable").astype(np.int32)
+        off = np.zeros(num_labels + 1, np.int32)
+        np.cumsum(np.bincount(lab, minlength=num_labels), out=off[1:])
+        return torch.from_numpy(order), torch.from_numpy(off)

@@ -1,0 +1,52 @@
+"""The C-ABI library loads on a box without a GPU and exports every symbol include/slic_b200.h declares
+(no compute calls here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from video_similarity_search_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "slic_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(slic_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    names = _declared()
+    assert len(names) >= 20
+    lib = ctypes.CDLL(_lib.load().__dict__.get("_name", _lib.library_path()))
+    for n in names:
+        assert hasattr(lib, n), "libslic_b200.so does not export %s" % n
+    # the Python binding covers exactly the header
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_abi_version_and_error_string():
+    lib = _lib.load()
+    assert lib.slic_abi_version() == 1
+    assert isinstance(lib.slic_last_error(), bytes)
+
+
+def test_no_device_is_a_loud_error_not_a_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from video_similarity_search_b200.backend import CudaBackend
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        CudaBackend()
+    lib = _lib.load()
+    assert lib.slic_require_device() == -4          # SLIC_ERR_NO_DEVICE
+    assert b"no CPU fallback" in lib.slic_last_error()
+
+
+def test_argument_validation_needs_no_gpu():
+    lib = _lib.load()
+    assert lib.slic_normalize_rows(None, -1, 0, 0, None, None, None, 0, None) == -1
+    assert b"normalize_rows" in lib.slic_last_error()
+    assert lib.slic_rows_topk(None, 1, 10, 10, 0, 11, None, None, None) == -1

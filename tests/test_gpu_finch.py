@@ -1,0 +1,93 @@
+"""-m gpu: the drop-in entry points (FINCH, fit_cluster, evaluate / iic retrieval) on the CUDA path against
+the fixtures produced by the unmodified reference and against the oracle."""
+import io
+import os
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import finch_oracle as fo
+from oracle import retrieval_oracle as ro
+from tests.golden.make_golden import CASES, make_input
+from video_similarity_search_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def be():
+    from video_similarity_search_b200.backend import CudaBackend
+    return CudaBackend()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_finch_matches_reference_golden(be, golden_dir, name, monkeypatch):
+    """Every fixture of the unmodified reference, labels compared EXACTLY (scipy's numbering)."""
+    from video_similarity_search_b200.clustering import finch as fm
+    case = CASES[name]
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    x = make_input(case)
+    kw = dict(ensure_early_exit=case.get("ensure_early_exit", True), req_clust=case.get("req_clust"), verbose=False)
+    if case.get("use_initial_rank"):
+        kw["initial_rank"] = g["initial_rank"]
+    if case.get("flann_threshold") is not None:
+        monkeypatch.setattr(fm, "FLANN_THRESHOLD", case["flann_threshold"])
+    c, num_clust, req_c = fm.FINCH(x, backend=be, **kw)
+    assert num_clust == g["num_clust"].tolist()
+    assert c.dtype == np.int32 and np.array_equal(c, g["c"])
+    if g["req_c"].size:
+        assert np.array_equal(req_c, g["req_c"])
+    else:
+        assert req_c is None
+
+
+def test_finch_accepts_cuda_tensor_and_fit_cluster(be, golden_dir):
+    from video_similarity_search_b200.clustering import cluster_masks as cm
+    g = np.load(os.path.join(golden_dir, "gmm_3000x128.npz"))
+    x = make_input(CASES["gmm_3000x128"])
+    with redirect_stdout(io.StringIO()):
+        lab_cpu = cm.fit_cluster(torch.from_numpy(x), method="finch", finch_partition=1)
+        lab_gpu = cm.fit_cluster(torch.from_numpy(x).cuda(), method="finch", finch_partition=1)
+    assert np.array_equal(lab_cpu, g["c"][:, 1]) and np.array_equal(lab_gpu, g["c"][:, 1])
+
+
+def test_finch_above_flann_threshold_matches_oracle(be):
+    """N > 70 000: the reference needs pyflann; the oracle stands in with the exact search and the reference's
+    own control flow (no dense distances => no min_sim).  Partition must match it exactly."""
+    from video_similarity_search_b200.clustering.finch import FINCH
+    x = synth.gaussian_mixture(80000, 64, 120, 17)
+    c, num_clust, _ = FINCH(x, backend=be, verbose=False)
+    # oracle: exact first neighbours of the GPU are fed back as initial_rank (same mode: no min_sim), so
+    # levels >= 1 are an independent float64 CPU computation
+    nn, _, _ = be.first_neighbors(be.to_device(x))
+    enn, _, gap = fo.first_neighbors_blocked(x, rows=np.arange(0, 80000, 40))
+    clear = gap > 2e-6
+    assert np.array_equal(nn.cpu().numpy()[::40][clear], enn[clear])
+    co, no, _ = fo.finch(x, initial_rank=nn.cpu().numpy())
+    assert num_clust == no and np.array_equal(c, co)
+
+
+def test_retrieval_c2_matches_oracle(be):
+    """BASELINE config 2: 3 783 x 9 537 x 512, k in {1,5,10,20,50}: exact hit counts; top-k sets on rows whose
+    k/k+1 boundary gap exceeds the margin; ordered lists on rows without adjacent near-ties."""
+    from video_similarity_search_b200 import evaluate as ev
+    from video_similarity_search_b200 import iic_retrieve_clips as iic
+    for dtype, margin in ((np.float32, 2e-6), (np.float64, 1e-12)):
+        xtr, ytr, xte, yte = synth.c2_retrieval(dtype)
+        ks = [1, 5, 10, 20, 50]
+        exp, order, d = ro.topk_retrieval_counts(xtr[:, None, :], ytr[:, None], xte[:, None, :], yte[:, None], ks)
+        got, idx, dist = iic.topk_retrieval_arrays(xtr, ytr, xte, yte, ks, backend=be, return_neighbors=True)
+        assert got == exp
+        ds = np.take_along_axis(d, order[:, :51], 1)
+        for k in ks:
+            ok = (ds[:, k] - ds[:, k - 1]) > margin
+            assert ok.mean() > 0.99
+            assert np.array_equal(np.sort(idx[ok, :k], 1), np.sort(order[ok, :k], 1))
+        clean = (np.diff(ds, axis=1) > margin).all(1)
+        assert np.array_equal(idx[clean], order[clean, :50])
+        np.testing.assert_allclose(dist, ds[:, :50], rtol=1e-5, atol=2e-6 if dtype == np.float32 else 1e-13)
+        dm = ev.get_distance_matrix(xte, xtr, backend=be)
+        acc = ev.get_topk_acc(dm, yte.tolist(), ytr.tolist())
+        np.testing.assert_array_equal(acc, ro.topk_acc(d, yte.tolist(), ytr.tolist()))

@@ -1,0 +1,252 @@
+"""-m gpu: every CUDA kernel through the C ABI against the oracle (bit-exact for integer / index work,
+stated tolerances for floating point)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import finch_oracle as fo
+from oracle import masks_oracle as mo
+from oracle import retrieval_oracle as ro
+from tests.fake_backend import FakeBackend
+from tests.golden.make_golden import CASES, make_input
+from video_similarity_search_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+TIE_MARGIN_F32 = 2e-6     # rows whose top-1/top-2 cosine-distance gap is below this are
+TIE_MARGIN_F64 = 1e-12    # "ties" (float32 GEMM order decides them); they are counted, never ignored silently
+
+
+@pytest.fixture(scope="module")
+def be():
+    from video_similarity_search_b200.backend import CudaBackend
+    return CudaBackend()
+
+
+def dev(be, a, dtype=None):
+    return be.to_device(a, dtype)
+
+
+# ---------------------------------------------------------------------------------------------------
+# integer primitives through their public users
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,c", [(1, 1), (33, 5), (5000, 700), (4097, 4097), (300000, 21436), (100000, 3),
+                                 (70000, 70000)])
+def test_group_by_label_bit_exact(be, n, c):
+    rng = np.random.default_rng(n + c)
+    lab = rng.integers(0, c, n).astype(np.int32)
+    order, off = be.group_by_label(dev(be, lab), c)
+    eo, eoff = mo.group_by_label(lab, c)
+    assert np.array_equal(order.cpu().numpy(), eo)
+    assert np.array_equal(off.cpu().numpy(), eoff)
+
+
+@pytest.mark.parametrize("n", [1, 2, 1000, 9537, 240000])
+def test_components_plain_matches_scipy_numbering(be, n):
+    rng = np.random.default_rng(n)
+    nn = rng.integers(0, max(n, 1), n).astype(np.int32)
+    lab, cnt = be.components(dev(be, nn))
+    elab, ecnt = FakeBackend().components(torch.from_numpy(nn))
+    assert cnt == ecnt and np.array_equal(lab.cpu().numpy(), elab.numpy())
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_components_filtered_and_min_sim(be, dtype):
+    x = synth.gaussian_mixture(1500, 96, 20, 3).astype(dtype)
+    fb = FakeBackend()
+    nn_f, d_f, unit_f = fb.first_neighbors(torch.from_numpy(x))
+    xd = dev(be, x)
+    nn, d, unit = be.first_neighbors(xd)
+    assert np.array_equal(nn.cpu().numpy(), nn_f.numpy())
+    ms = be.min_sim(nn, unit, d)
+    ms_f = fb.min_sim(nn_f, unit_f, d_f)
+    assert abs(float(ms) - float(ms_f)) <= 1e-6 * float(ms_f)
+    for frac in (0.3, 0.6, 1.0):
+        thr = float(ms_f) * frac
+        lab, cnt = be.components(nn, min_sim=thr, unit=unit, dist=d)
+        elab, ecnt = fb.components(nn_f, min_sim=thr, unit=unit_f, dist=d_f)
+        assert cnt == ecnt and np.array_equal(lab.cpu().numpy(), elab.numpy()), frac
+    i, j = be.closest_link(nn, unit, d)
+    assert (i, j) == fb.closest_link(nn_f, unit_f, d_f)
+
+
+def test_compose_and_segmented_mean(be):
+    x = synth.gaussian_mixture(20000, 512, 40, 5)
+    rng = np.random.default_rng(0)
+    for c in (1, 7, 3000):
+        lab = np.unique(rng.integers(0, c, len(x)), return_inverse=True)[1].astype(np.int32)
+        k = int(lab.max()) + 1
+        m = be.segmented_mean(dev(be, x), dev(be, lab), k).cpu().numpy()
+        ref = fo.cluster_means(x, lab)
+        assert m.dtype == np.float64 and m.shape == ref.shape
+        np.testing.assert_allclose(m, ref, rtol=1e-5, atol=1e-12)          # north_star tolerance: 1e-5 relative
+        assert np.max(np.abs(m - ref)) < 1e-11                             # and in fact float64-exact
+    prev = rng.integers(0, 50, 1000).astype(np.int32)
+    u = rng.integers(0, 9, 50).astype(np.int32)
+    assert np.array_equal(be.compose_labels(dev(be, prev), dev(be, u)).cpu().numpy(), u[prev])
+    xo = synth.gaussian_mixture(333, 77, 5, 1)                               # odd D: scalar path
+    lab = (np.arange(333) % 4).astype(np.int32)
+    np.testing.assert_allclose(be.segmented_mean(dev(be, xo), dev(be, lab), 4).cpu().numpy(),
+                               fo.cluster_means(xo, lab), rtol=0, atol=1e-11)
+
+
+def test_label_masks(be):
+    rng = np.random.default_rng(4)
+    for (na, nb) in [(1, 1), (37, 301), (64, 64), (1024, 65536), (5, 4099)]:
+        a, b = rng.integers(0, 97, na), rng.integers(0, 97, nb)
+        ad, bd = dev(be, a), dev(be, b)
+        full = a[:, None] == b[None, :]
+        assert np.array_equal(be.label_mask(ad, bd).cpu().numpy(), full)
+        assert np.array_equal(be.label_mask(ad, bd, negate=True).cpu().numpy(), ~full)
+        assert np.array_equal(be.label_mask(ad, bd, prepend_ones=True).cpu().numpy(), mo.queue_positive_mask(a, b))
+        bits = be.label_mask_bits(ad, bd).cpu().numpy().view(np.uint32)
+        unpacked = np.unpackbits(bits.view(np.uint8), axis=1, bitorder="little")[:, :nb].astype(bool)
+        assert np.array_equal(unpacked, full)
+
+
+# ---------------------------------------------------------------------------------------------------
+# K1
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_normalize_rows(be, dtype):
+    x = synth.gaussian_mixture(1000, 200, 9, 2).astype(dtype)
+    x[17] = 0                                                    # zero row: norm replaced by 1
+    unit, ub = be.normalize_rows(dev(be, x))
+    ref = fo._unit_rows(x)
+    tol = 3e-7 if dtype == np.float32 else 1e-15
+    np.testing.assert_allclose(unit.cpu().numpy(), ref, rtol=tol, atol=tol)
+    assert ub.shape == (1000, 256) and torch.all(ub[:, 200:] == 0)
+    np.testing.assert_allclose(ub[:, :200].float().cpu().numpy(), ref, rtol=2 ** -8, atol=1e-30)
+
+
+def _check_nn(nn, d, x, margin):
+    """nn/d against the oracle's blocked exact search; rows inside the tie margin are excluded and counted."""
+    enn, ed, gap = fo.first_neighbors_blocked(x)
+    clear = gap > margin
+    assert clear.mean() > 0.99
+    assert np.array_equal(nn[clear], enn[clear])
+    np.testing.assert_allclose(d[clear], ed[clear], rtol=1e-5, atol=1e-6)
+    return int((~clear).sum())
+
+
+@pytest.mark.parametrize("name", ["gmm_1200x64", "iid_600x32", "gmm_777x200_odd", "gmm_3000x128"])
+def test_exact_first_neighbors_vs_reference_golden(be, golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    x = make_input(CASES[name])
+    unit, _ = be.normalize_rows(dev(be, x), want_bf16=False)
+    nn, d = be.nn_exact_top1(unit, unit, self_offset=0)
+    _check_nn(nn.cpu().numpy(), d.cpu().numpy(), x, TIE_MARGIN_F32)
+    _, _, gap = fo.first_neighbors_blocked(x)
+    clear = gap > TIE_MARGIN_F32
+    assert np.array_equal(nn.cpu().numpy()[clear], g["nn_level0"][clear])      # the reference's own argmin
+
+
+@pytest.mark.parametrize("nq,n,d", [(128, 256, 64), (100, 300, 64), (257, 1000, 128), (384, 2100, 512), (130, 513, 200)])
+def test_tensor_core_screen_scores(be, nq, n, d):
+    """Raw tcgen05 scores element by element against a float32 product of the same bf16 inputs."""
+    rng = np.random.default_rng(nq * n)
+    dp = (d + 63) // 64 * 64
+    q = torch.zeros((nq, dp), dtype=torch.bfloat16, device=be.device)
+    x = torch.zeros((n, dp), dtype=torch.bfloat16, device=be.device)
+    q[:, :d] = torch.from_numpy(rng.standard_normal((nq, d)).astype(np.float32) / np.sqrt(d)).to(be.device)
+    x[:, :d] = torch.from_numpy(rng.standard_normal((n, d)).astype(np.float32) / np.sqrt(d)).to(be.device)
+    got = be.screen_scores_debug(q, x).cpu().numpy()
+    ref = q.float().cpu().numpy().astype(np.float64) @ x.float().cpu().numpy().astype(np.float64).T
+    np.testing.assert_allclose(got, ref, rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n,d,k,seed", [(3000, 128, 30, 7), (9537, 512, 101, 0), (5000, 200, 10, 9)])
+def test_screened_first_neighbors_equal_exact(be, dtype, n, d, k, seed):
+    x = synth.gaussian_mixture(n, d, k, seed).astype(dtype)
+    unit, ub = be.normalize_rows(dev(be, x))
+    nn_e, d_e = be.nn_exact_top1(unit, unit, self_offset=0)
+    nn_s, d_s = be.nn_top1(unit, ub, unit, ub, self_offset=0)
+    assert torch.equal(nn_e, nn_s)                                # same float64-accumulated argmax, no margin needed
+    assert torch.equal(d_e, d_s)
+    stats = be.last_stats.cpu().numpy()
+    assert stats[1] == 0                                          # no row needed the exact finisher
+    # row-sharded form (what each rank of the multi-GPU path runs)
+    r0, r1 = n // 3, n // 3 + 1000
+    nn_p, _ = be.nn_top1(unit[r0:r1], ub[r0:r1], unit, ub, self_offset=r0)
+    assert torch.equal(nn_p, nn_e[r0:r1])
+
+
+def test_screen_overflow_rows_are_finished_exactly(be):
+    """80 identical rows: more than 32 columns tie at the top, the candidate list overflows and the exact
+    kernel must finish those rows (lowest index wins, as np.argmin does)."""
+    x = synth.gaussian_mixture(4000, 64, 8, 21)
+    x[100:180] = x[100]
+    unit, ub = be.normalize_rows(dev(be, x))
+    nn_e, _ = be.nn_exact_top1(unit, unit, self_offset=0)
+    nn_s, _ = be.nn_top1(unit, ub, unit, ub, self_offset=0)
+    assert torch.equal(nn_e, nn_s)
+    assert int(be.last_stats[1]) >= 80
+    got = nn_s.cpu().numpy()
+    assert got[100] == 101 and np.all(got[101:180] == 100)
+
+
+def test_c1_first_neighbors_vs_reference_golden(be, golden_dir):
+    """BASELINE config 1 through the tensor-core path against the reference's own argmin."""
+    g = np.load(os.path.join(golden_dir, "c1_9537x512.npz"))
+    x = synth.config("C1")
+    nn, d, _ = be.first_neighbors(dev(be, x))
+    ties = _check_nn(nn.cpu().numpy(), d.cpu().numpy(), x, TIE_MARGIN_F32)
+    _, _, gap = fo.first_neighbors_blocked(x)
+    clear = gap > TIE_MARGIN_F32
+    assert np.array_equal(nn.cpu().numpy()[clear], g["nn_level0"][clear])
+    assert ties <= 10
+
+
+# ---------------------------------------------------------------------------------------------------
+# retrieval
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_distance_matrix_and_topk(be, dtype):
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((1500, 96)).astype(dtype)
+    q = rng.standard_normal((333, 96)).astype(dtype)
+    ux, _ = be.normalize_rows(dev(be, x), want_bf16=False)
+    uq, _ = be.normalize_rows(dev(be, q), want_bf16=False)
+    ref = ro.distance_matrix(q, x)
+    got = be.distance_matrix(uq, ux).cpu().numpy()
+    assert got.dtype == ref.dtype
+    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=2e-6 if dtype == np.float32 else 1e-13)
+    refe = ro.distance_matrix(q, x, "euclidean")
+    gote = be.distance_matrix(dev(be, q), dev(be, x), metric="euclidean").cpu().numpy()
+    np.testing.assert_allclose(gote, refe, rtol=1e-5, atol=1e-5 if dtype == np.float32 else 1e-12)
+    # rows_topk is an exact integer/selection kernel: check it on the SAME matrix the oracle sees
+    for k in (1, 5, 50, 333):
+        idx, val = be.rows_topk(dev(be, ref), k)
+        order = np.lexsort((np.broadcast_to(np.arange(ref.shape[1]), ref.shape), ref), axis=1)[:, :k]
+        assert np.array_equal(idx.cpu().numpy(), order)
+        assert np.array_equal(val.cpu().numpy(), np.take_along_axis(ref, order, 1))
+    # duplicate distances at the boundary: lowest columns win
+    tie = np.ones((3, 700), dtype=dtype)
+    tie[:, 650:] = 0.5
+    idx, _ = be.rows_topk(dev(be, tie), 60)
+    assert np.array_equal(idx.cpu().numpy()[0], np.concatenate([np.arange(650, 700), np.arange(0, 10)]))
+
+
+def test_hit_at_k(be):
+    rng = np.random.default_rng(6)
+    idx = rng.integers(0, 500, (200, 50)).astype(np.int32)
+    ql, xl = rng.integers(0, 30, 200), rng.integers(0, 30, 500)
+    ks = [1, 5, 10, 20, 50]
+    got = be.hit_at_k(dev(be, idx), dev(be, ql), dev(be, xl), ks).cpu().numpy()
+    exp = [int((xl[idx[:, :k]] == ql[:, None]).any(1).sum()) for k in ks]
+    assert got.tolist() == exp
+
+
+def test_host_buffer_entry_point(be):
+    """slic_first_neighbors_host: the call a reference-side binding makes with numpy arrays."""
+    import ctypes
+    from video_similarity_search_b200 import _lib
+    x = synth.gaussian_mixture(3000, 128, 30, 7)
+    nn = np.empty(3000, dtype=np.int32)
+    d = np.empty(3000, dtype=np.float32)
+    _lib.call("slic_first_neighbors_host", x.ctypes.data_as(ctypes.c_void_p), 3000, 128, 0,
+              nn.ctypes.data_as(ctypes.c_void_p), d.ctypes.data_as(ctypes.c_void_p))
+    _check_nn(nn, d, x, TIE_MARGIN_F32)

@@ -1,0 +1,214 @@
+"""Device backend: thin torch-tensor wrappers over the C ABI (include/slic_b200.h).
+
+torch supplies device memory and the current stream; every computation is a call into
+libslic_b200.so.  There is no CPU implementation here - without a CUDA device `CudaBackend()`
+raises.  (tests/fake_backend.py provides a numpy stand-in with the same method names so that the
+host logic in clustering/finch.py can be exercised on a box without a GPU; it is test
+infrastructure and is never selected by the product code.)
+"""
+import torch
+
+from . import _lib
+
+_DT = {torch.float32: _lib.SLIC_F32, torch.float64: _lib.SLIC_F64}
+
+# below this many rows the tensor-core screen is pure launch overhead: use the exact kernel
+SCREEN_MIN_ROWS = 2048
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def d_pad_of(d):
+    return (d + 63) // 64 * 64
+
+
+class CudaBackend:
+    name = "cuda"
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("video_similarity_search_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.lib = _lib.load()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.slic_require_device(), "slic_require_device")
+        self.last_stats = None
+
+    # -- plumbing ------------------------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def to_device(self, array, dtype=None):
+        t = torch.as_tensor(array)
+        if dtype is not None and t.dtype != dtype:
+            t = t.to(dtype)
+        return t.to(self.device, non_blocking=True).contiguous()
+
+    def empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def to_host(self, t):
+        return t.cpu().numpy()
+
+    # -- K1 --------------------------------------------------------------------------------------
+    def normalize_rows(self, x, want_bf16=True):
+        """-> (unit [n,d] same dtype, unit_bf16 [n,d_pad] or None)."""
+        n, d = x.shape
+        unit = torch.empty_like(x)
+        dp = d_pad_of(d)
+        ub = torch.empty((n, dp), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+        _lib.call("slic_normalize_rows", _p(x), n, d, _DT[x.dtype], _p(unit), None, _p(ub), dp, self._stream())
+        return unit, ub
+
+    def nn_exact_top1(self, q_unit, x_unit, self_offset=-1, q_rows=None):
+        nq = q_unit.shape[0] if q_rows is None else q_rows.shape[0]
+        n, d = x_unit.shape
+        idx = torch.empty(nq, dtype=torch.int32, device=x_unit.device)
+        dist = torch.empty(nq, dtype=x_unit.dtype, device=x_unit.device)
+        _lib.call("slic_nn_exact_top1", _p(q_unit), _p(q_rows), nq, _p(x_unit), n, d, _DT[x_unit.dtype],
+                  self_offset, _p(idx), _p(dist), self._stream())
+        return idx, dist
+
+    def nn_top1(self, q_unit, q_bf16, x_unit, x_bf16, self_offset=-1, eps=0.0):
+        """tcgen05 screen + exact re-rank (slic_nn_top1)."""
+        nq = q_unit.shape[0]
+        n, d = x_unit.shape
+        idx = torch.empty(nq, dtype=torch.int32, device=x_unit.device)
+        dist = torch.empty(nq, dtype=x_unit.dtype, device=x_unit.device)
+        stats = torch.zeros(4, dtype=torch.int32, device=x_unit.device)
+        _lib.call("slic_nn_top1", _p(q_unit), _p(q_bf16), nq, _p(x_unit), _p(x_bf16), n, d, x_bf16.shape[1],
+                  _DT[x_unit.dtype], self_offset, float(eps), _p(idx), _p(dist), _p(stats), self._stream())
+        self.last_stats = stats
+        return idx, dist
+
+    def first_neighbors(self, x, row_range=None):
+        """First neighbour of every row of x (or of rows [r0, r1)) among all rows of x, self excluded.
+        -> (nn int32, dist x.dtype, unit).  Chooses the screen for large inputs, the exact kernel below."""
+        n = x.shape[0]
+        use_screen = n >= SCREEN_MIN_ROWS
+        unit, ub = self.normalize_rows(x, want_bf16=use_screen)
+        r0, r1 = (0, n) if row_range is None else row_range
+        if r1 <= r0:
+            return (torch.empty(0, dtype=torch.int32, device=x.device), torch.empty(0, dtype=x.dtype, device=x.device),
+                    unit)
+        if use_screen:
+            nn, dist = self.nn_top1(unit[r0:r1], ub[r0:r1], unit, ub, self_offset=r0)
+        else:
+            nn, dist = self.nn_exact_top1(unit[r0:r1], unit, self_offset=r0)
+        return nn, dist, unit
+
+    def screen_scores_debug(self, q_bf16, x_bf16):
+        nq, n = q_bf16.shape[0], x_bf16.shape[0]
+        out = torch.zeros((nq, n), dtype=torch.float32, device=x_bf16.device)
+        _lib.call("slic_screen_scores_debug", _p(q_bf16), nq, _p(x_bf16), n, x_bf16.shape[1], _p(out), self._stream())
+        return out
+
+    def distance_matrix(self, q, x, metric="cosine", same=False):
+        nq, d = q.shape
+        n = x.shape[0]
+        out = torch.empty((nq, n), dtype=x.dtype, device=x.device)
+        m = _lib.SLIC_METRIC_COSINE if metric == "cosine" else _lib.SLIC_METRIC_EUCLIDEAN
+        _lib.call("slic_distance_matrix", _p(q), nq, _p(x), n, d, _DT[x.dtype], m, int(same), _p(out), n, self._stream())
+        return out
+
+    def rows_topk(self, mat, k):
+        nq, n = mat.shape
+        idx = torch.empty((nq, k), dtype=torch.int32, device=mat.device)
+        val = torch.empty((nq, k), dtype=mat.dtype, device=mat.device)
+        _lib.call("slic_rows_topk", _p(mat), nq, n, mat.stride(0), _DT[mat.dtype], k, _p(idx), _p(val), self._stream())
+        return idx, val
+
+    def topk_cosine(self, q_unit, x_unit, k, self_offset=-1):
+        nq, d = q_unit.shape
+        n = x_unit.shape[0]
+        idx = torch.empty((nq, k), dtype=torch.int32, device=x_unit.device)
+        val = torch.empty((nq, k), dtype=x_unit.dtype, device=x_unit.device)
+        _lib.call("slic_topk_cosine", _p(q_unit), nq, _p(x_unit), n, d, _DT[x_unit.dtype], k, self_offset, _p(idx),
+                  _p(val), self._stream())
+        return idx, val
+
+    def hit_at_k(self, topk_idx, q_labels, x_labels, ks):
+        ks_t = torch.tensor(list(ks), dtype=torch.int32, device=topk_idx.device)
+        hits = torch.empty(len(ks), dtype=torch.int32, device=topk_idx.device)
+        _lib.call("slic_hit_at_k", _p(topk_idx), topk_idx.shape[0], topk_idx.stride(0), _p(q_labels), _p(x_labels),
+                  _p(ks_t), len(ks), _p(hits), self._stream())
+        return hits
+
+    # -- K2 --------------------------------------------------------------------------------------
+    def components(self, nn, min_sim=None, unit=None, dist=None):
+        """-> (labels int32 [n], num_clust python int).  Synchronises to read the count."""
+        n = nn.shape[0]
+        labels = torch.empty(n, dtype=torch.int32, device=nn.device)
+        count = torch.empty(1, dtype=torch.int32, device=nn.device)
+        use_filter = min_sim is not None
+        d = unit.shape[1] if use_filter else 0
+        dt = _DT[unit.dtype] if use_filter else 0
+        _lib.call("slic_finch_components", _p(nn), n, int(use_filter), float(min_sim) if use_filter else 0.0,
+                  _p(unit) if use_filter else None, d, dt, _p(dist) if use_filter else None, _p(labels), _p(count),
+                  self._stream())
+        return labels, int(count.item())
+
+    def min_sim(self, nn, unit, dist):
+        out = torch.empty(1, dtype=torch.float32, device=nn.device)
+        _lib.call("slic_finch_min_sim", _p(nn), nn.shape[0], _p(unit), unit.shape[1], _DT[unit.dtype], _p(dist), _p(out),
+                  self._stream())
+        return out.cpu().numpy()[0]          # np.float32 scalar, as the reference holds it
+
+    def closest_link(self, nn, unit, dist):
+        out = torch.empty(2, dtype=torch.int32, device=nn.device)
+        _lib.call("slic_finch_closest_link", _p(nn), nn.shape[0], _p(unit), unit.shape[1], _DT[unit.dtype], _p(dist),
+                  _p(out), self._stream())
+        i, j = out.tolist()
+        return i, j
+
+    # -- K3 --------------------------------------------------------------------------------------
+    def compose_labels(self, prev, u):
+        n = u.shape[0] if prev is None else prev.shape[0]
+        out = torch.empty(n, dtype=torch.int32, device=u.device)
+        _lib.call("slic_compose_labels", _p(prev), _p(u), n, _p(out), self._stream())
+        return out
+
+    def segmented_mean(self, data, labels, num_clust):
+        n, d = data.shape
+        out = torch.empty((num_clust, d), dtype=torch.float64, device=data.device)
+        _lib.call("slic_segmented_mean", _p(data), _p(labels), n, d, num_clust, _p(out), self._stream())
+        return out
+
+    # -- K4 --------------------------------------------------------------------------------------
+    def label_mask(self, a, b, prepend_ones=False, negate=False):
+        na, nb = a.shape[0], b.shape[0]
+        out = torch.empty((na, nb + int(prepend_ones)), dtype=torch.bool, device=a.device)
+        _lib.call("slic_label_mask_u8", _p(a), na, _p(b), nb, int(prepend_ones), int(negate), _p(out), self._stream())
+        return out
+
+    def label_mask_bits(self, a, b, negate=False):
+        na, nb = a.shape[0], b.shape[0]
+        out = torch.zeros((na, (nb + 31) // 32), dtype=torch.int32, device=a.device)
+        _lib.call("slic_label_mask_bits", _p(a), na, _p(b), nb, int(negate), _p(out), self._stream())
+        return out
+
+    def group_by_label(self, labels, num_labels):
+        n = labels.shape[0]
+        order = torch.empty(n, dtype=torch.int32, device=labels.device)
+        offsets = torch.empty(num_labels + 1, dtype=torch.int32, device=labels.device)
+        _lib.call("slic_group_by_label", _p(labels), n, num_labels, _p(order), _p(offsets), self._stream())
+        return order, offsets
+
+
+_default = None
+
+
+def default_backend():
+    """The process-wide CUDA backend (created on first use; raises without a GPU)."""
+    global _default
+    if _default is None:
+        _default = CudaBackend()
+    return _default
+
+
+def set_default_backend(backend):
+    """Tests only: install a stand-in backend."""
+    global _default
+    _default = backend

@@ -1,0 +1,148 @@
+"""FINCH first-neighbour clustering on B200 - drop-in for /root/reference/clustering/finch.py.
+
+Same call signature and return values as the reference's FINCH (finch.py:108-178):
+
+    c, num_clust, req_c = FINCH(data, initial_rank=None, req_clust=None, distance='cosine',
+                                ensure_early_exit=True, verbose=True)
+
+What runs where
+  host (this file): the level loop and its exit rules, exactly as finch.py:134-176 has them.
+  device (libslic_b200.so through backend.CudaBackend):
+    a2  first neighbours   slic_normalize_rows + slic_nn_top1 (tcgen05 bf16 screen, exact re-rank in
+                           float32 at level 0 / float64 at levels >= 1) or slic_nn_exact_top1 (small n)
+    a4  components         slic_finch_components (union-find on nn[], optional min_sim cut)
+    a5/a6 merge + means    slic_compose_labels, slic_segmented_mean (float64)
+    a7  min_sim            slic_finch_min_sim
+    a8  req_clust          slic_finch_closest_link + the calls above
+There is no CPU path: without a CUDA device the backend constructor raises.
+
+Differences from the reference, all deliberate:
+  * N > 70 000 does not need pyflann: the exact cosine first neighbour is computed at every size.
+    The reference's control flow for that case is kept - no dense distances => no min_sim filter
+    (finch.py:30-38,142-144).
+  * only distance='cosine' (the one value any caller passes) is implemented.
+"""
+import numpy as np
+import torch
+
+from .. import backend as _backend
+
+FLANN_THRESHOLD = 70000  # finch.py:19 - above it the reference has no dense distance matrix
+
+
+class _Level:
+    """Result of the clust_rank step (finch.py:22-47) for one level, kept on the device."""
+
+    def __init__(self, nn, dist, unit, dense):
+        self.nn, self.dist, self.unit, self.dense = nn, dist, unit, dense
+
+
+def _rank(be, mat, initial_rank, first_neighbors=None):
+    """finch.py:22-38.  `dense` mirrors `len(orig_dist) != 0` in the reference."""
+    n = mat.shape[0]
+    if initial_rank is not None:
+        nn = be.to_device(np.asarray(initial_rank).astype(np.int32, copy=False), torch.int32)
+        if nn.shape[0] != n:
+            raise ValueError("initial_rank must have one entry per row of data")
+        return _Level(nn, None, None, False)
+    if n == 1:
+        return _Level(torch.zeros(1, dtype=torch.int32, device=mat.device), torch.zeros(1, dtype=mat.dtype,
+                      device=mat.device), mat, n <= FLANN_THRESHOLD)
+    if first_neighbors is not None:
+        nn, dist, unit = first_neighbors(mat)
+    else:
+        nn, dist, unit = be.first_neighbors(mat)
+    return _Level(nn, dist, unit, n <= FLANN_THRESHOLD)
+
+
+def _clust(be, lvl, min_sim):
+    """finch.py:50-55."""
+    if min_sim is not None and lvl.dense:
+        return be.components(lvl.nn, min_sim=float(min_sim), unit=lvl.unit, dist=lvl.dist)
+    return be.components(lvl.nn)
+
+
+def _merge(be, prev, u, data, num_clust):
+    """finch.py:74-82: compose the labels, recompute the float64 centroids of the ORIGINAL rows."""
+    cur = be.compose_labels(prev, u)
+    return cur, be.segmented_mean(data, cur, num_clust)
+
+
+def _req_numclust(be, labels, n_labels, data, req_clust):
+    """finch.py:97-105: merge the closest linked pair until req_clust clusters remain."""
+    cur, mat = _merge(be, None, labels, data, n_labels)
+    for _ in range(n_labels - req_clust):
+        n = mat.shape[0]
+        lvl = _rank(be, mat, None)
+        i, j = be.closest_link(lvl.nn, lvl.unit, lvl.dist)          # update_adj, finch.py:85-94
+        link = torch.arange(n, dtype=torch.int32, device=mat.device)
+        link[j] = i                                                 # the single surviving link
+        u, cnt = be.components(link)
+        cur, mat = _merge(be, cur, u, data, cnt)
+    return cur
+
+
+def FINCH(data, initial_rank=None, req_clust=None, distance='cosine', ensure_early_exit=True, verbose=True,
+          backend=None, first_neighbors=None):
+    """FINCH clustering (reference: clustering/finch.py:108-178).
+
+    :param data: [N, D] features in rows - numpy array or torch tensor (CPU or CUDA), any float dtype;
+                 cast to float32 as the reference does (finch.py:131).
+    :param initial_rank: optional [N] first-neighbour indices (skips the level-0 search and, as in the
+                 reference, disables the min_sim filter).
+    :param req_clust: optional exact number of clusters to refine to.
+    :param distance: only 'cosine'.
+    :param ensure_early_exit: apply the min_sim purity filter when level 0 had dense distances.
+    :param verbose: print 'Partition k: n clusters' lines like the reference.
+    :param backend: device backend (default: the process-wide CudaBackend).
+    :param first_neighbors: optional callable mat -> (nn, dist, unit) overriding the level-0 search
+                 (the multi-GPU row-sharded search in sharded.py plugs in here).
+    :return: c int32 [N, P] (numpy), num_clust list[int], req_c int32 [N] or None.
+    """
+    if distance != 'cosine':
+        raise NotImplementedError("only distance='cosine' is implemented (the value every reference caller passes)")
+    be = backend if backend is not None else _backend.default_backend()
+    if isinstance(data, torch.Tensor):
+        data = data.detach()
+    data = be.to_device(data, torch.float32)                        # finch.py:131
+    if data.dim() != 2 or data.shape[0] < 1:
+        raise ValueError("data must be a non-empty [N, D] matrix")
+
+    min_sim = None
+    lvl = _rank(be, data, initial_rank, first_neighbors)            # finch.py:134
+    group, n0 = _clust(be, lvl, None)                               # finch.py:136
+    c_, mat = _merge(be, None, group, data, n0)                     # finch.py:137
+    if verbose:
+        print('Partition 0: {} clusters'.format(n0))
+    if ensure_early_exit and lvl.dense and lvl.dist is not None and data.shape[0] > 1:
+        min_sim = be.min_sim(lvl.nn, lvl.unit, lvl.dist)            # finch.py:142-144
+
+    columns = [c_]
+    num_clust = [n0]
+    exit_clust = 2
+    k = 1
+    while exit_clust > 1:                                           # finch.py:151
+        lvl = _rank(be, mat, None)
+        u, cur = _clust(be, lvl, min_sim)
+        c_, mat = _merge(be, c_, u, data, cur)
+        num_clust.append(cur)
+        columns.append(c_)
+        exit_clust = num_clust[-2] - cur
+        if cur == 1 or exit_clust < 1:                              # finch.py:160-163
+            num_clust = num_clust[:-1]
+            columns = columns[:-1]
+            break
+        if verbose:
+            print('Partition {}: {} clusters'.format(k, num_clust[k]))
+        k += 1
+
+    req_c = None
+    if req_clust is not None:                                       # finch.py:169-176
+        if req_clust not in num_clust:
+            ind = [i for i, v in enumerate(num_clust) if v >= req_clust]
+            req_c = be.to_host(_req_numclust(be, columns[ind[-1]], num_clust[ind[-1]], data, req_clust))
+        else:
+            req_c = be.to_host(columns[num_clust.index(req_clust)])
+
+    c = be.to_host(torch.stack(columns, dim=1))
+    return c, num_clust, req_c

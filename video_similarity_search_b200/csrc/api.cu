@@ -1,0 +1,58 @@
+// Library-level entry points of the C ABI: error state, version, device check.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace slic {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int num_sms() {
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+            cached = sms;
+        else
+            return 148;
+    }
+    return cached;
+}
+
+}  // namespace slic
+
+extern "C" {
+
+int slic_abi_version(void) { return SLIC_ABI_VERSION; }
+
+const char* slic_last_error(void) { return slic::g_error; }
+
+int slic_require_device(void) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        slic::set_error("no CUDA device visible (%s): slic_b200 has no CPU fallback",
+                        e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        cudaGetLastError();
+        return SLIC_ERR_NO_DEVICE;
+    }
+    int dev = 0, major = 0;
+    SLIC_CUDA_OK(cudaGetDevice(&dev));
+    SLIC_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) {
+        slic::set_error("device %d has compute capability %d.x; the kernels are built for sm_100a only", dev, major);
+        return SLIC_ERR_NO_DEVICE;
+    }
+    return SLIC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,128 @@
+// Shared host/device helpers for the slic_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/slic_b200.h"
+
+namespace slic {
+
+void set_error(const char* fmt, ...);
+
+#define SLIC_CUDA_OK(expr)                                                                     \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            slic::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return SLIC_ERR_CUDA;                                                              \
+        }                                                                                      \
+    } while (0)
+
+#define SLIC_REQUIRE(cond, msg)                                        \
+    do {                                                               \
+        if (!(cond)) {                                                 \
+            slic::set_error("%s:%d %s", __FILE__, __LINE__, msg);      \
+            return SLIC_ERR_INVALID_ARG;                               \
+        }                                                              \
+    } while (0)
+
+#define SLIC_PROPAGATE(expr)              \
+    do {                                  \
+        int _s = (expr);                  \
+        if (_s != SLIC_OK) return _s;     \
+    } while (0)
+
+#define SLIC_LAUNCH_OK() SLIC_CUDA_OK(cudaGetLastError())
+
+inline cudaStream_t as_stream(slic_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Stream-ordered temporary: freed (stream-ordered) when it goes out of scope.
+struct Scratch {
+    void* ptr = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaError_t alloc(size_t bytes, cudaStream_t s) {
+        stream = s;
+        if (bytes == 0) bytes = 16;
+        return cudaMallocAsync(&ptr, bytes, s);
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(ptr); }
+    ~Scratch() {
+        if (ptr) cudaFreeAsync(ptr, stream);
+    }
+    Scratch() = default;
+    Scratch(const Scratch&) = delete;
+    Scratch& operator=(const Scratch&) = delete;
+};
+
+int num_sms();
+
+__host__ __device__ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- device helpers ---------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// (score, index) ordering used everywhere a neighbour is chosen: larger similarity wins,
+// equal similarity -> lower index (np.argmin takes the first minimum, finch.py:29).
+__device__ __forceinline__ bool better(double s, int j, double sb, int jb) {
+    return (s > sb) || (s == sb && j < jb);
+}
+
+// distance in the reference dtype from a float64 similarity: sklearn cosine_distances does
+// S *= -1; S += 1; clip(S, 0, 2) in the array dtype (sklearn/metrics/pairwise.py:1174-1177).
+template <typename T>
+__device__ __forceinline__ T cosine_distance_from_sim(double s) {
+    T st = static_cast<T>(s);
+    T dd = static_cast<T>(1) - st;
+    dd = dd < static_cast<T>(0) ? static_cast<T>(0) : dd;
+    dd = dd > static_cast<T>(2) ? static_cast<T>(2) : dd;
+    return dd;
+}
+
+// exact <a, b> of two rows of unit vectors, float64 accumulation, one warp per pair.
+template <typename T>
+__device__ __forceinline__ double warp_dot(const T* __restrict__ a, const T* __restrict__ b, int d, int lane);
+
+template <>
+__device__ __forceinline__ double warp_dot<float>(const float* __restrict__ a, const float* __restrict__ b,
+                                                  int d, int lane) {
+    double acc = 0.0;
+    if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0) {
+        const float4* a4 = reinterpret_cast<const float4*>(a);
+        const float4* b4 = reinterpret_cast<const float4*>(b);
+        for (int k = lane; k < (d >> 2); k += 32) {
+            float4 x = __ldg(a4 + k), y = __ldg(b4 + k);
+            acc = fma((double)x.x, (double)y.x, acc);
+            acc = fma((double)x.y, (double)y.y, acc);
+            acc = fma((double)x.z, (double)y.z, acc);
+            acc = fma((double)x.w, (double)y.w, acc);
+        }
+    } else {
+        for (int k = lane; k < d; k += 32) acc = fma((double)__ldg(a + k), (double)__ldg(b + k), acc);
+    }
+    return warp_sum(acc);
+}
+
+template <>
+__device__ __forceinline__ double warp_dot<double>(const double* __restrict__ a, const double* __restrict__ b,
+                                                   int d, int lane) {
+    double acc = 0.0;
+    if ((d & 1) == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0) {
+        const double2* a2 = reinterpret_cast<const double2*>(a);
+        const double2* b2 = reinterpret_cast<const double2*>(b);
+        for (int k = lane; k < (d >> 1); k += 32) {
+            double2 x = __ldg(a2 + k), y = __ldg(b2 + k);
+            acc = fma(x.x, y.x, acc);
+            acc = fma(x.y, y.y, acc);
+        }
+    } else {
+        for (int k = lane; k < d; k += 32) acc = fma(__ldg(a + k), __ldg(b + k), acc);
+    }
+    return warp_sum(acc);
+}
+
+}  // namespace slic

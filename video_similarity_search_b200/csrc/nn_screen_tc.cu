@@ -1,0 +1,618 @@
+// K1-tc: first-neighbour screen on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), with the
+// per-row candidate filter fused into the epilogue so the nq x n score matrix never reaches HBM.
+// Replaces the O(n^2 D) sgemm/dgemm + three n^2 elementwise passes + argmin behind
+// clustering/finch.py:27-29 (sklearn pairwise_distances -> OpenBLAS).
+//
+// Work decomposition
+//   unit  = (128-row query block) x (one of `splits` contiguous column ranges)
+//   tile  = 128 x 256 scores of a unit, K = d_pad in 64-wide slabs (bf16, 128-byte swizzled rows)
+//   CTA   = persistent, one per SM, walks units round-robin; 6 warps:
+//           warp 0  TMA producer   : cp.async.bulk.tensor of the A (16 KB) and B (32 KB) slab per stage
+//           warp 1  MMA issuer     : one thread issues tcgen05.mma (M128 N256 K16) x 4 per slab, commits to
+//                                    the stage's "empty" barrier and, per tile, to the accumulator's "full" barrier
+//           warps 2-5 epilogue     : tcgen05.ld 32 columns at a time out of TMEM (two 256-column accumulators,
+//                                    so the filter of tile t overlaps the MMAs of tile t+1)
+//   Concurrent CTAs work on different row blocks of the SAME column range, so every B slab is fetched
+//   from HBM once per wave and served to the other 147 SMs from L2.
+//
+// Fused filter (per query row = one epilogue thread, state in registers)
+//   best = running maximum of the screened scores seen so far; a column is appended to the row's
+//   candidate list iff score >= best - eps at the time it is seen.  Because best only grows, the list
+//   is a superset of {j : score_j >= final best - eps}; with eps >= 2 * (max screening error) that set
+//   contains the exact first neighbour.  The common case costs one FMNMX3 per two scores plus one
+//   compare per 32; appends are rare (O(log n) per row).  A full list is first compacted against the
+//   current threshold; only if it is still full is the row flagged and later finished by the exact
+//   kernel - the result never depends on bf16 precision.
+//
+// Bound: tensor pipe.  Algorithmic work 2 * nq * n * d_pad flop; HBM traffic ~ (nq + n) * d_pad * 2 bytes.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace slic {
+
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 4, TC_UMMA_K = 16;
+constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
+constexpr uint32_t TC_B_BYTES = TC_BN * TC_BK * 2;   // 32 KB
+constexpr uint32_t TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr int TC_THREADS = 192;
+constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
+constexpr int TC_TMEM_COLS = 512;
+
+struct ScreenParams {
+    int64_t nq, n;
+    int num_k_slabs;       // d_pad / 64
+    int64_t self_offset;   // query row r is database row r + self_offset (excluded); < 0: no exclusion
+    float eps;
+    int cap;               // candidate slots per (split, row)
+    int splits;
+    int tiles_per_split;   // 256-column tiles per split
+    int64_t num_units;     // row blocks * splits
+    int* cand_idx;         // [splits][nq][cap]
+    float* cand_score;     // [splits][nq][cap]
+    int* cand_cnt;         // [splits][nq]
+    int* cand_flags;       // [splits][nq]  bit0 = overflow, bit1 = compacted
+    float* dump;           // debug: raw scores [nq][n] or nullptr
+    int* error_flag;       // set when a barrier wait times out
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug must not hang the GPU - after ~4 s the kernel flags the error and traps.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* error_flag) {
+    uint32_t done = 0;
+    long long t0 = 0;
+    uint32_t polls = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if ((++polls & 0x3ff) == 0) {
+            long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 8000000000ll) {
+                if (error_flag) atomicExch(error_flag, 1);
+                __trap();
+            }
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_load_32cols(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+        "%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte-swizzled operand tile (rows of 64 bf16 = 128 B, 8-row groups 1024 B apart):
+//   bits [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for swizzled K-major, 1),
+//   [32,46) stride byte offset >> 4 (1024 B), [46,48) descriptor version 1 (sm_100), [61,64) layout 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), both K-major,
+// N >> 3 at bits 17-22, M >> 4 at bits 24-28.
+constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
+                              ((uint32_t)(TC_BM >> 4) << 24);
+
+// ---- candidate list maintenance (slow path, rare) -------------------------------------------
+struct RowState {
+    float best, thr;
+    int cnt, flags;
+};
+
+__device__ __noinline__ RowState push_candidate(RowState st, float s, int col, float eps, int cap,
+                                                int* __restrict__ li, float* __restrict__ ls) {
+    if (s > st.best) {
+        st.best = s;
+        st.thr = s - eps;
+    }
+    if (st.cnt == cap) {
+        // compact against the current threshold (entries appended under an older, lower threshold)
+        int w = 0;
+        for (int r = 0; r < st.cnt; ++r) {
+            const float sc = ls[r];
+            if (sc >= st.thr) {
+                ls[w] = sc;
+                li[w] = li[r];
+                ++w;
+            }
+        }
+        st.cnt = w;
+        st.flags |= 2;
+    }
+    if (st.cnt < cap) {
+        ls[st.cnt] = s;
+        li[st.cnt] = col;
+        ++st.cnt;
+    } else {
+        st.flags |= 1;  // genuinely more than cap columns within eps of the best: exact kernel finishes the row
+    }
+    return st;
+}
+
+// ---- the kernel ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_constant__ CUtensorMap tmap_q,
+                                                                  const __grid_constant__ CUtensorMap tmap_x,
+                                                                  const ScreenParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+    const uint32_t bar_full = smem_u32(bars);                       // [TC_STAGES]
+    const uint32_t bar_empty = smem_u32(bars + TC_STAGES);          // [TC_STAGES]
+    const uint32_t bar_acc_full = smem_u32(bars + 2 * TC_STAGES);   // [2]
+    const uint32_t bar_acc_empty = smem_u32(bars + 2 * TC_STAGES + 2);  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
+    const uint32_t smem_base = smem_u32(smem);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_acc_full + 8 * a, 1);
+            mbar_init(bar_acc_empty + 8 * a, 4);  // one arrive per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(TC_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+    const int64_t n_col_tiles = (p.n + TC_BN - 1) / TC_BN;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+                const int split = (int)(u % p.splits);
+                const int64_t row_block = u / p.splits;
+                const int64_t ct0 = (int64_t)split * p.tiles_per_split;
+                const int64_t ct1 = min(ct0 + p.tiles_per_split, n_col_tiles);
+                for (int64_t ct = ct0; ct < ct1; ++ct) {
+                    for (int ks = 0; ks < p.num_k_slabs; ++ks) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1, p.error_flag);
+                        const uint32_t a_dst = smem_base + stage * TC_STAGE_BYTES;
+                        const uint32_t b_dst = a_dst + TC_A_BYTES;
+                        mbar_expect_tx(bar_full + 8 * stage, TC_STAGE_BYTES);
+                        tma_load_2d(&tmap_q, a_dst, bar_full + 8 * stage, ks * TC_BK, (int)(row_block * TC_BM));
+                        tma_load_2d(&tmap_x, b_dst, bar_full + 8 * stage, ks * TC_BK, (int)(ct * TC_BN));
+                        if (++stage == TC_STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int64_t u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+                const int split = (int)(u % p.splits);
+                const int64_t ct0 = (int64_t)split * p.tiles_per_split;
+                const int64_t ct1 = min(ct0 + p.tiles_per_split, n_col_tiles);
+                for (int64_t ct = ct0; ct < ct1; ++ct) {
+                    mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1, p.error_flag);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TC_BN);
+                    for (int ks = 0; ks < p.num_k_slabs; ++ks) {
+                        mbar_wait(bar_full + 8 * stage, phase, p.error_flag);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_base + stage * TC_STAGE_BYTES;
+                        const uint64_t da = umma_smem_desc(a_addr);
+                        const uint64_t db = umma_smem_desc(a_addr + TC_A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+                            // advancing 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the address field
+                            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), TC_IDESC,
+                                      (uint32_t)((ks | k) != 0));
+                        }
+                        umma_commit(bar_empty + 8 * stage);  // frees the smem stage once these MMAs retire
+                        if (++stage == TC_STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    umma_commit(bar_acc_full + 8 * acc);  // accumulator complete -> epilogue
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue: fused candidate filter =====================
+        const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are the ones this warp may read
+        const int row_in_tile = quad * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int64_t u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+            const int split = (int)(u % p.splits);
+            const int64_t row_block = u / p.splits;
+            const int64_t ct0 = (int64_t)split * p.tiles_per_split;
+            const int64_t ct1 = min(ct0 + p.tiles_per_split, n_col_tiles);
+            const int64_t row = row_block * TC_BM + row_in_tile;
+            const bool row_ok = row < p.nq;
+            const int64_t self_col = (p.self_offset >= 0 && row_ok) ? row + p.self_offset : -1;
+            const int64_t slot = (int64_t)split * p.nq + (row_ok ? row : 0);
+            int* li = p.cand_idx + slot * p.cap;
+            float* ls = p.cand_score + slot * p.cap;
+            RowState st;
+            st.best = -CUDART_INF_F;
+            st.thr = -CUDART_INF_F;
+            st.cnt = 0;
+            st.flags = 0;
+            for (int64_t ct = ct0; ct < ct1; ++ct) {
+                mbar_wait(bar_acc_full + 8 * acc, acc_phase, p.error_flag);
+                tc_fence_after();
+                const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_BN);
+#pragma unroll 1
+                for (int c = 0; c < TC_BN / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_load_32cols(taddr0 + (uint32_t)(c * 32), v);
+                    const int64_t col_base = ct * TC_BN + c * 32;
+                    if (col_base >= p.n) continue;  // whole chunk is padding (warp-uniform)
+                    if (col_base + 32 > p.n || (self_col >= col_base && self_col < col_base + 32)) {
+#pragma unroll
+                        for (int t = 0; t < 32; ++t)
+                            if (col_base + t >= p.n || col_base + t == self_col) v[t] = __float_as_uint(-CUDART_INF_F);
+                    }
+                    if (p.dump && row_ok) {
+#pragma unroll
+                        for (int t = 0; t < 32; ++t)
+                            if (col_base + t < p.n) p.dump[row * p.n + col_base + t] = __uint_as_float(v[t]);
+                    }
+                    float m = __uint_as_float(v[0]);
+#pragma unroll
+                    for (int t = 1; t < 32; ++t) m = fmaxf(m, __uint_as_float(v[t]));
+                    if (row_ok && m >= st.thr) {
+#pragma unroll
+                        for (int t = 0; t < 32; ++t) {
+                            const float s = __uint_as_float(v[t]);
+                            if (s >= st.thr && s > -CUDART_INF_F)
+                                st = push_candidate(st, s, (int)(col_base + t), p.eps, p.cap, li, ls);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+            if (row_ok) {
+                p.cand_cnt[slot] = st.cnt;
+                p.cand_flags[slot] = st.flags;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS)
+                     : "memory");
+    }
+}
+
+// ---- exact re-rank of the surviving candidates (one warp per query row) ------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) rerank_top1_kernel(const T* __restrict__ q_unit, const T* __restrict__ x_unit,
+                                                          int64_t nq, int d, float eps, int cap, int splits,
+                                                          const int* __restrict__ cand_idx,
+                                                          const float* __restrict__ cand_score,
+                                                          const int* __restrict__ cand_cnt,
+                                                          const int* __restrict__ cand_flags, int* __restrict__ idx_out,
+                                                          T* __restrict__ dist_out, int* __restrict__ overflow_rows,
+                                                          int* __restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= nq) return;
+    float gbest = -CUDART_INF_F;
+    int flags = 0;
+    for (int sp = 0; sp < splits; ++sp) {
+        const int64_t slot = (int64_t)sp * nq + r;
+        const int c = cand_cnt[slot];
+        flags |= cand_flags[slot];
+        for (int e = lane; e < c; e += 32) gbest = fmaxf(gbest, cand_score[slot * cap + e]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gbest = fmaxf(gbest, __shfl_xor_sync(0xffffffffu, gbest, o));
+    const float thr = gbest - eps;
+    const T* qr = q_unit + r * d;
+    double best_s = -CUDART_INF;
+    int best_j = 0x7fffffff, reranked = 0;
+    for (int sp = 0; sp < splits; ++sp) {
+        const int64_t slot = (int64_t)sp * nq + r;
+        const int c = cand_cnt[slot];
+        for (int e = 0; e < c; ++e) {
+            if (cand_score[slot * cap + e] < thr) continue;  // warp-uniform
+            const int j = cand_idx[slot * cap + e];
+            const double s = warp_dot<T>(qr, x_unit + (int64_t)j * d, d, lane);
+            ++reranked;
+            if (better(s, j, best_s, best_j)) {
+                best_s = s;
+                best_j = j;
+            }
+        }
+    }
+    if (lane == 0) {
+        idx_out[r] = best_j == 0x7fffffff ? -1 : best_j;
+        if (dist_out) dist_out[r] = cosine_distance_from_sim<T>(best_s);
+        atomicAdd(&stats[0], reranked);
+        if (flags & 2) atomicAdd(&stats[2], 1);
+        if ((flags & 1) || best_j == 0x7fffffff) {
+            const int pos = atomicAdd(&stats[1], 1);
+            overflow_rows[pos] = (int)r;
+        }
+    }
+}
+
+template <typename T>
+__global__ void scatter_rows_kernel(const int* __restrict__ rows, int count, const int* __restrict__ idx_src,
+                                    const T* __restrict__ dist_src, int* __restrict__ idx_out, T* __restrict__ dist_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    idx_out[rows[i]] = idx_src[i];
+    if (dist_out) dist_out[rows[i]] = dist_src[i];
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int get_encode_fn(EncodeTiledFn* out) {
+    static EncodeTiledFn cached = nullptr;
+    if (!cached) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        SLIC_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !fn) {
+            set_error("cuTensorMapEncodeTiled is not available from the driver");
+            return SLIC_ERR_UNSUPPORTED;
+        }
+        cached = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    *out = cached;
+    return SLIC_OK;
+}
+
+// rows x d_pad bf16, row-major; box = 64 (K) x box_rows, 128-byte swizzle, out-of-bounds rows read as zero
+static int make_tmap(CUtensorMap* map, const uint16_t* base, int64_t rows, int d_pad, int box_rows) {
+    EncodeTiledFn enc;
+    SLIC_PROPAGATE(get_encode_fn(&enc));
+    cuuint64_t gdim[2] = {(cuuint64_t)d_pad, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)d_pad * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<uint16_t*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld d_pad=%d)", (int)r, (long long)rows, d_pad);
+        return SLIC_ERR_CUDA;
+    }
+    return SLIC_OK;
+}
+
+struct ScreenPlan {
+    int splits, tiles_per_split;
+    int64_t units;
+};
+
+static ScreenPlan plan_screen(int64_t nq, int64_t n) {
+    const int64_t row_blocks = ceil_div(nq, TC_BM), col_tiles = ceil_div(n, TC_BN);
+    const int64_t sms = num_sms();
+    // enough units for >= ~6 waves when the problem allows it, but keep >= 8 tiles per unit
+    int64_t want = ceil_div(6 * sms, row_blocks);
+    int64_t max_splits = col_tiles / 8 > 0 ? col_tiles / 8 : 1;
+    int64_t splits = want < 1 ? 1 : (want > max_splits ? max_splits : want);
+    ScreenPlan pl;
+    pl.tiles_per_split = (int)ceil_div(col_tiles, splits);
+    pl.splits = (int)ceil_div(col_tiles, pl.tiles_per_split);
+    pl.units = row_blocks * pl.splits;
+    return pl;
+}
+
+static int launch_screen(const uint16_t* q_bf16, int64_t nq, const uint16_t* x_bf16, int64_t n, int d_pad,
+                         int64_t self_offset, float eps, int cap, const ScreenPlan& pl, int* cand_idx, float* cand_score,
+                         int* cand_cnt, int* cand_flags, float* dump, int* error_flag, cudaStream_t st) {
+    CUtensorMap tq, tx;
+    SLIC_PROPAGATE(make_tmap(&tq, q_bf16, nq, d_pad, TC_BM));
+    SLIC_PROPAGATE(make_tmap(&tx, x_bf16, n, d_pad, TC_BN));
+    ScreenParams p;
+    p.nq = nq;
+    p.n = n;
+    p.num_k_slabs = d_pad / TC_BK;
+    p.self_offset = self_offset;
+    p.eps = eps;
+    p.cap = cap;
+    p.splits = pl.splits;
+    p.tiles_per_split = pl.tiles_per_split;
+    p.num_units = pl.units;
+    p.cand_idx = cand_idx;
+    p.cand_score = cand_score;
+    p.cand_cnt = cand_cnt;
+    p.cand_flags = cand_flags;
+    p.dump = dump;
+    p.error_flag = error_flag;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SLIC_CUDA_OK(cudaFuncSetAttribute(nn_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        attr_set = true;
+    }
+    const int64_t grid = pl.units < num_sms() ? pl.units : num_sms();
+    nn_screen_kernel<<<(unsigned)grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tq, tx, p);
+    SLIC_LAUNCH_OK();
+    return SLIC_OK;
+}
+
+constexpr int TC_CAP = 32;
+
+template <typename T>
+static int nn_top1_impl(const T* q_unit, const uint16_t* q_bf16, int64_t nq, const T* x_unit, const uint16_t* x_bf16,
+                        int64_t n, int d, int d_pad, int64_t self_offset, float eps, int* idx_out, T* dist_out,
+                        int* stats_out, cudaStream_t st) {
+    const ScreenPlan pl = plan_screen(nq, n);
+    const int64_t slots = (int64_t)pl.splits * nq;
+    Scratch ci, cs, cc, cf, ovr, stats;
+    SLIC_CUDA_OK(ci.alloc(slots * TC_CAP * sizeof(int), st));
+    SLIC_CUDA_OK(cs.alloc(slots * TC_CAP * sizeof(float), st));
+    SLIC_CUDA_OK(cc.alloc(slots * sizeof(int), st));
+    SLIC_CUDA_OK(cf.alloc(slots * sizeof(int), st));
+    SLIC_CUDA_OK(ovr.alloc(nq * sizeof(int), st));
+    SLIC_CUDA_OK(stats.alloc(8 * sizeof(int), st));
+    SLIC_CUDA_OK(cudaMemsetAsync(stats.ptr, 0, 8 * sizeof(int), st));
+    SLIC_PROPAGATE(launch_screen(q_bf16, nq, x_bf16, n, d_pad, self_offset, eps, TC_CAP, pl, ci.as<int>(), cs.as<float>(),
+                                 cc.as<int>(), cf.as<int>(), nullptr, stats.as<int>() + 4, st));
+    rerank_top1_kernel<T><<<(unsigned)ceil_div(nq, 8), 256, 0, st>>>(q_unit, x_unit, nq, d, eps, TC_CAP, pl.splits,
+                                                                     ci.as<int>(), cs.as<float>(), cc.as<int>(),
+                                                                     cf.as<int>(), idx_out, dist_out, ovr.as<int>(),
+                                                                     stats.as<int>());
+    SLIC_LAUNCH_OK();
+    int host_stats[8];
+    SLIC_CUDA_OK(cudaMemcpyAsync(host_stats, stats.ptr, sizeof(host_stats), cudaMemcpyDeviceToHost, st));
+    SLIC_CUDA_OK(cudaStreamSynchronize(st));
+    if (host_stats[4] != 0) {
+        set_error("nn_screen_kernel: pipeline barrier timed out");
+        return SLIC_ERR_CUDA;
+    }
+    const int n_over = host_stats[1];
+    if (n_over > 0) {
+        Scratch oi, od;
+        SLIC_CUDA_OK(oi.alloc((int64_t)n_over * sizeof(int), st));
+        SLIC_CUDA_OK(od.alloc((int64_t)n_over * sizeof(T), st));
+        SLIC_PROPAGATE(slic_nn_exact_top1(q_unit, ovr.as<int>(), n_over, x_unit, n, d,
+                                          sizeof(T) == 4 ? SLIC_F32 : SLIC_F64, self_offset, oi.as<int>(), od.ptr, st));
+        scatter_rows_kernel<T><<<(unsigned)ceil_div(n_over, 256), 256, 0, st>>>(ovr.as<int>(), n_over, oi.as<int>(),
+                                                                                od.as<T>(), idx_out, dist_out);
+        SLIC_LAUNCH_OK();
+    }
+    if (stats_out) SLIC_CUDA_OK(cudaMemcpyAsync(stats_out, stats.ptr, 4 * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    return SLIC_OK;
+}
+
+}  // namespace slic
+
+extern "C" {
+
+int slic_nn_top1(const void* q_unit_dev, const uint16_t* q_bf16_dev, int64_t nq, const void* x_unit_dev,
+                 const uint16_t* x_bf16_dev, int64_t n, int32_t d, int32_t d_pad, int32_t dtype, int64_t self_offset,
+                 float eps, int32_t* idx_out_dev, void* dist_out_dev, int32_t* stats_out_dev, slic_stream_t stream) {
+    SLIC_REQUIRE(nq > 0 && n > 1 && n < ((int64_t)1 << 31) && nq < ((int64_t)1 << 31), "nn_top1: bad shape");
+    SLIC_REQUIRE(d > 0 && d_pad >= d && d_pad % 64 == 0, "nn_top1: d_pad must be a multiple of 64 >= d");
+    SLIC_REQUIRE(q_unit_dev && q_bf16_dev && x_unit_dev && x_bf16_dev && idx_out_dev, "nn_top1: null pointer");
+    SLIC_REQUIRE(dtype == SLIC_F32 || dtype == SLIC_F64, "nn_top1: bad dtype");
+    SLIC_REQUIRE((reinterpret_cast<uintptr_t>(q_bf16_dev) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_bf16_dev) & 15) == 0,
+                 "nn_top1: bf16 matrices must be 16-byte aligned");
+    SLIC_PROPAGATE(slic_require_device());
+    if (eps <= 0.f) eps = 0.0078125f;
+    cudaStream_t st = slic::as_stream(stream);
+    if (dtype == SLIC_F32)
+        return slic::nn_top1_impl<float>((const float*)q_unit_dev, q_bf16_dev, nq, (const float*)x_unit_dev, x_bf16_dev,
+                                         n, d, d_pad, self_offset, eps, idx_out_dev, (float*)dist_out_dev,
+                                         stats_out_dev, st);
+    return slic::nn_top1_impl<double>((const double*)q_unit_dev, q_bf16_dev, nq, (const double*)x_unit_dev, x_bf16_dev, n,
+                                      d, d_pad, self_offset, eps, idx_out_dev, (double*)dist_out_dev, stats_out_dev,
+                                      st);
+}
+
+int slic_screen_scores_debug(const uint16_t* q_bf16_dev, int64_t nq, const uint16_t* x_bf16_dev, int64_t n,
+                             int32_t d_pad, float* out_dev, slic_stream_t stream) {
+    using namespace slic;
+    SLIC_REQUIRE(nq > 0 && n > 0 && d_pad > 0 && d_pad % 64 == 0, "screen_scores_debug: bad shape");
+    SLIC_REQUIRE(q_bf16_dev && x_bf16_dev && out_dev, "screen_scores_debug: null pointer");
+    SLIC_PROPAGATE(slic_require_device());
+    cudaStream_t st = as_stream(stream);
+    const ScreenPlan pl = plan_screen(nq, n);
+    const int64_t slots = (int64_t)pl.splits * nq;
+    Scratch ci, cs, cc, cf, err;
+    SLIC_CUDA_OK(ci.alloc(slots * TC_CAP * sizeof(int), st));
+    SLIC_CUDA_OK(cs.alloc(slots * TC_CAP * sizeof(float), st));
+    SLIC_CUDA_OK(cc.alloc(slots * sizeof(int), st));
+    SLIC_CUDA_OK(cf.alloc(slots * sizeof(int), st));
+    SLIC_CUDA_OK(err.alloc(sizeof(int), st));
+    SLIC_CUDA_OK(cudaMemsetAsync(err.ptr, 0, sizeof(int), st));
+    SLIC_PROPAGATE(launch_screen(q_bf16_dev, nq, x_bf16_dev, n, d_pad, -1, 0.0078125f, TC_CAP, pl, ci.as<int>(),
+                                 cs.as<float>(), cc.as<int>(), cf.as<int>(), out_dev, err.as<int>(), st));
+    int host_err = 0;
+    SLIC_CUDA_OK(cudaMemcpyAsync(&host_err, err.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SLIC_CUDA_OK(cudaStreamSynchronize(st));
+    if (host_err) {
+        set_error("nn_screen_kernel: pipeline barrier timed out");
+        return SLIC_ERR_CUDA;
+    }
+    return SLIC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,68 @@
+"""IIC-style clip retrieval on B200 - drop-in for topk_retrieval of
+/root/reference/iic_retrieve_clips.py:275-314.
+
+Same files in ({train,test}_{feature,class}.npy under args.feature_dir) and out (topk_correct.json),
+same printed lines.  The cosine distances, the top-50 selection and the hit counting run on the GPU;
+the reference's full-row np.argsort (iic_retrieve_clips.py:296) is replaced by a top-50 select
+because only the first 50 columns are ever read (:298-306).
+"""
+import json
+import os
+
+import numpy as np
+import torch
+
+from . import backend as _backend
+
+KS = [1, 5, 10, 20, 50]
+
+
+def topk_retrieval_arrays(X_train, y_train, X_test, y_test, ks=KS, backend=None, return_neighbors=False):
+    """The arithmetic of iic_retrieve_clips.py:280-306 on in-memory arrays.
+    X_*: [videos, clips, D] (or already [videos, D]); y_*: [videos, clips] (or [videos])."""
+    be = backend or _backend.default_backend()
+    X_train, X_test = np.asarray(X_train), np.asarray(X_test)
+    y_train, y_test = np.asarray(y_train), np.asarray(y_test)
+    if X_train.ndim == 3:
+        X_train = np.mean(X_train, 1)                                # :280
+        y_train = y_train[:, 0]                                      # :281
+    if X_test.ndim == 3:
+        X_test = np.mean(X_test, 1)                                  # :287
+        y_test = y_test[:, 0]
+    X_train = X_train.reshape((-1, X_train.shape[-1]))
+    X_test = X_test.reshape((-1, X_test.shape[-1]))
+    y_train, y_test = y_train.reshape(-1), y_test.reshape(-1)
+    # sklearn keeps float32 only if both sides are float32
+    dt = np.float32 if (X_train.dtype == np.float32 and X_test.dtype == np.float32) else np.float64
+    tdt = torch.float32 if dt == np.float32 else torch.float64
+    xd = be.to_device(np.ascontiguousarray(X_train.astype(dt, copy=False)), tdt)
+    qd = be.to_device(np.ascontiguousarray(X_test.astype(dt, copy=False)), tdt)
+    ux, _ = be.normalize_rows(xd, want_bf16=False)
+    uq, _ = be.normalize_rows(qd, want_bf16=False)
+    kmax = min(max(ks), X_train.shape[0])
+    idx, dist = be.topk_cosine(uq, ux, kmax)                         # :295-296
+    ks_eff = [min(int(k), kmax) for k in ks]
+    hits = be.to_host(be.hit_at_k(idx, be.to_device(y_test.astype(np.int64), torch.int64),
+                                  be.to_device(y_train.astype(np.int64), torch.int64), ks_eff))
+    topk_correct = {int(k): int(h) for k, h in zip(ks, hits)}         # :298-306
+    if return_neighbors:
+        return topk_correct, be.to_host(idx).astype(np.int64), be.to_host(dist)
+    return topk_correct
+
+
+def topk_retrieval(args, backend=None):
+    """Extract features from test split and search on train split features.
+    (iic_retrieve_clips.py:275-314; args.feature_dir holds the four .npy files.)"""
+    print('Load local .npy files.')
+    X_train = np.load(os.path.join(args.feature_dir, 'train_feature.npy'))
+    y_train = np.load(os.path.join(args.feature_dir, 'train_class.npy'))
+    X_test = np.load(os.path.join(args.feature_dir, 'test_feature.npy'))
+    y_test = np.load(os.path.join(args.feature_dir, 'test_class.npy'))
+    topk_correct = topk_retrieval_arrays(X_train, y_train, X_test, y_test, KS, backend=backend)
+    total = len(X_test)
+    for k in KS:
+        correct = topk_correct[k]
+        print('Top-{}, correct = {:.2f}, total = {}, acc = {:.3f}'.format(k, correct, total, correct / total))
+    with open(os.path.join(args.feature_dir, 'topk_correct.json'), 'w') as fp:
+        json.dump(topk_correct, fp)
+    return topk_correct

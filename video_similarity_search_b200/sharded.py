@@ -1,0 +1,69 @@
+"""Multi-GPU level-0 first-neighbour search: query rows sharded across the ranks of one box, every
+rank holding the full embedding matrix; per-row neighbour ids (and distances, which the min_sim
+filter needs) are all-gathered over NCCL / NVLink.  Levels >= 1 (n_1 << N), the components and the
+means are serial work of a few milliseconds and run redundantly on every rank, so all ranks return
+the same partition without a broadcast.
+
+One process per GPU (torch.distributed, backend nccl on GPUs; gloo works for the CPU tests with the
+stand-in backend).  The reference runs FINCH on rank 0 only while the other ranks wait at a barrier
+(online_train.py:619-627, 660-662); here those ranks do a 1/world share of the O(N^2 D) stage.
+"""
+import torch
+import torch.distributed as dist
+
+from . import backend as _backend
+from .clustering.finch import FINCH
+
+
+def shard_range(n, rank, world):
+    per = (n + world - 1) // world
+    r0 = min(rank * per, n)
+    return r0, min(r0 + per, n), per
+
+
+def sharded_first_neighbors(be, group=None, timings=None):
+    """Returns a callable mat -> (nn, dist, unit) for FINCH(first_neighbors=...)."""
+
+    def search(mat):
+        world = dist.get_world_size(group)
+        rank = dist.get_rank(group)
+        n = mat.shape[0]
+        r0, r1, per = shard_range(n, rank, world)
+        nn_loc, d_loc, unit = be.first_neighbors(mat, row_range=(r0, r1))
+        if world == 1:
+            return nn_loc, d_loc, unit
+        nn_pad = torch.full((per,), -1, dtype=torch.int32, device=mat.device)
+        d_pad = torch.zeros((per,), dtype=mat.dtype, device=mat.device)
+        nn_pad[: r1 - r0] = nn_loc
+        d_pad[: r1 - r0] = d_loc
+        nn_all = torch.empty(per * world, dtype=torch.int32, device=mat.device)
+        d_all = torch.empty(per * world, dtype=mat.dtype, device=mat.device)
+        # the one exchange step of the path: 4 N bytes of ids + 4 N bytes of distances in total
+        dist.all_gather_into_tensor(nn_all, nn_pad, group=group)
+        dist.all_gather_into_tensor(d_all, d_pad, group=group)
+        return nn_all[:n].contiguous(), d_all[:n].contiguous(), unit
+
+    return search
+
+
+def FINCH_sharded(data, group=None, backend=None, **kwargs):
+    """FINCH with the level-0 nearest-neighbour stage row-sharded over the process group.  Every rank
+    must pass the same `data`; every rank returns the same (c, num_clust, req_c)."""
+    be = backend or _backend.default_backend()
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return FINCH(data, backend=be, **kwargs)
+    return FINCH(data, backend=be, first_neighbors=sharded_first_neighbors(be, group), **kwargs)
+
+
+def replicate(data, src=0, group=None, backend=None):
+    """Broadcast the [N, D] float32 matrix held by rank `src` to every rank's GPU (NCCL over NVLink)."""
+    be = backend or _backend.default_backend()
+    shape = torch.zeros(2, dtype=torch.int64, device=be.device)
+    if dist.get_rank(group) == src:
+        t = be.to_device(data, torch.float32)
+        shape[0], shape[1] = t.shape
+    dist.broadcast(shape, src, group=group)
+    if dist.get_rank(group) != src:
+        t = torch.empty((int(shape[0]), int(shape[1])), dtype=torch.float32, device=be.device)
+    dist.broadcast(t, src, group=group)
+    return t
