@@ -145,13 +145,20 @@ def _rank(mat, initial_rank, exact_above_threshold):
 
 
 def finch(data, initial_rank=None, req_clust=None, ensure_early_exit=True, verbose=False,
-          exact_above_threshold=True, return_trace=False):
+          exact_above_threshold=True, return_trace=False, nn0_override=None):
     """finch.py:108-178 with distance='cosine'.  Returns (c int [N,P], num_clust list, req_c)
-    and, with return_trace, a dict of per-level first neighbours / min_sim for diagnostics."""
+    and, with return_trace, a dict of per-level first neighbours / min_sim for diagnostics.
+
+    nn0_override (tests only): replace the level-0 first neighbours by the given ones while keeping
+    everything else of the dense mode (distances, min_sim).  Used to show that a partition difference
+    is explained entirely by rows whose float32 top-1/top-2 distances tie."""
     data = data.astype(np.float32)                                    # :131
     trace = {"nn": [], "min_sim": None}
     min_sim = None
     adj, dist, nn = _rank(data, initial_rank, exact_above_threshold)  # :134
+    if nn0_override is not None:
+        nn = np.asarray(nn0_override)
+        adj = link_graph(nn)
     trace["nn"].append(np.asarray(nn))
     group, n0 = components(adj, [], None)                             # :136
     c, mat = compose([], group, data)                                 # :137

@@ -49,10 +49,11 @@ class FakeBackend:
         if self_offset >= 0:
             rows = np.arange(len(q)) if q_rows is None else _np(q_rows)
             s[np.arange(len(q)), rows + self_offset] = -np.inf
-        j = np.argmax(s, axis=1)
         dt = _np(x_unit).dtype
-        d = np.clip(dt.type(1) - s[np.arange(len(q)), j].astype(dt), 0, 2).astype(dt)
-        return torch.from_numpy(j.astype(np.int32)), torch.from_numpy(d)
+        dmat = np.clip(dt.type(1) - s.astype(dt), 0, 2).astype(dt)     # distances in the reference dtype
+        dmat[np.isneginf(s)] = np.inf
+        j = np.argmin(dmat, axis=1)                                      # ties -> lowest index (np.argmin)
+        return torch.from_numpy(j.astype(np.int32)), torch.from_numpy(dmat[np.arange(len(q)), j])
 
     def nn_top1(self, q_unit, q_bf16, x_unit, x_bf16, self_offset=-1, eps=0.0):
         return self.nn_exact_top1(q_unit, x_unit, self_offset)

@@ -164,8 +164,9 @@ def test_screened_first_neighbors_equal_exact(be, dtype, n, d, k, seed):
     unit, ub = be.normalize_rows(dev(be, x))
     nn_e, d_e = be.nn_exact_top1(unit, unit, self_offset=0)
     nn_s, d_s = be.nn_top1(unit, ub, unit, ub, self_offset=0)
-    assert torch.equal(nn_e, nn_s)                                # same float64-accumulated argmax, no margin needed
-    assert torch.equal(d_e, d_s)
+    assert torch.equal(nn_e, nn_s)
+    # the two kernels add the float64 products in different orders: equal to rounding of the reference dtype
+    np.testing.assert_allclose(d_s.cpu().numpy(), d_e.cpu().numpy(), rtol=0, atol=1.2e-7 if dtype == np.float32 else 1e-14)
     stats = be.last_stats.cpu().numpy()
     assert stats[1] == 0                                          # no row needed the exact finisher
     # row-sharded form (what each rank of the multi-GPU path runs)

@@ -66,10 +66,12 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// (score, index) ordering used everywhere a neighbour is chosen: larger similarity wins,
-// equal similarity -> lower index (np.argmin takes the first minimum, finch.py:29).
-__device__ __forceinline__ bool better(double s, int j, double sb, int jb) {
-    return (s > sb) || (s == sb && j < jb);
+// (distance, index) ordering used everywhere a neighbour is chosen.  The reference takes np.argmin of
+// distances held in the array dtype (finch.py:27-29): the smaller distance wins and equal distances -
+// including float32 values that only tie after rounding - go to the lower index.  Callers therefore pass
+// the distance ALREADY ROUNDED to the reference dtype (cosine_distance_from_sim<T>), widened to double.
+__device__ __forceinline__ bool closer(double dd, int j, double db, int jb) {
+    return (dd < db) || (dd == db && j < jb);
 }
 
 // distance in the reference dtype from a float64 similarity: sklearn cosine_distances does

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(EX_THREADS) exact_top1_kernel(const T* __restr
     int64_t self_col[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        best_s[i] = -CUDART_INF;
+        best_s[i] = CUDART_INF;  // holds the best DISTANCE (rounded to T) seen so far
         best_j[i] = 0x7fffffff;
         const int64_t r = row0 + ty * 4 + i;
         self_col[i] = -1;
@@ -90,13 +90,14 @@ __global__ void __launch_bounds__(EX_THREADS) exact_top1_kernel(const T* __restr
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            double s = -CUDART_INF;
+            double s = CUDART_INF;
             int jb = 0x7fffffff;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int64_t col = col0 + tx * 4 + j;
-                if (col < n && col != self_col[i] && better(acc[i][j], (int)col, s, jb)) {
-                    s = acc[i][j];
+                const double dist = (double)cosine_distance_from_sim<T>(acc[i][j]);
+                if (col < n && col != self_col[i] && closer(dist, (int)col, s, jb)) {
+                    s = dist;
                     jb = (int)col;
                 }
             }
@@ -104,12 +105,12 @@ __global__ void __launch_bounds__(EX_THREADS) exact_top1_kernel(const T* __restr
             for (int o = 8; o > 0; o >>= 1) {
                 const double so = __shfl_xor_sync(0xffffffffu, s, o);
                 const int jo = __shfl_xor_sync(0xffffffffu, jb, o);
-                if (better(so, jo, s, jb)) {
+                if (closer(so, jo, s, jb)) {
                     s = so;
                     jb = jo;
                 }
             }
-            if (better(s, jb, best_s[i], best_j[i])) {
+            if (closer(s, jb, best_s[i], best_j[i])) {
                 best_s[i] = s;
                 best_j[i] = jb;
             }
@@ -132,18 +133,18 @@ __global__ void exact_top1_merge_kernel(const double* __restrict__ part_score, c
                                         int64_t nq, int splits, int* __restrict__ idx_out, T* __restrict__ dist_out) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nq) return;
-    double s = -CUDART_INF;
+    double s = CUDART_INF;
     int jb = 0x7fffffff;
     for (int p = 0; p < splits; ++p) {
         const double so = part_score[(int64_t)p * nq + r];
         const int jo = part_idx[(int64_t)p * nq + r];
-        if (better(so, jo, s, jb)) {
+        if (closer(so, jo, s, jb)) {
             s = so;
             jb = jo;
         }
     }
     idx_out[r] = jb == 0x7fffffff ? -1 : jb;
-    if (dist_out) dist_out[r] = cosine_distance_from_sim<T>(s);
+    if (dist_out) dist_out[r] = (T)s;  // already a distance in T
 }
 
 // ---- dense distance matrix ---------------------------------------------------------------

@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(256) rerank_top1_kernel(const T* __restrict__ 
     for (int o = 16; o > 0; o >>= 1) gbest = fmaxf(gbest, __shfl_xor_sync(0xffffffffu, gbest, o));
     const float thr = gbest - eps;
     const T* qr = q_unit + r * d;
-    double best_s = -CUDART_INF;
+    double best_d = CUDART_INF;  // best distance, rounded to T as the reference holds it
     int best_j = 0x7fffffff, reranked = 0;
     for (int sp = 0; sp < splits; ++sp) {
         const int64_t slot = (int64_t)sp * nq + r;
@@ -399,15 +399,16 @@ __global__ void __launch_bounds__(256) rerank_top1_kernel(const T* __restrict__ 
             const int j = cand_idx[slot * cap + e];
             const double s = warp_dot<T>(qr, x_unit + (int64_t)j * d, d, lane);
             ++reranked;
-            if (better(s, j, best_s, best_j)) {
-                best_s = s;
+            const double dist = (double)cosine_distance_from_sim<T>(s);
+            if (closer(dist, j, best_d, best_j)) {
+                best_d = dist;
                 best_j = j;
             }
         }
     }
     if (lane == 0) {
         idx_out[r] = best_j == 0x7fffffff ? -1 : best_j;
-        if (dist_out) dist_out[r] = cosine_distance_from_sim<T>(best_s);
+        if (dist_out) dist_out[r] = (T)best_d;
         atomicAdd(&stats[0], reranked);
         if (flags & 2) atomicAdd(&stats[2], 1);
         if ((flags & 1) || best_j == 0x7fffffff) {
