@@ -54,6 +54,13 @@ int slic_abi_version(void);
 const char* slic_last_error(void);
 /* SLIC_OK only if the current device is compute capability 10.x (B200 / sm_100a). */
 int slic_require_device(void);
+/* Number of CUDA kernels this library has launched in this process (monotonic). */
+int64_t slic_launch_count(void);
+/* Measurement hooks: with profiling enabled every launch of the tensor-core screen kernel is
+ * bracketed by CUDA events on its own stream; slic_last_screen_time waits for the most recent
+ * one and returns its duration and its algorithmic work (2 * nq * n * d_pad flop). */
+int slic_profile_screen(int32_t enable);
+int slic_last_screen_time(float* ms_out, double* flop_out);
 
 /* ---- K1 prep: row normalisation --------------------------------------------------------- */
 /* sklearn cosine_similarity's normalize step behind clustering/finch.py:27, evaluate.py:213,

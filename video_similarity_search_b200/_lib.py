@@ -17,6 +17,9 @@ SIGNATURES = {
     "slic_abi_version": [],
     "slic_last_error": [],
     "slic_require_device": [],
+    "slic_launch_count": [],
+    "slic_profile_screen": [_i32],
+    "slic_last_screen_time": [_ptr, _ptr],
     "slic_normalize_rows": [_ptr, _i64, _i32, _i32, _ptr, _ptr, _ptr, _i32, _ptr],
     "slic_nn_exact_top1": [_ptr, _ptr, _i64, _ptr, _i64, _i32, _i32, _i64, _ptr, _ptr, _ptr],
     "slic_nn_top1": [_ptr, _ptr, _i64, _ptr, _ptr, _i64, _i32, _i32, _i32, _i64, _f32, _ptr, _ptr, _ptr, _ptr],
@@ -35,7 +38,7 @@ SIGNATURES = {
     "slic_group_by_label": [_ptr, _i64, _i32, _ptr, _ptr, _ptr],
     "slic_first_neighbors_host": [_ptr, _i64, _i32, _i32, _ptr, _ptr],
 }
-_RESTYPES = {"slic_last_error": _c.c_char_p}
+_RESTYPES = {"slic_last_error": _c.c_char_p, "slic_launch_count": _c.c_int64}
 
 SLIC_F32, SLIC_F64 = 0, 1
 SLIC_METRIC_COSINE, SLIC_METRIC_EUCLIDEAN = 0, 1

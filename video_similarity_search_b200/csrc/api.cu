@@ -2,9 +2,14 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace slic {
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 static thread_local char g_error[512] = "";
 
@@ -33,6 +38,8 @@ int num_sms() {
 extern "C" {
 
 int slic_abi_version(void) { return SLIC_ABI_VERSION; }
+
+int64_t slic_launch_count(void) { return (int64_t)slic::g_launches.load(std::memory_order_relaxed); }
 
 const char* slic_last_error(void) { return slic::g_error; }
 

@@ -33,7 +33,14 @@ void set_error(const char* fmt, ...);
         if (_s != SLIC_OK) return _s;     \
     } while (0)
 
-#define SLIC_LAUNCH_OK() SLIC_CUDA_OK(cudaGetLastError())
+// every kernel launch in the library goes through this: checks the launch and counts it
+// (slic_launch_count(), read by bench.py for its gpu_launches claim)
+void count_launch();
+#define SLIC_LAUNCH_OK()                  \
+    do {                                  \
+        SLIC_CUDA_OK(cudaGetLastError()); \
+        slic::count_launch();             \
+    } while (0)
 
 inline cudaStream_t as_stream(slic_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

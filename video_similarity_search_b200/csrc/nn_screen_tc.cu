@@ -466,6 +466,11 @@ static int make_tmap(CUtensorMap* map, const uint16_t* base, int64_t rows, int d
     return SLIC_OK;
 }
 
+// optional CUDA-event timing of the screen kernel on its own stream (bench.py's roofline leg)
+static bool g_profile = false, g_have_sample = false;
+static cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
+static double g_last_flop = 0.0;
+
 struct ScreenPlan {
     int splits, tiles_per_split;
     int64_t units;
@@ -513,8 +518,20 @@ static int launch_screen(const uint16_t* q_bf16, int64_t nq, const uint16_t* x_b
         attr_set = true;
     }
     const int64_t grid = pl.units < num_sms() ? pl.units : num_sms();
+    if (g_profile) {
+        if (!g_ev_start) {
+            SLIC_CUDA_OK(cudaEventCreate(&g_ev_start));
+            SLIC_CUDA_OK(cudaEventCreate(&g_ev_stop));
+        }
+        SLIC_CUDA_OK(cudaEventRecord(g_ev_start, st));
+    }
     nn_screen_kernel<<<(unsigned)grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tq, tx, p);
     SLIC_LAUNCH_OK();
+    if (g_profile) {
+        SLIC_CUDA_OK(cudaEventRecord(g_ev_stop, st));
+        g_last_flop = 2.0 * (double)nq * (double)n * (double)d_pad;
+        g_have_sample = true;
+    }
     return SLIC_OK;
 }
 
@@ -586,6 +603,24 @@ int slic_nn_top1(const void* q_unit_dev, const uint16_t* q_bf16_dev, int64_t nq,
     return slic::nn_top1_impl<double>((const double*)q_unit_dev, q_bf16_dev, nq, (const double*)x_unit_dev, x_bf16_dev, n,
                                       d, d_pad, self_offset, eps, idx_out_dev, (double*)dist_out_dev, stats_out_dev,
                                       st);
+}
+
+int slic_profile_screen(int32_t enable) {
+    slic::g_profile = enable != 0;
+    slic::g_have_sample = false;
+    return SLIC_OK;
+}
+
+int slic_last_screen_time(float* ms_out, double* flop_out) {
+    SLIC_REQUIRE(ms_out && flop_out, "last_screen_time: null pointer");
+    if (!slic::g_have_sample) {
+        slic::set_error("last_screen_time: no profiled launch (call slic_profile_screen(1) first)");
+        return SLIC_ERR_INVALID_ARG;
+    }
+    SLIC_CUDA_OK(cudaEventSynchronize(slic::g_ev_stop));
+    SLIC_CUDA_OK(cudaEventElapsedTime(ms_out, slic::g_ev_start, slic::g_ev_stop));
+    *flop_out = slic::g_last_flop;
+    return SLIC_OK;
 }
 
 int slic_screen_scores_debug(const uint16_t* q_bf16_dev, int64_t nq, const uint16_t* x_bf16_dev, int64_t n,
