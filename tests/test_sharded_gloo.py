@@ -1,0 +1,52 @@
+"""world_size-2 gloo run of the row-sharded level-0 search (sharded.py) with the numpy stand-in backend:
+shard ranges, padding, the all-gather of ids + distances, and identical partitions on every rank."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tests.golden.make_golden import CASES, make_input
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, name, golden_dir, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tests.fake_backend import FakeBackend
+        from video_similarity_search_b200.sharded import FINCH_sharded, shard_range, sharded_first_neighbors
+        be = FakeBackend()
+        x = make_input(CASES[name])
+        n = len(x)
+        r0, r1, per = shard_range(n, rank, world)
+        assert per * world >= n and 0 <= r0 <= r1 <= n
+        nn, d, _ = sharded_first_neighbors(be)(be.to_device(x, torch.float32))
+        full_nn, full_d, _ = FakeBackend().first_neighbors(torch.from_numpy(x))
+        assert torch.equal(nn, full_nn) and torch.equal(d, full_d)
+        # only this rank's shard was searched locally
+        assert [c[3] for c in be.calls if c[0] == "first_neighbors"] == [(r0, r1)]
+        c, num_clust, _ = FINCH_sharded(x, backend=FakeBackend(), verbose=False)
+        np.save(os.path.join(out_dir, "c_rank%d.npy" % rank), c)
+        g = np.load(os.path.join(golden_dir, name + ".npz"))
+        assert num_clust == g["num_clust"].tolist() and np.array_equal(c, g["c"])
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name,world", [("gmm_1200x64", 2), ("gmm_777x200_odd", 3)])
+def test_sharded_first_neighbors_and_finch_under_gloo(tmp_path, golden_dir, name, world):
+    mp.spawn(_worker, args=(world, _free_port(), name, golden_dir, str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(tmp_path / ("c_rank%d.npy" % r)) for r in range(world)]
+    assert all(np.array_equal(parts[0], p) for p in parts[1:])

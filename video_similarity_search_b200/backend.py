@@ -50,7 +50,15 @@ class CudaBackend:
         return torch.empty(shape, dtype=dtype, device=self.device)
 
     def to_host(self, t):
-        return t.cpu().numpy()
+        """Device -> numpy through a pinned staging buffer (a pageable D2H of the [N, P] label matrix costs
+        milliseconds; pinned it is PCIe-bound)."""
+        if t.numel() * t.element_size() < (1 << 16):
+            return t.cpu().numpy()
+        t = t.contiguous()
+        stage = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        stage.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return stage.numpy().copy()
 
     # -- K1 --------------------------------------------------------------------------------------
     def normalize_rows(self, x, want_bf16=True):

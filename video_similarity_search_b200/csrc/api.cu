@@ -59,6 +59,16 @@ int slic_require_device(void) {
         slic::set_error("device %d has compute capability %d.x; the kernels are built for sm_100a only", dev, major);
         return SLIC_ERR_NO_DEVICE;
     }
+    // keep the stream-ordered pool's memory across synchronisations: the default threshold (0) hands every
+    // temporary back to the OS at each sync, which costs milliseconds per FINCH level
+    static bool pool_ready[64] = {false};
+    if (dev < 64 && !pool_ready[dev]) {
+        cudaMemPool_t pool;
+        SLIC_CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t keep = UINT64_MAX;
+        SLIC_CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        pool_ready[dev] = true;
+    }
     return SLIC_OK;
 }
 

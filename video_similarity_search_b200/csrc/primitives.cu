@@ -106,9 +106,18 @@ int exclusive_scan_i32(const int* in, int* out, int64_t n, int* total_out, cudaS
 // ------------------------------------------------------------------------------------------
 // histogram of int32 keys in [0, bins)
 // ------------------------------------------------------------------------------------------
+// Warp-aggregated: lanes holding the same key elect one leader that adds the group's size, so a label array
+// with few distinct values (the coarse FINCH levels) does not serialise on a handful of addresses.
 __global__ void histogram_kernel(const int* __restrict__ keys, int64_t n, int* __restrict__ counts) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        atomicAdd(&counts[keys[i]], 1);
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n_round = (n + 31) / 32 * 32;  // keep whole warps in the loop for the match
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        const bool valid = i < n;
+        const int key = valid ? keys[i] : -1 - lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (valid && (__ffs(peers) - 1) == lane) atomicAdd(&counts[key], __popc(peers));
+    }
 }
 
 int histogram_i32(const int* keys, int64_t n, int* counts, int64_t bins, cudaStream_t st) {

@@ -92,20 +92,36 @@ __global__ void __launch_bounds__(SM_THREADS) segmean_chunk_kernel(const float* 
     }
 }
 
-// clusters that span several chunks: add the partial sums in chunk order, divide by the count
-__global__ void __launch_bounds__(SM_THREADS) segmean_finalize_kernel(const int* __restrict__ offsets,
-                                                                      const int* __restrict__ chunk_base,
-                                                                      int num_clust, int d,
-                                                                      const double* __restrict__ partial,
-                                                                      double* __restrict__ out) {
+// clusters that span several chunks: add the partial sums, divide by the count.  One CTA owns FIN_COLS
+// columns of one cluster; its FIN_LANES thread rows each add every FIN_LANES-th chunk (fixed order), then the
+// lanes are combined by a fixed-order shared-memory tree - deterministic and parallel over (cluster, column
+// tile, lane) instead of one serial chain per cluster.
+constexpr int FIN_COLS = 8, FIN_LANES = 32;
+
+__global__ void __launch_bounds__(FIN_COLS * FIN_LANES) segmean_finalize_kernel(const int* __restrict__ offsets,
+                                                                                const int* __restrict__ chunk_base,
+                                                                                int num_clust, int d,
+                                                                                const double* __restrict__ partial,
+                                                                                double* __restrict__ out) {
+    __shared__ double red[FIN_LANES][FIN_COLS];
     const int c = blockIdx.x;
     const int first = chunk_base[c], n_chunks = chunk_base[c + 1] - first;
     if (n_chunks <= 1) return;
+    const int cx = threadIdx.x % FIN_COLS, ly = threadIdx.x / FIN_COLS;
     const double cnt = (double)(offsets[c + 1] - offsets[c]);
-    for (int k = threadIdx.x; k < d; k += SM_THREADS) {
+    for (int k0 = blockIdx.y * FIN_COLS; k0 < d; k0 += gridDim.y * FIN_COLS) {
+        const int k = k0 + cx;
         double a = 0;
-        for (int j = 0; j < n_chunks; ++j) a += partial[(int64_t)(first + j) * d + k];
-        out[(int64_t)c * d + k] = a / cnt;
+        if (k < d)
+            for (int j = ly; j < n_chunks; j += FIN_LANES) a += partial[(int64_t)(first + j) * d + k];
+        red[ly][cx] = a;
+        __syncthreads();
+        for (int s = FIN_LANES / 2; s > 0; s >>= 1) {
+            if (ly < s) red[ly][cx] += red[ly + s][cx];
+            __syncthreads();
+        }
+        if (ly == 0 && k < d) out[(int64_t)c * d + k] = red[0][cx] / cnt;
+        __syncthreads();
     }
 }
 
@@ -141,8 +157,13 @@ extern "C" int slic_segmented_mean(const float* data_dev, const int32_t* labels_
             data_dev, order.as<int>(), offsets.as<int>(), chunk_base.as<int>(), num_clust, d, out_dev,
             partial.as<double>());
     SLIC_LAUNCH_OK();
-    segmean_finalize_kernel<<<(unsigned)num_clust, SM_THREADS, 0, st>>>(offsets.as<int>(), chunk_base.as<int>(),
-                                                                       num_clust, d, partial.as<double>(), out_dev);
+    {
+        int col_tiles = (d + FIN_COLS - 1) / FIN_COLS;
+        if (col_tiles > 64) col_tiles = 64;
+        dim3 grid((unsigned)num_clust, (unsigned)col_tiles);
+        segmean_finalize_kernel<<<grid, FIN_COLS * FIN_LANES, 0, st>>>(offsets.as<int>(), chunk_base.as<int>(), num_clust, d,
+                                                                       partial.as<double>(), out_dev);
+    }
     SLIC_LAUNCH_OK();
     return SLIC_OK;
 }
