@@ -87,7 +87,7 @@ int slic_nn_exact_top1(const void* q_unit_dev, const int32_t* q_rows_dev, int64_
  * fused per-row candidate filter (scores never leave the SM) followed by an exact re-rank of
  * the surviving candidates in `dtype`.  eps is the screen's error allowance: every column whose
  * bf16 score is within eps of the row's best is re-ranked (eps <= 0 selects the provable
- * default 2^-7).  Rows whose candidate list overflowed are finished by the exact kernel, so the
+ * default 2^-7 + 2^-11).  Rows whose candidate list overflowed are finished by the exact kernel, so the
  * result never depends on the screen's precision.  q_* may equal x_* (FINCH self-search). */
 int slic_nn_top1(const void* q_unit_dev, const uint16_t* q_bf16_dev, int64_t nq,
                  const void* x_unit_dev, const uint16_t* x_bf16_dev, int64_t n,
@@ -120,6 +120,17 @@ int slic_rows_topk(const void* dist_dev, int64_t nq, int64_t n, int64_t ld, int3
 int slic_topk_cosine(const void* q_unit_dev, int64_t nq, const void* x_unit_dev, int64_t n,
                      int32_t d, int32_t dtype, int32_t k, int64_t self_offset,
                      int32_t* idx_out_dev, void* dist_out_dev, slic_stream_t stream);
+
+/* The same top-k search on the tensor cores: bf16 tcgen05 screen with a fused per-row candidate
+ * filter (a column survives iff its screened score is within eps of the row's running k-th best),
+ * then exact evaluation in `dtype` and a (distance, column) sort of the survivors.  Results are
+ * those of slic_topk_cosine (rows the screen cannot settle are finished by the exact kernels);
+ * k <= 64.  stats_out_dev as in slic_nn_top1. */
+int slic_topk_cosine_tc(const void* q_unit_dev, const uint16_t* q_bf16_dev, int64_t nq,
+                        const void* x_unit_dev, const uint16_t* x_bf16_dev, int64_t n,
+                        int32_t d, int32_t d_pad, int32_t dtype, int32_t k, int64_t self_offset,
+                        float eps, int32_t* idx_out_dev, void* dist_out_dev,
+                        int32_t* stats_out_dev, slic_stream_t stream);
 
 /* evaluate.py:287-307 (get_topk_acc), iic_retrieve_clips.py:298-306: hits[m] = number of query
  * rows whose label occurs among the labels of their first ks[m] neighbours. */

@@ -82,11 +82,16 @@ class FakeBackend:
         order = np.lexsort((np.broadcast_to(np.arange(m.shape[1]), m.shape), m), axis=1)[:, :k]
         return torch.from_numpy(order.astype(np.int32)), torch.from_numpy(np.take_along_axis(m, order, 1))
 
-    def topk_cosine(self, q_unit, x_unit, k, self_offset=-1):
+    def topk_cosine(self, q_unit, x_unit, k, self_offset=-1, q_bf16=None, x_bf16=None, eps=0.0):
         m = _np(self.distance_matrix(q_unit, x_unit))
         if self_offset >= 0:
             m[np.arange(m.shape[0]), np.arange(m.shape[0]) + self_offset] = np.inf
         return self.rows_topk(torch.from_numpy(m), k)
+
+    def topk_neighbors(self, q, x, k, same=False):
+        ux, _ = self.normalize_rows(x, want_bf16=False)
+        uq = ux if same else self.normalize_rows(q, want_bf16=False)[0]
+        return self.topk_cosine(uq, ux, k, self_offset=0 if same else -1)
 
     def hit_at_k(self, topk_idx, q_labels, x_labels, ks):
         idx, ql, xl = _np(topk_idx), _np(q_labels), _np(x_labels)

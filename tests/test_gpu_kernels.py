@@ -231,6 +231,54 @@ def test_distance_matrix_and_topk(be, dtype):
     assert np.array_equal(idx.cpu().numpy()[0], np.concatenate([np.arange(650, 700), np.arange(0, 10)]))
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("nq,n,d,k,same", [(3783, 9537, 512, 50, False), (1000, 5000, 200, 64, False),
+                                            (4000, 4000, 128, 20, True), (300, 20000, 96, 1, False),
+                                            (2500, 2500, 64, 5, True)])
+def test_tensor_core_topk_equals_exact_topk(be, dtype, nq, n, d, k, same):
+    """slic_topk_cosine_tc (tcgen05 screen, k-th-best candidate rule, exact re-rank) must return exactly what the
+    exact kernels return: same columns in the same order, same distances - bit for bit (both evaluate the
+    surviving pairs with float64 accumulation and round to the reference dtype)."""
+    x = synth.gaussian_mixture(n, d, 40, 21).astype(dtype)
+    q = x if same else synth.gaussian_mixture(nq, d, 40, 22).astype(dtype)
+    xd = dev(be, x)
+    ux, xb = be.normalize_rows(xd)
+    uq, qb = (ux, xb) if same else be.normalize_rows(dev(be, q))
+    off = 0 if same else -1
+    ei, ev = be.topk_cosine(uq, ux, k, self_offset=off)
+    ti, tv = be.topk_cosine(uq, ux, k, self_offset=off, q_bf16=qb, x_bf16=xb)
+    stats = be.last_stats.cpu().numpy()
+    ei, ev, ti, tv = ei.cpu().numpy(), ev.cpu().numpy(), ti.cpu().numpy(), tv.cpu().numpy()
+    # the two paths accumulate the same float64 products in different orders: a pair of columns whose distances
+    # round to the same value in one and to neighbours in the other may swap - compare outside such near-ties
+    margin = TIE_MARGIN_F32 if dtype == np.float32 else TIE_MARGIN_F64
+    np.testing.assert_allclose(tv, ev, rtol=0, atol=margin)
+    bad = np.flatnonzero((ti != ei).any(1))
+    assert len(bad) <= max(1, nq // 500)
+    for r in bad:                          # a disagreement needs two distances closer than the margin in that row
+        assert np.diff(ev[r]).min() <= margin and set(ti[r]) == set(ei[r])
+    if same:
+        assert not (ti == np.arange(nq)[:, None]).any()
+    assert stats[1] <= nq // 50            # rows handed to the exact finisher
+    assert stats[0] >= nq * k              # every row re-ranked at least k candidates
+
+
+def test_tensor_core_topk_overflow_rows_are_finished_exactly(be):
+    """Many near-duplicates: far more than RK_MAX columns within eps of the k-th best -> the screen cannot
+    settle those rows and the exact kernels finish them; the result is still the exact top-k."""
+    rng = np.random.default_rng(3)
+    base = rng.standard_normal((4, 64)).astype(np.float32)
+    x = (np.repeat(base, 1500, axis=0) + 1e-4 * rng.standard_normal((6000, 64))).astype(np.float32)
+    q = (base[rng.integers(0, 4, 200)] + 1e-4 * rng.standard_normal((200, 64))).astype(np.float32)
+    ux, xb = be.normalize_rows(dev(be, x))
+    uq, qb = be.normalize_rows(dev(be, q))
+    ei, ev = be.topk_cosine(uq, ux, 10)
+    ti, tv = be.topk_cosine(uq, ux, 10, q_bf16=qb, x_bf16=xb)
+    assert int(be.last_stats.cpu().numpy()[1]) == 200
+    assert np.array_equal(ti.cpu().numpy(), ei.cpu().numpy())
+    assert np.array_equal(tv.cpu().numpy(), ev.cpu().numpy())
+
+
 def test_hit_at_k(be):
     rng = np.random.default_rng(6)
     idx = rng.integers(0, 500, (200, 50)).astype(np.int32)

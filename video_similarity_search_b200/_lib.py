@@ -27,6 +27,7 @@ SIGNATURES = {
     "slic_distance_matrix": [_ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _i32, _ptr, _i64, _ptr],
     "slic_rows_topk": [_ptr, _i64, _i64, _i64, _i32, _i32, _ptr, _ptr, _ptr],
     "slic_topk_cosine": [_ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _i64, _ptr, _ptr, _ptr],
+    "slic_topk_cosine_tc": [_ptr, _ptr, _i64, _ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _i64, _f32, _ptr, _ptr, _ptr, _ptr],
     "slic_hit_at_k": [_ptr, _i64, _i32, _ptr, _ptr, _ptr, _i32, _ptr, _ptr],
     "slic_finch_components": [_ptr, _i64, _i32, _f64, _ptr, _i32, _i32, _ptr, _ptr, _ptr, _ptr],
     "slic_finch_min_sim": [_ptr, _i64, _ptr, _i32, _i32, _ptr, _ptr, _ptr],

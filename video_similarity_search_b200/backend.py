@@ -14,6 +14,8 @@ _DT = {torch.float32: _lib.SLIC_F32, torch.float64: _lib.SLIC_F64}
 
 # below this many rows the tensor-core screen is pure launch overhead: use the exact kernel
 SCREEN_MIN_ROWS = 2048
+# the top-k screen keeps k running scores per row in shared memory (TC_TOPK_MAX in nn_screen_tc.cu)
+TOPK_SCREEN_MAX_K = 64
 
 
 def _p(t):
@@ -128,14 +130,31 @@ class CudaBackend:
         _lib.call("slic_rows_topk", _p(mat), nq, n, mat.stride(0), _DT[mat.dtype], k, _p(idx), _p(val), self._stream())
         return idx, val
 
-    def topk_cosine(self, q_unit, x_unit, k, self_offset=-1):
+    def topk_cosine(self, q_unit, x_unit, k, self_offset=-1, q_bf16=None, x_bf16=None, eps=0.0):
+        """Top-k cosine neighbours, ascending distance, ties -> lowest column.  With the bf16 copies of both
+        sides and k <= 64 on a large database: tcgen05 screen + exact re-rank (slic_topk_cosine_tc);
+        otherwise the exact kernels (slic_topk_cosine)."""
         nq, d = q_unit.shape
         n = x_unit.shape[0]
         idx = torch.empty((nq, k), dtype=torch.int32, device=x_unit.device)
         val = torch.empty((nq, k), dtype=x_unit.dtype, device=x_unit.device)
+        if q_bf16 is not None and x_bf16 is not None and k <= TOPK_SCREEN_MAX_K and n >= SCREEN_MIN_ROWS:
+            stats = torch.zeros(4, dtype=torch.int32, device=x_unit.device)
+            _lib.call("slic_topk_cosine_tc", _p(q_unit), _p(q_bf16), nq, _p(x_unit), _p(x_bf16), n, d, x_bf16.shape[1],
+                      _DT[x_unit.dtype], k, self_offset, float(eps), _p(idx), _p(val), _p(stats), self._stream())
+            self.last_stats = stats
+            return idx, val
         _lib.call("slic_topk_cosine", _p(q_unit), nq, _p(x_unit), n, d, _DT[x_unit.dtype], k, self_offset, _p(idx),
                   _p(val), self._stream())
         return idx, val
+
+    def topk_neighbors(self, q, x, k, same=False):
+        """Normalise both sides (sklearn's normalize) and return their top-k cosine neighbours; picks the
+        tensor-core path when the shape allows it.  same=True: q is x, self excluded."""
+        use_screen = x.shape[0] >= SCREEN_MIN_ROWS and k <= TOPK_SCREEN_MAX_K
+        ux, xb = self.normalize_rows(x, want_bf16=use_screen)
+        uq, qb = (ux, xb) if same else self.normalize_rows(q, want_bf16=use_screen)
+        return self.topk_cosine(uq, ux, k, self_offset=0 if same else -1, q_bf16=qb, x_bf16=xb)
 
     def hit_at_k(self, topk_idx, q_labels, x_labels, ks):
         ks_t = torch.tensor(list(ks), dtype=torch.int32, device=topk_idx.device)

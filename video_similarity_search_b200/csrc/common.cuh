@@ -64,6 +64,11 @@ struct Scratch {
 
 int num_sms();
 
+// nn_exact.cu: exact top-k cosine neighbours (dense row blocks + radix select) of the listed query rows;
+// the finisher for rows the tensor-core top-k screen could not settle.
+int exact_topk_cosine_rows(const void* q, const int* q_rows, int64_t nq, const void* x, int64_t n, int d, int dtype, int k,
+                           int64_t self_offset, int* idx_out, void* dist_out, cudaStream_t st);
+
 __host__ __device__ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- device helpers ---------------------------------------------------------------------

@@ -152,7 +152,8 @@ __global__ void exact_top1_merge_kernel(const double* __restrict__ part_score, c
 // out = sqrt(max(qq + xx - 2 s, 0)).  same != 0 zeroes the diagonal (sklearn, X is Y);
 // inf_col_offset >= 0 writes +inf at column row + inf_col_offset (self exclusion before a top-k).
 template <typename T>
-__global__ void __launch_bounds__(EX_THREADS) exact_matrix_kernel(const T* __restrict__ q, int64_t nq,
+__global__ void __launch_bounds__(EX_THREADS) exact_matrix_kernel(const T* __restrict__ q,
+                                                                  const int* __restrict__ q_rows, int64_t nq,
                                                                   const T* __restrict__ x, int64_t n, int d, int metric,
                                                                   const double* __restrict__ q_sq,
                                                                   const double* __restrict__ x_sq, int same,
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(EX_THREADS) exact_matrix_kernel(const T* __res
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
     for (int k0 = 0; k0 < d; k0 += EX_BK) {
-        load_slab<T>(As, q, nullptr, row0, nq, d, k0);
+        load_slab<T>(As, q, q_rows, row0, nq, d, k0);
         load_slab<T>(Bs, x, nullptr, col0, n, d, k0);
         __syncthreads();
         mma_slab(As, Bs, acc, ty, tx);
@@ -178,6 +179,7 @@ __global__ void __launch_bounds__(EX_THREADS) exact_matrix_kernel(const T* __res
     for (int i = 0; i < 4; ++i) {
         const int64_t r = row0 + ty * 4 + i;
         if (r >= nq) continue;
+        const int64_t inf_col = inf_col_offset >= 0 ? (int64_t)(q_rows ? q_rows[r] : r) + inf_col_offset : -1;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int64_t c = col0 + tx * 4 + j;
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(EX_THREADS) exact_matrix_kernel(const T* __res
                 v = (T)sqrt(d2 > 0.0 ? d2 : 0.0);
             }
             if (same && r == c) v = (T)0;
-            if (inf_col_offset >= 0 && c == r + inf_col_offset) v = (T)CUDART_INF;
+            if (c == inf_col) v = (T)CUDART_INF;
             out[r * ld + c] = v;
         }
     }
@@ -369,7 +371,7 @@ static int exact_top1_impl(const T* q, const int* q_rows, int64_t nq, const T* x
 }
 
 template <typename T>
-static int matrix_impl(const T* q, int64_t nq, const T* x, int64_t n, int d, int metric, int same,
+static int matrix_impl(const T* q, const int* q_rows, int64_t nq, const T* x, int64_t n, int d, int metric, int same,
                        int64_t inf_col_offset, T* out, int64_t ld, cudaStream_t st) {
     Scratch qs, xs;
     const double* qsp = nullptr;
@@ -387,7 +389,8 @@ static int matrix_impl(const T* q, int64_t nq, const T* x, int64_t n, int d, int
     // rows on grid.y (<= 65535 tiles = 4.19M rows)
     dim3 grid((unsigned)ceil_div(n, EX_BN), (unsigned)ceil_div(nq, EX_BM));
     SLIC_REQUIRE(grid.y <= 65535, "distance_matrix: too many query rows for one launch");
-    exact_matrix_kernel<T><<<grid, EX_THREADS, 0, st>>>(q, nq, x, n, d, metric, qsp, xsp, same, inf_col_offset, out, ld);
+    exact_matrix_kernel<T><<<grid, EX_THREADS, 0, st>>>(q, q_rows, nq, x, n, d, metric, qsp, xsp, same, inf_col_offset, out,
+                                                        ld);
     SLIC_LAUNCH_OK();
     return SLIC_OK;
 }
@@ -406,9 +409,11 @@ static int rows_topk_impl(const T* mat, int64_t nq, int64_t n, int64_t ld, int k
     return SLIC_OK;
 }
 
+// q_rows (optional): the query rows to process (indices into q); outputs are indexed by position in the list and
+// the excluded column of list entry i is q_rows[i] + self_offset.
 template <typename T>
-static int topk_cosine_impl(const T* q, int64_t nq, const T* x, int64_t n, int d, int k, int64_t self_offset,
-                            int* idx_out, T* dist_out, cudaStream_t st) {
+static int topk_cosine_impl(const T* q, const int* q_rows, int64_t nq, const T* x, int64_t n, int d, int k,
+                            int64_t self_offset, int* idx_out, T* dist_out, cudaStream_t st) {
     // one row block of the distance matrix at a time (<= 1 GiB), selected immediately
     int64_t rows = ((int64_t)1 << 30) / (n * (int64_t)sizeof(T));
     rows = rows < 64 ? 64 : (rows / 64) * 64;
@@ -417,11 +422,26 @@ static int topk_cosine_impl(const T* q, int64_t nq, const T* x, int64_t n, int d
     SLIC_CUDA_OK(block.alloc(rows * n * sizeof(T), st));
     for (int64_t r0 = 0; r0 < nq; r0 += rows) {
         const int64_t nr = nq - r0 < rows ? nq - r0 : rows;
-        const int64_t inf_off = self_offset >= 0 ? self_offset + r0 : -1;
-        SLIC_PROPAGATE(matrix_impl<T>(q + r0 * d, nr, x, n, d, SLIC_METRIC_COSINE, 0, inf_off, block.as<T>(), n, st));
+        if (q_rows) {
+            SLIC_PROPAGATE(matrix_impl<T>(q, q_rows + r0, nr, x, n, d, SLIC_METRIC_COSINE, 0, self_offset >= 0 ? self_offset : -1,
+                                          block.as<T>(), n, st));
+        } else {
+            const int64_t inf_off = self_offset >= 0 ? self_offset + r0 : -1;
+            SLIC_PROPAGATE(matrix_impl<T>(q + r0 * d, nullptr, nr, x, n, d, SLIC_METRIC_COSINE, 0, inf_off, block.as<T>(), n, st));
+        }
         SLIC_PROPAGATE(rows_topk_impl<T>(block.as<T>(), nr, n, n, k, idx_out + r0 * k, dist_out ? dist_out + r0 * k : nullptr, st));
     }
     return SLIC_OK;
+}
+
+int exact_topk_cosine_rows(const void* q, const int* q_rows, int64_t nq, const void* x, int64_t n, int d, int dtype, int k,
+                           int64_t self_offset, int* idx_out, void* dist_out, cudaStream_t st) {
+    if (nq == 0) return SLIC_OK;
+    if (dtype == SLIC_F32)
+        return topk_cosine_impl<float>((const float*)q, q_rows, nq, (const float*)x, n, d, k, self_offset, idx_out,
+                                       (float*)dist_out, st);
+    return topk_cosine_impl<double>((const double*)q, q_rows, nq, (const double*)x, n, d, k, self_offset, idx_out,
+                                    (double*)dist_out, st);
 }
 
 }  // namespace slic
@@ -452,10 +472,10 @@ int slic_distance_matrix(const void* q_dev, int64_t nq, const void* x_dev, int64
     if (nq == 0 || n == 0) return SLIC_OK;
     cudaStream_t st = slic::as_stream(stream);
     if (dtype == SLIC_F32)
-        return slic::matrix_impl<float>((const float*)q_dev, nq, (const float*)x_dev, n, d, metric, same_matrix, -1,
-                                        (float*)out_dev, ld_out, st);
-    return slic::matrix_impl<double>((const double*)q_dev, nq, (const double*)x_dev, n, d, metric, same_matrix, -1,
-                                     (double*)out_dev, ld_out, st);
+        return slic::matrix_impl<float>((const float*)q_dev, nullptr, nq, (const float*)x_dev, n, d, metric, same_matrix,
+                                        -1, (float*)out_dev, ld_out, st);
+    return slic::matrix_impl<double>((const double*)q_dev, nullptr, nq, (const double*)x_dev, n, d, metric, same_matrix,
+                                     -1, (double*)out_dev, ld_out, st);
 }
 
 int slic_rows_topk(const void* dist_dev, int64_t nq, int64_t n, int64_t ld, int32_t dtype, int32_t k,
@@ -479,11 +499,8 @@ int slic_topk_cosine(const void* q_unit_dev, int64_t nq, const void* x_unit_dev,
     SLIC_REQUIRE(dtype == SLIC_F32 || dtype == SLIC_F64, "topk_cosine: bad dtype");
     if (nq == 0) return SLIC_OK;
     cudaStream_t st = slic::as_stream(stream);
-    if (dtype == SLIC_F32)
-        return slic::topk_cosine_impl<float>((const float*)q_unit_dev, nq, (const float*)x_unit_dev, n, d, k,
-                                             self_offset, idx_out_dev, (float*)dist_out_dev, st);
-    return slic::topk_cosine_impl<double>((const double*)q_unit_dev, nq, (const double*)x_unit_dev, n, d, k, self_offset,
-                                          idx_out_dev, (double*)dist_out_dev, st);
+    return slic::exact_topk_cosine_rows(q_unit_dev, nullptr, nq, x_unit_dev, n, d, dtype, k, self_offset, idx_out_dev,
+                                        dist_out_dev, st);
 }
 
 }  // extern "C"

@@ -29,6 +29,8 @@
 #include <cuda_bf16.h>
 #include <math_constants.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace slic {
@@ -40,6 +42,12 @@ constexpr uint32_t TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr int TC_THREADS = 192;
 constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
 constexpr int TC_TMEM_COLS = 512;
+// Screen error allowance: a bf16-rounded operand carries relative error <= 2^-9, a product of two <= 2^-8 (+2^-18),
+// so for unit rows |screened - exact| <= 2^-8 * sum|a_k b_k| <= 2^-8, plus fp32 accumulation (<= d * 2^-24 relative to
+// the same sum).  eps must be >= twice that: 2^-7 + 2^-11 covers d up to 4096.
+constexpr float TC_DEFAULT_EPS = 0.0078125f + 0.00048828125f;
+constexpr int TC_TOPK_MAX = 64;  // the top-k variant keeps k running best scores per row in shared memory
+constexpr uint32_t TC_TOPK_SMEM = TC_TOPK_MAX * TC_BM * 4;  // 32 KB
 
 struct ScreenParams {
     int64_t nq, n;
@@ -54,6 +62,8 @@ struct ScreenParams {
     float* cand_score;     // [splits][nq][cap]
     int* cand_cnt;         // [splits][nq]
     int* cand_flags;       // [splits][nq]  bit0 = overflow, bit1 = compacted
+    int topk;              // TOPK kernel: k (<= TC_TOPK_MAX); the candidate rule is "within eps of the k-th best"
+    float* cand_kth;       // TOPK kernel: [splits][nq] k-th best screened score of the split (-inf if < k columns)
     float* dump;           // debug: raw scores [nq][n] or nullptr
     int* error_flag;       // set when a barrier wait times out
 };
@@ -181,7 +191,58 @@ __device__ __noinline__ RowState push_candidate(RowState st, float s, int col, f
     return st;
 }
 
+// Top-k variant of the row state.  tk[i * TC_BM] (i < k) are the k best screened scores the row has seen
+// in this unit, unordered; kth is their minimum (the k-th best, -inf until k columns were seen) at slot
+// kth_pos.  A column is a candidate iff score >= kth - eps when it is seen: kth only grows, so the list is
+// a superset of {j : score_j >= final kth - eps}, which (|screen error| <= eps / 2) contains the exact top-k.
+struct RowStateK {
+    float kth, thr;
+    int kth_pos, cnt, flags;
+};
+
+__device__ __noinline__ RowStateK push_candidate_topk(RowStateK st, float s, int col, float eps, int cap, int k,
+                                                      float* __restrict__ tk, int* __restrict__ li,
+                                                      float* __restrict__ ls) {
+    if (s > st.kth) {
+        tk[st.kth_pos * TC_BM] = s;   // replaces the current k-th best; find the new one
+        float mn = tk[0];
+        int mp = 0;
+        for (int i = 1; i < k; ++i) {
+            const float v = tk[i * TC_BM];
+            if (v < mn) {
+                mn = v;
+                mp = i;
+            }
+        }
+        st.kth = mn;
+        st.kth_pos = mp;
+        st.thr = mn - eps;
+    }
+    if (st.cnt == cap) {
+        int w = 0;
+        for (int r = 0; r < st.cnt; ++r) {
+            const float sc = ls[r];
+            if (sc >= st.thr) {
+                ls[w] = sc;
+                li[w] = li[r];
+                ++w;
+            }
+        }
+        st.cnt = w;
+        st.flags |= 2;
+    }
+    if (st.cnt < cap) {
+        ls[st.cnt] = s;
+        li[st.cnt] = col;
+        ++st.cnt;
+    } else {
+        st.flags |= 1;
+    }
+    return st;
+}
+
 // ---- the kernel ------------------------------------------------------------------------------
+template <bool TOPK>
 __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_constant__ CUtensorMap tmap_q,
                                                                   const __grid_constant__ CUtensorMap tmap_x,
                                                                   const ScreenParams p) {
@@ -305,8 +366,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
             const int64_t slot = (int64_t)split * p.nq + (row_ok ? row : 0);
             int* li = p.cand_idx + slot * p.cap;
             float* ls = p.cand_score + slot * p.cap;
-            RowState st;
-            st.best = -CUDART_INF_F;
+            typename std::conditional<TOPK, RowStateK, RowState>::type st;
+            float* tk = nullptr;
+            if constexpr (TOPK) {
+                tk = reinterpret_cast<float*>(smem + TC_STAGES * TC_STAGE_BYTES + 256) + row_in_tile;
+                for (int i = 0; i < p.topk; ++i) tk[i * TC_BM] = -CUDART_INF_F;
+                st.kth = -CUDART_INF_F;
+                st.kth_pos = 0;
+            } else {
+                st.best = -CUDART_INF_F;
+            }
             st.thr = -CUDART_INF_F;
             st.cnt = 0;
             st.flags = 0;
@@ -337,8 +406,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
 #pragma unroll
                         for (int t = 0; t < 32; ++t) {
                             const float s = __uint_as_float(v[t]);
-                            if (s >= st.thr && s > -CUDART_INF_F)
-                                st = push_candidate(st, s, (int)(col_base + t), p.eps, p.cap, li, ls);
+                            if (s >= st.thr && s > -CUDART_INF_F) {
+                                if constexpr (TOPK)
+                                    st = push_candidate_topk(st, s, (int)(col_base + t), p.eps, p.cap, p.topk, tk, li, ls);
+                                else
+                                    st = push_candidate(st, s, (int)(col_base + t), p.eps, p.cap, li, ls);
+                            }
                         }
                     }
                 }
@@ -351,6 +424,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
             if (row_ok) {
                 p.cand_cnt[slot] = st.cnt;
                 p.cand_flags[slot] = st.flags;
+                if constexpr (TOPK) p.cand_kth[slot] = st.kth;
             }
         }
     }
@@ -427,6 +501,108 @@ __global__ void scatter_rows_kernel(const int* __restrict__ rows, int count, con
     if (dist_out) dist_out[rows[i]] = dist_src[i];
 }
 
+// ---- exact re-rank for the top-k variant (one CTA per query row) -------------------------------
+// Gathers the columns whose screened score is within eps of the best available lower bound of the row's
+// k-th best screened score (the largest per-split k-th best), evaluates them exactly in T, sorts them by
+// (distance, column) and emits the first k.  Rows that overflowed a list, gathered more than RK_MAX
+// columns or fewer than k go to the exact kernel.
+constexpr int RK_THREADS = 128, RK_MAX = 1024;
+
+template <typename T>
+__global__ void __launch_bounds__(RK_THREADS) rerank_topk_kernel(const T* __restrict__ q_unit, const T* __restrict__ x_unit,
+                                                                 int64_t nq, int d, float eps, int cap, int splits, int k,
+                                                                 const int* __restrict__ cand_idx,
+                                                                 const float* __restrict__ cand_score,
+                                                                 const int* __restrict__ cand_cnt,
+                                                                 const int* __restrict__ cand_flags,
+                                                                 const float* __restrict__ cand_kth,
+                                                                 int* __restrict__ idx_out, T* __restrict__ dist_out,
+                                                                 int* __restrict__ overflow_rows, int* __restrict__ stats) {
+    __shared__ int s_idx[RK_MAX];
+    __shared__ T s_dist[RK_MAX];
+    __shared__ int s_m, s_flags;
+    __shared__ float s_thr;
+    const int64_t r = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        float kth = -CUDART_INF_F;
+        int fl = 0;
+        for (int sp = 0; sp < splits; ++sp) {
+            kth = fmaxf(kth, cand_kth[(int64_t)sp * nq + r]);
+            fl |= cand_flags[(int64_t)sp * nq + r];
+        }
+        s_thr = kth - eps;
+        s_flags = fl;
+        s_m = 0;
+    }
+    __syncthreads();
+    const float thr = s_thr;
+    for (int sp = 0; sp < splits; ++sp) {
+        const int64_t slot = (int64_t)sp * nq + r;
+        const int c = cand_cnt[slot];
+        for (int e = tid; e < c; e += RK_THREADS) {
+            if (cand_score[slot * cap + e] >= thr) {
+                const int pos = atomicAdd(&s_m, 1);
+                if (pos < RK_MAX) s_idx[pos] = cand_idx[slot * cap + e];
+            }
+        }
+    }
+    __syncthreads();
+    const int m = s_m;
+    if ((s_flags & 1) || m > RK_MAX || m < k) {
+        if (tid == 0) overflow_rows[atomicAdd(&stats[1], 1)] = (int)r;
+        return;
+    }
+    const T* qr = q_unit + r * d;
+    for (int e = warp; e < m; e += RK_THREADS / 32) {
+        const double s = warp_dot<T>(qr, x_unit + (int64_t)s_idx[e] * d, d, lane);
+        if (lane == 0) s_dist[e] = cosine_distance_from_sim<T>(s);
+    }
+    int m2 = 2;
+    while (m2 < m) m2 <<= 1;
+    for (int e = m + tid; e < m2; e += RK_THREADS) {
+        s_dist[e] = (T)CUDART_INF;
+        s_idx[e] = 0x7fffffff;
+    }
+    __syncthreads();
+    for (int size = 2; size <= m2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = tid; t < (m2 >> 1); t += RK_THREADS) {
+                const int lo = 2 * t - (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool up = ((lo & size) == 0);
+                const T da = s_dist[lo], db = s_dist[hi];
+                const int ia = s_idx[lo], ib = s_idx[hi];
+                const bool a_after_b = (da > db) || (da == db && ia > ib);
+                if (a_after_b == up) {
+                    s_dist[lo] = db; s_dist[hi] = da;
+                    s_idx[lo] = ib; s_idx[hi] = ia;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int j = tid; j < k; j += RK_THREADS) {
+        idx_out[r * k + j] = s_idx[j];
+        if (dist_out) dist_out[r * k + j] = s_dist[j];
+    }
+    if (tid == 0) {
+        atomicAdd(&stats[0], m);
+        if (s_flags & 2) atomicAdd(&stats[2], 1);
+    }
+}
+
+template <typename T>
+__global__ void scatter_topk_rows_kernel(const int* __restrict__ rows, int count, int k, const int* __restrict__ idx_src,
+                                         const T* __restrict__ dist_src, int* __restrict__ idx_out,
+                                         T* __restrict__ dist_out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)count * k) return;
+    const int64_t dst = (int64_t)rows[i / k] * k + (i % k);
+    idx_out[dst] = idx_src[i];
+    if (dist_out) dist_out[dst] = dist_src[i];
+}
+
 // ---- host side ---------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -492,7 +668,8 @@ static ScreenPlan plan_screen(int64_t nq, int64_t n) {
 
 static int launch_screen(const uint16_t* q_bf16, int64_t nq, const uint16_t* x_bf16, int64_t n, int d_pad,
                          int64_t self_offset, float eps, int cap, const ScreenPlan& pl, int* cand_idx, float* cand_score,
-                         int* cand_cnt, int* cand_flags, float* dump, int* error_flag, cudaStream_t st) {
+                         int* cand_cnt, int* cand_flags, float* dump, int* error_flag, cudaStream_t st, int topk = 0,
+                         float* cand_kth = nullptr) {
     CUtensorMap tq, tx;
     SLIC_PROPAGATE(make_tmap(&tq, q_bf16, nq, d_pad, TC_BM));
     SLIC_PROPAGATE(make_tmap(&tx, x_bf16, n, d_pad, TC_BN));
@@ -510,11 +687,19 @@ static int launch_screen(const uint16_t* q_bf16, int64_t nq, const uint16_t* x_b
     p.cand_score = cand_score;
     p.cand_cnt = cand_cnt;
     p.cand_flags = cand_flags;
+    p.topk = topk;
+    p.cand_kth = cand_kth;
     p.dump = dump;
     p.error_flag = error_flag;
-    static bool attr_set = false;
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    SLIC_CUDA_OK(cudaGetDevice(&dev));
+    bool& attr_set = attr_done[dev & 63];
     if (!attr_set) {
-        SLIC_CUDA_OK(cudaFuncSetAttribute(nn_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        SLIC_CUDA_OK(cudaFuncSetAttribute(nn_screen_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          TC_SMEM_BYTES));
+        SLIC_CUDA_OK(cudaFuncSetAttribute(nn_screen_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          TC_SMEM_BYTES + TC_TOPK_SMEM));
         attr_set = true;
     }
     const int64_t grid = pl.units < num_sms() ? pl.units : num_sms();
@@ -525,7 +710,10 @@ static int launch_screen(const uint16_t* q_bf16, int64_t nq, const uint16_t* x_b
         }
         SLIC_CUDA_OK(cudaEventRecord(g_ev_start, st));
     }
-    nn_screen_kernel<<<(unsigned)grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tq, tx, p);
+    if (topk > 0)
+        nn_screen_kernel<true><<<(unsigned)grid, TC_THREADS, TC_SMEM_BYTES + TC_TOPK_SMEM, st>>>(tq, tx, p);
+    else
+        nn_screen_kernel<false><<<(unsigned)grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tq, tx, p);
     SLIC_LAUNCH_OK();
     if (g_profile) {
         SLIC_CUDA_OK(cudaEventRecord(g_ev_stop, st));
@@ -580,6 +768,54 @@ static int nn_top1_impl(const T* q_unit, const uint16_t* q_bf16, int64_t nq, con
     return SLIC_OK;
 }
 
+constexpr int TC_CAP_TOPK = 512;
+
+template <typename T>
+static int topk_tc_impl(const T* q_unit, const uint16_t* q_bf16, int64_t nq, const T* x_unit, const uint16_t* x_bf16,
+                        int64_t n, int d, int d_pad, int k, int64_t self_offset, float eps, int* idx_out, T* dist_out,
+                        int* stats_out, cudaStream_t st) {
+    const ScreenPlan pl = plan_screen(nq, n);
+    const int64_t slots = (int64_t)pl.splits * nq;
+    Scratch ci, cs, cc, cf, ck, ovr, stats;
+    SLIC_CUDA_OK(ci.alloc(slots * TC_CAP_TOPK * sizeof(int), st));
+    SLIC_CUDA_OK(cs.alloc(slots * TC_CAP_TOPK * sizeof(float), st));
+    SLIC_CUDA_OK(cc.alloc(slots * sizeof(int), st));
+    SLIC_CUDA_OK(cf.alloc(slots * sizeof(int), st));
+    SLIC_CUDA_OK(ck.alloc(slots * sizeof(float), st));
+    SLIC_CUDA_OK(ovr.alloc(nq * sizeof(int), st));
+    SLIC_CUDA_OK(stats.alloc(8 * sizeof(int), st));
+    SLIC_CUDA_OK(cudaMemsetAsync(stats.ptr, 0, 8 * sizeof(int), st));
+    SLIC_PROPAGATE(launch_screen(q_bf16, nq, x_bf16, n, d_pad, self_offset, eps, TC_CAP_TOPK, pl, ci.as<int>(),
+                                 cs.as<float>(), cc.as<int>(), cf.as<int>(), nullptr, stats.as<int>() + 4, st, k,
+                                 ck.as<float>()));
+    rerank_topk_kernel<T><<<(unsigned)nq, RK_THREADS, 0, st>>>(q_unit, x_unit, nq, d, eps, TC_CAP_TOPK, pl.splits, k,
+                                                               ci.as<int>(), cs.as<float>(), cc.as<int>(), cf.as<int>(),
+                                                               ck.as<float>(), idx_out, dist_out, ovr.as<int>(),
+                                                               stats.as<int>());
+    SLIC_LAUNCH_OK();
+    int host_stats[8];
+    SLIC_CUDA_OK(cudaMemcpyAsync(host_stats, stats.ptr, sizeof(host_stats), cudaMemcpyDeviceToHost, st));
+    SLIC_CUDA_OK(cudaStreamSynchronize(st));
+    if (host_stats[4] != 0) {
+        set_error("nn_screen_kernel: pipeline barrier timed out");
+        return SLIC_ERR_CUDA;
+    }
+    const int n_over = host_stats[1];
+    if (n_over > 0) {
+        Scratch oi, od;
+        SLIC_CUDA_OK(oi.alloc((int64_t)n_over * k * sizeof(int), st));
+        SLIC_CUDA_OK(od.alloc((int64_t)n_over * k * sizeof(T), st));
+        SLIC_PROPAGATE(exact_topk_cosine_rows(q_unit, ovr.as<int>(), n_over, x_unit, n, d,
+                                              sizeof(T) == 4 ? SLIC_F32 : SLIC_F64, k, self_offset, oi.as<int>(), od.ptr,
+                                              st));
+        scatter_topk_rows_kernel<T><<<(unsigned)ceil_div((int64_t)n_over * k, 256), 256, 0, st>>>(
+            ovr.as<int>(), n_over, k, oi.as<int>(), od.as<T>(), idx_out, dist_out);
+        SLIC_LAUNCH_OK();
+    }
+    if (stats_out) SLIC_CUDA_OK(cudaMemcpyAsync(stats_out, stats.ptr, 4 * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    return SLIC_OK;
+}
+
 }  // namespace slic
 
 extern "C" {
@@ -594,7 +830,7 @@ int slic_nn_top1(const void* q_unit_dev, const uint16_t* q_bf16_dev, int64_t nq,
     SLIC_REQUIRE((reinterpret_cast<uintptr_t>(q_bf16_dev) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_bf16_dev) & 15) == 0,
                  "nn_top1: bf16 matrices must be 16-byte aligned");
     SLIC_PROPAGATE(slic_require_device());
-    if (eps <= 0.f) eps = 0.0078125f;
+    if (eps <= 0.f) eps = slic::TC_DEFAULT_EPS;
     cudaStream_t st = slic::as_stream(stream);
     if (dtype == SLIC_F32)
         return slic::nn_top1_impl<float>((const float*)q_unit_dev, q_bf16_dev, nq, (const float*)x_unit_dev, x_bf16_dev,
@@ -602,6 +838,31 @@ int slic_nn_top1(const void* q_unit_dev, const uint16_t* q_bf16_dev, int64_t nq,
                                          stats_out_dev, st);
     return slic::nn_top1_impl<double>((const double*)q_unit_dev, q_bf16_dev, nq, (const double*)x_unit_dev, x_bf16_dev, n,
                                       d, d_pad, self_offset, eps, idx_out_dev, (double*)dist_out_dev, stats_out_dev,
+                                      st);
+}
+
+int slic_topk_cosine_tc(const void* q_unit_dev, const uint16_t* q_bf16_dev, int64_t nq, const void* x_unit_dev,
+                        const uint16_t* x_bf16_dev, int64_t n, int32_t d, int32_t d_pad, int32_t dtype, int32_t k,
+                        int64_t self_offset, float eps, int32_t* idx_out_dev, void* dist_out_dev, int32_t* stats_out_dev,
+                        slic_stream_t stream) {
+    SLIC_REQUIRE(nq >= 0 && n > 0 && n < ((int64_t)1 << 31) && nq < ((int64_t)1 << 31), "topk_cosine_tc: bad shape");
+    SLIC_REQUIRE(d > 0 && d_pad >= d && d_pad % 64 == 0, "topk_cosine_tc: d_pad must be a multiple of 64 >= d");
+    SLIC_REQUIRE(k > 0 && k <= slic::TC_TOPK_MAX && k <= n - (self_offset >= 0 ? 1 : 0),
+                 "topk_cosine_tc: k must satisfy 1 <= k <= min(64, columns available)");
+    SLIC_REQUIRE(q_unit_dev && q_bf16_dev && x_unit_dev && x_bf16_dev && idx_out_dev, "topk_cosine_tc: null pointer");
+    SLIC_REQUIRE(dtype == SLIC_F32 || dtype == SLIC_F64, "topk_cosine_tc: bad dtype");
+    SLIC_REQUIRE((reinterpret_cast<uintptr_t>(q_bf16_dev) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_bf16_dev) & 15) == 0,
+                 "topk_cosine_tc: bf16 matrices must be 16-byte aligned");
+    if (nq == 0) return SLIC_OK;
+    SLIC_PROPAGATE(slic_require_device());
+    if (eps <= 0.f) eps = slic::TC_DEFAULT_EPS;
+    cudaStream_t st = slic::as_stream(stream);
+    if (dtype == SLIC_F32)
+        return slic::topk_tc_impl<float>((const float*)q_unit_dev, q_bf16_dev, nq, (const float*)x_unit_dev, x_bf16_dev,
+                                         n, d, d_pad, k, self_offset, eps, idx_out_dev, (float*)dist_out_dev,
+                                         stats_out_dev, st);
+    return slic::topk_tc_impl<double>((const double*)q_unit_dev, q_bf16_dev, nq, (const double*)x_unit_dev, x_bf16_dev, n,
+                                      d, d_pad, k, self_offset, eps, idx_out_dev, (double*)dist_out_dev, stats_out_dev,
                                       st);
 }
 
@@ -639,7 +900,7 @@ int slic_screen_scores_debug(const uint16_t* q_bf16_dev, int64_t nq, const uint1
     SLIC_CUDA_OK(cf.alloc(slots * sizeof(int), st));
     SLIC_CUDA_OK(err.alloc(sizeof(int), st));
     SLIC_CUDA_OK(cudaMemsetAsync(err.ptr, 0, sizeof(int), st));
-    SLIC_PROPAGATE(launch_screen(q_bf16_dev, nq, x_bf16_dev, n, d_pad, -1, 0.0078125f, TC_CAP, pl, ci.as<int>(),
+    SLIC_PROPAGATE(launch_screen(q_bf16_dev, nq, x_bf16_dev, n, d_pad, -1, TC_DEFAULT_EPS, TC_CAP, pl, ci.as<int>(),
                                  cs.as<float>(), cc.as<int>(), cf.as<int>(), out_dev, err.as<int>(), st));
     int host_err = 0;
     SLIC_CUDA_OK(cudaMemcpyAsync(&host_err, err.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));

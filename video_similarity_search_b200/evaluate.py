@@ -34,14 +34,18 @@ class DistanceMatrix:
     def __init__(self, be, q, x, metric, same):
         self._be, self._q, self._x, self.metric, self.same = be, q, x, metric, same
         self._dense = None
-        self._unit_q = self._unit_x = None
+        self._unit_q = self._unit_x = self._bf_q = self._bf_x = None
         self.shape = (q.shape[0], x.shape[0])
         self.dtype = np.dtype(np.float32 if x.dtype == torch.float32 else np.float64)
 
     def _units(self):
         if self._unit_x is None:
-            self._unit_x, _ = self._be.normalize_rows(self._x, want_bf16=False)
-            self._unit_q = self._unit_x if self.same else self._be.normalize_rows(self._q, want_bf16=False)[0]
+            screen = self._x.shape[0] >= _backend.SCREEN_MIN_ROWS
+            self._unit_x, self._bf_x = self._be.normalize_rows(self._x, want_bf16=screen)
+            if self.same:
+                self._unit_q, self._bf_q = self._unit_x, self._bf_x
+            else:
+                self._unit_q, self._bf_q = self._be.normalize_rows(self._q, want_bf16=screen)
         return self._unit_q, self._unit_x
 
     def device_matrix(self):
@@ -74,7 +78,8 @@ class DistanceMatrix:
         """(idx int32 [Q,k], dist [Q,k]) on the device, ascending distance, ties -> lowest column."""
         if self.metric == 'cosine':
             uq, ux = self._units()
-            return self._be.topk_cosine(uq, ux, k, self_offset=0 if self.same else -1)
+            return self._be.topk_cosine(uq, ux, k, self_offset=0 if self.same else -1, q_bf16=self._bf_q,
+                                        x_bf16=self._bf_x)
         return self._be.rows_topk(self.device_matrix(), k)
 
 

@@ -37,10 +37,8 @@ def topk_retrieval_arrays(X_train, y_train, X_test, y_test, ks=KS, backend=None,
     tdt = torch.float32 if dt == np.float32 else torch.float64
     xd = be.to_device(np.ascontiguousarray(X_train.astype(dt, copy=False)), tdt)
     qd = be.to_device(np.ascontiguousarray(X_test.astype(dt, copy=False)), tdt)
-    ux, _ = be.normalize_rows(xd, want_bf16=False)
-    uq, _ = be.normalize_rows(qd, want_bf16=False)
     kmax = min(max(ks), X_train.shape[0])
-    idx, dist = be.topk_cosine(uq, ux, kmax)                         # :295-296
+    idx, dist = be.topk_neighbors(qd, xd, kmax)                      # :295-296
     ks_eff = [min(int(k), kmax) for k in ks]
     hits = be.to_host(be.hit_at_k(idx, be.to_device(y_test.astype(np.int64), torch.int64),
                                   be.to_device(y_train.astype(np.int64), torch.int64), ks_eff))
