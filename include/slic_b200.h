@@ -62,6 +62,14 @@ int64_t slic_launch_count(void);
 int slic_profile_screen(int32_t enable);
 int slic_last_screen_time(float* ms_out, double* flop_out);
 
+/* Pipeline trace of the screen kernel (diagnostic): while enabled every launch adds, summed over its CTAs,
+ * [0] cycles the TMA producer waited for a free smem stage, [1] cycles the MMA issuer waited for a free
+ * accumulator (epilogue-bound), [2] for operands (TMA/L2-bound), [3] MMA issuer total, [4] cycles epilogue
+ * warp 0 waited for a complete accumulator (MMA-bound), [5] epilogue warp 0 total, [6] 32-column chunks with
+ * at least one candidate row and [7] chunks examined (top-k variant).  counters_out_host (optional, [8])
+ * receives the counters accumulated so far; they are then reset.  enable = 0 releases the buffer. */
+int slic_screen_trace(int32_t enable, uint64_t* counters_out_host);
+
 /* ---- K1 prep: row normalisation --------------------------------------------------------- */
 /* sklearn cosine_similarity's normalize step behind clustering/finch.py:27, evaluate.py:213,
  * iic_retrieve_clips.py:295:  norm_i = sqrt(sum_k x_ik^2) (0 -> 1),  unit_i = x_i / norm_i in

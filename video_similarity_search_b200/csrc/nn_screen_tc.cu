@@ -27,6 +27,8 @@
 // Bound: tensor pipe.  Algorithmic work 2 * nq * n * d_pad flop; HBM traffic ~ (nq + n) * d_pad * 2 bytes.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <math.h>
+#include <stdlib.h>
 #include <math_constants.h>
 
 #include <type_traits>
@@ -39,15 +41,18 @@ constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 4, TC_UMMA_K = 1
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
 constexpr uint32_t TC_B_BYTES = TC_BN * TC_BK * 2;   // 32 KB
 constexpr uint32_t TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;   // two per TMEM lane quadrant: each takes one 128-column half of every tile
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
 constexpr int TC_TMEM_COLS = 512;
 // Screen error allowance: a bf16-rounded operand carries relative error <= 2^-9, a product of two <= 2^-8 (+2^-18),
 // so for unit rows |screened - exact| <= 2^-8 * sum|a_k b_k| <= 2^-8, plus fp32 accumulation (<= d * 2^-24 relative to
 // the same sum).  eps must be >= twice that: 2^-7 + 2^-11 covers d up to 4096.
 constexpr float TC_DEFAULT_EPS = 0.0078125f + 0.00048828125f;
-constexpr int TC_TOPK_MAX = 64;  // the top-k variant keeps k running best scores per row in shared memory
-constexpr uint32_t TC_TOPK_SMEM = TC_TOPK_MAX * TC_BM * 4;  // 32 KB
+constexpr int TC_TOPK_MAX = 64;  // the top-k variant's per-row score histogram has saturating 8-bit counts: k must stay well below 255
+constexpr int TC_HIST_BINS = 128;
+constexpr int TC_HIST_STRIDE = 2 * TC_BM;   // one histogram per (row, column half)
+constexpr uint32_t TC_TOPK_SMEM = TC_HIST_BINS * TC_HIST_STRIDE;  // 128 bins x 256 epilogue threads x uint8 = 32 KB
 
 struct ScreenParams {
     int64_t nq, n;
@@ -58,14 +63,15 @@ struct ScreenParams {
     int splits;
     int tiles_per_split;   // 256-column tiles per split
     int64_t num_units;     // row blocks * splits
-    int* cand_idx;         // [splits][nq][cap]
-    float* cand_score;     // [splits][nq][cap]
-    int* cand_cnt;         // [splits][nq]
-    int* cand_flags;       // [splits][nq]  bit0 = overflow, bit1 = compacted
+    int* cand_idx;         // [2 * splits][nq][cap]   (stream = split * 2 + column half of the tiles)
+    float* cand_score;     // [2 * splits][nq][cap]
+    int* cand_cnt;         // [2 * splits][nq]
+    int* cand_flags;       // [2 * splits][nq]  bit0 = overflow, bit1 = compacted
     int topk;              // TOPK kernel: k (<= TC_TOPK_MAX); the candidate rule is "within eps of the k-th best"
-    float* cand_kth;       // TOPK kernel: [splits][nq] k-th best screened score of the split (-inf if < k columns)
+    float* cand_kth;       // TOPK kernel: [splits][nq] lower bound of the split's k-th best screened score
     float* dump;           // debug: raw scores [nq][n] or nullptr
     int* error_flag;       // set when a barrier wait times out
+    unsigned long long* trace;  // optional [8] cycle counters summed over CTAs (diagnostic, see slic_screen_trace)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -104,6 +110,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
         }
     }
 }
+// wait + add the stall cycles to a trace slot (only when tracing)
+__device__ __forceinline__ void mbar_wait_traced(uint32_t bar, uint32_t parity, int* error_flag, unsigned long long& acc,
+                                                 bool tracing) {
+    if (!tracing) {
+        mbar_wait(bar, parity, error_flag);
+        return;
+    }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity, error_flag);
+    acc += (unsigned long long)(clock64() - t0);
+}
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -124,18 +141,30 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_load_32cols(uint32_t taddr, uint32_t (&v)[32]) {
+// TMEM -> registers, 32 lanes x 32 columns per warp.  Issue and wait are separate so that the load of the next
+// 32-column chunk is in flight while the current one is filtered; the wait names the registers as in/out operands
+// so that no use of them can be scheduled above it.
+#define SLIC_V32_OUT(v)                                                                                              \
+    "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),     \
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),      \
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),     \
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+#define SLIC_V32_INOUT(v)                                                                                            \
+    "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),     \
+        "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),      \
+        "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),     \
+        "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+__device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
         "%29,%30,%31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : SLIC_V32_OUT(v)
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : SLIC_V32_INOUT(v)::"memory");
 }
 
 // K-major, 128-byte-swizzled operand tile (rows of 64 bf16 = 128 B, 8-row groups 1024 B apart):
@@ -191,33 +220,54 @@ __device__ __noinline__ RowState push_candidate(RowState st, float s, int col, f
     return st;
 }
 
-// Top-k variant of the row state.  tk[i * TC_BM] (i < k) are the k best screened scores the row has seen
-// in this unit, unordered; kth is their minimum (the k-th best, -inf until k columns were seen) at slot
-// kth_pos.  A column is a candidate iff score >= kth - eps when it is seen: kth only grows, so the list is
-// a superset of {j : score_j >= final kth - eps}, which (|screen error| <= eps / 2) contains the exact top-k.
+// Top-k variant of the row state.  Instead of the k running best scores themselves the row keeps a 128-bin
+// histogram of the scores it has seen or listed (shared memory, uint8, h[bin * TC_HIST_STRIDE]; bin b >= 1 covers
+// [b / 128, (b + 1) / 128), bin 0 everything below 2^-7).  tb is the highest bin with at least k listed scores at or
+// above its lower edge, so edge(tb) <= (k-th best screened score so far); cge counts the listed scores in bins
+// >= tb and ctb those in bin tb itself (registers).  Bins above tb hold < k <= 64 entries, so the 8-bit counts
+// cannot wrap where they are read.  A column is a candidate iff score >= edge(tb) - eps when it is seen: edge(tb)
+// only grows, so the list is a superset of {j : score_j >= final k-th best - eps}, which (|screen error| <= eps / 2)
+// contains the exact top-k.  (A row whose k-th best similarity is not positive keeps edge = -1, lists every
+// column, overflows and is finished by the exact kernel.)
 struct RowStateK {
-    float kth, thr;
-    int kth_pos, cnt, flags;
+    float thr;
+    int tb, cge, ctb, cnt, flags;
 };
 
-__device__ __noinline__ RowStateK push_candidate_topk(RowStateK st, float s, int col, float eps, int cap, int k,
-                                                      float* __restrict__ tk, int* __restrict__ li,
-                                                      float* __restrict__ ls) {
-    if (s > st.kth) {
-        tk[st.kth_pos * TC_BM] = s;   // replaces the current k-th best; find the new one
-        float mn = tk[0];
-        int mp = 0;
-        for (int i = 1; i < k; ++i) {
-            const float v = tk[i * TC_BM];
-            if (v < mn) {
-                mn = v;
-                mp = i;
-            }
-        }
-        st.kth = mn;
-        st.kth_pos = mp;
-        st.thr = mn - eps;
+__device__ __forceinline__ int score_bin(float s) {
+    const int b = __float2int_rd(s * (float)TC_HIST_BINS);
+    return min(max(b, 0), TC_HIST_BINS - 1);
+}
+__device__ __forceinline__ float bin_edge(int b) { return b == 0 ? -1.0f : (float)b * (1.0f / (float)TC_HIST_BINS); }
+
+// count one listed score; returns true when tb may have to advance
+__device__ __forceinline__ bool hist_insert(RowStateK& st, uint8_t* __restrict__ h, float s, int k) {
+    const int b = score_bin(s);
+    if (b > st.tb) {
+        h[b * TC_HIST_STRIDE] = (uint8_t)(h[b * TC_HIST_STRIDE] + 1);
+        ++st.cge;
+        return st.cge - st.ctb >= k;
     }
+    if (b == st.tb) {
+        ++st.cge;
+        ++st.ctb;
+    }
+    return false;
+}
+__device__ __forceinline__ void hist_advance(RowStateK& st, const uint8_t* __restrict__ h, int k, float eps) {
+    while (st.cge - st.ctb >= k) {   // at the last bin: cge == ctb
+        st.cge -= st.ctb;
+        ++st.tb;
+        st.ctb = h[st.tb * TC_HIST_STRIDE];
+    }
+    st.thr = bin_edge(st.tb) - eps;
+}
+
+// `count`: also enter the score into the histogram (false while the unit's first tile is being listed - the
+// bootstrap pass has already counted every column of that tile).
+__device__ __noinline__ RowStateK push_candidate_topk(RowStateK st, float s, int col, float eps, int cap, int k,
+                                                      bool count, uint8_t* __restrict__ h, int* __restrict__ li,
+                                                      float* __restrict__ ls) {
     if (st.cnt == cap) {
         int w = 0;
         for (int r = 0; r < st.cnt; ++r) {
@@ -238,7 +288,132 @@ __device__ __noinline__ RowStateK push_candidate_topk(RowStateK st, float s, int
     } else {
         st.flags |= 1;
     }
+    if (count && hist_insert(st, h, s, k)) hist_advance(st, h, k, eps);
     return st;
+}
+
+// Listing a column is ~45 dependent instructions executed by ONE lane of a lone warp (each lane owns a different
+// row), i.e. ~250 cycles per listed column if done on the spot.  Triggered columns are therefore parked in four
+// registers per lane and listed in batches when some lane's buffer fills: all lanes with parked columns then run
+// the listing code together.  The threshold is stale for parked columns, which only makes the list a superset.
+struct Pending {
+    float s0, s1, s2, s3;
+    int c0, c1, c2, c3;
+    int n;
+};
+__device__ __forceinline__ void pend_put(Pending& pd, float s, int col) {
+    if (pd.n == 0) {
+        pd.s0 = s;
+        pd.c0 = col;
+    } else if (pd.n == 1) {
+        pd.s1 = s;
+        pd.c1 = col;
+    } else if (pd.n == 2) {
+        pd.s2 = s;
+        pd.c2 = col;
+    } else {
+        pd.s3 = s;
+        pd.c3 = col;
+    }
+    ++pd.n;
+}
+__device__ __forceinline__ void pend_flush(Pending& pd, RowStateK& st, float eps, int cap, int k, bool count,
+                                           uint8_t* __restrict__ h, int* __restrict__ li, float* __restrict__ ls) {
+    if (pd.n > 0) st = push_candidate_topk(st, pd.s0, pd.c0, eps, cap, k, count, h, li, ls);
+    if (pd.n > 1) st = push_candidate_topk(st, pd.s1, pd.c1, eps, cap, k, count, h, li, ls);
+    if (pd.n > 2) st = push_candidate_topk(st, pd.s2, pd.c2, eps, cap, k, count, h, li, ls);
+    if (pd.n > 3) st = push_candidate_topk(st, pd.s3, pd.c3, eps, cap, k, count, h, li, ls);
+    pd.n = 0;
+}
+
+// ---- per-thread epilogue context and the filter of one 32-column chunk ----------------------------
+template <bool TOPK>
+struct EpiCtx {
+    const ScreenParams* p;
+    typename std::conditional<TOPK, RowStateK, RowState>::type st;
+    Pending pd;          // TOPK only
+    uint8_t* hist;       // TOPK only
+    int* li;
+    float* ls;
+    int64_t row, self_col;
+    bool row_ok, count, tracing;
+    unsigned long long n_trig, n_chunks;
+};
+
+template <bool TOPK>
+__device__ __forceinline__ void epi_chunk(EpiCtx<TOPK>& cx, uint32_t (&v)[32], int64_t col_base) {
+    const ScreenParams& p = *cx.p;
+    if (col_base >= p.n) return;  // whole chunk is padding (warp-uniform)
+    if (col_base + 32 > p.n || (cx.self_col >= col_base && cx.self_col < col_base + 32)) {
+#pragma unroll
+        for (int t = 0; t < 32; ++t)
+            if (col_base + t >= p.n || col_base + t == cx.self_col) v[t] = __float_as_uint(-CUDART_INF_F);
+    }
+    if (p.dump && cx.row_ok) {
+#pragma unroll
+        for (int t = 0; t < 32; ++t)
+            if (col_base + t < p.n) p.dump[cx.row * p.n + col_base + t] = __uint_as_float(v[t]);
+    }
+    if constexpr (TOPK) {
+        float g[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            g[q] = __uint_as_float(v[8 * q]);
+#pragma unroll
+            for (int t = 1; t < 8; ++t) g[q] = fmaxf(g[q], __uint_as_float(v[8 * q + t]));
+        }
+        const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+        if (cx.tracing) {
+            ++cx.n_chunks;
+            cx.n_trig += __any_sync(0xffffffffu, cx.row_ok && m >= cx.st.thr) ? 1 : 0;
+        }
+        if (cx.row_ok && m >= cx.st.thr) {
+            // rare path, kept small (the whole epilogue must stay inside the instruction cache): per group of 8
+            // columns take the maximum while it qualifies, park it, blank it, repeat
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float gm = g[q];
+                while (gm >= cx.st.thr && gm > -CUDART_INF_F) {
+                    int ga = 0;
+                    float best = __uint_as_float(v[8 * q]);
+#pragma unroll
+                    for (int t = 1; t < 8; ++t) {
+                        const float s = __uint_as_float(v[8 * q + t]);
+                        if (s > best) {
+                            best = s;
+                            ga = t;
+                        }
+                    }
+                    const int col = (int)(col_base + 8 * q + ga);
+                    if (cx.pd.n < 4)
+                        pend_put(cx.pd, best, col);
+                    else
+                        cx.st = push_candidate_topk(cx.st, best, col, p.eps, p.cap, p.topk, cx.count, cx.hist, cx.li,
+                                                    cx.ls);
+                    gm = -CUDART_INF_F;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        if (t == ga) v[8 * q + t] = __float_as_uint(-CUDART_INF_F);
+                        gm = fmaxf(gm, __uint_as_float(v[8 * q + t]));
+                    }
+                }
+            }
+        }
+        if (__any_sync(0xffffffffu, cx.pd.n >= 3))
+            pend_flush(cx.pd, cx.st, p.eps, p.cap, p.topk, cx.count, cx.hist, cx.li, cx.ls);
+    } else {
+        float m = __uint_as_float(v[0]);
+#pragma unroll
+        for (int t = 1; t < 32; ++t) m = fmaxf(m, __uint_as_float(v[t]));
+        if (cx.row_ok && m >= cx.st.thr) {
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+                const float s = __uint_as_float(v[t]);
+                if (s >= cx.st.thr && s > -CUDART_INF_F)
+                    cx.st = push_candidate(cx.st, s, (int)(col_base + t), p.eps, p.cap, cx.li, cx.ls);
+            }
+        }
+    }
 }
 
 // ---- the kernel ------------------------------------------------------------------------------
@@ -257,6 +432,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
     const uint32_t smem_base = smem_u32(smem);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool tracing = p.trace != nullptr;
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
@@ -267,7 +443,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(bar_acc_full + 8 * a, 1);
-            mbar_init(bar_acc_empty + 8 * a, 4);  // one arrive per epilogue warp
+            mbar_init(bar_acc_empty + 8 * a, TC_EPI_WARPS);  // one arrive per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -289,6 +465,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            unsigned long long t_wait = 0;
             for (int64_t u = blockIdx.x; u < p.num_units; u += gridDim.x) {
                 const int split = (int)(u % p.splits);
                 const int64_t row_block = u / p.splits;
@@ -296,7 +473,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
                 const int64_t ct1 = min(ct0 + p.tiles_per_split, n_col_tiles);
                 for (int64_t ct = ct0; ct < ct1; ++ct) {
                     for (int ks = 0; ks < p.num_k_slabs; ++ks) {
-                        mbar_wait(bar_empty + 8 * stage, phase ^ 1, p.error_flag);
+                        mbar_wait_traced(bar_empty + 8 * stage, phase ^ 1, p.error_flag, t_wait, tracing);
                         const uint32_t a_dst = smem_base + stage * TC_STAGE_BYTES;
                         const uint32_t b_dst = a_dst + TC_A_BYTES;
                         mbar_expect_tx(bar_full + 8 * stage, TC_STAGE_BYTES);
@@ -309,6 +486,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
                     }
                 }
             }
+            if (tracing) atomicAdd(p.trace + 0, t_wait);   // producer stalled on a free smem stage
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
@@ -317,16 +495,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            unsigned long long t_acc = 0, t_smem = 0;
+            const long long t_begin = tracing ? clock64() : 0;
             for (int64_t u = blockIdx.x; u < p.num_units; u += gridDim.x) {
                 const int split = (int)(u % p.splits);
                 const int64_t ct0 = (int64_t)split * p.tiles_per_split;
                 const int64_t ct1 = min(ct0 + p.tiles_per_split, n_col_tiles);
                 for (int64_t ct = ct0; ct < ct1; ++ct) {
-                    mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1, p.error_flag);
+                    mbar_wait_traced(bar_acc_empty + 8 * acc, acc_phase ^ 1, p.error_flag, t_acc, tracing);
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TC_BN);
                     for (int ks = 0; ks < p.num_k_slabs; ++ks) {
-                        mbar_wait(bar_full + 8 * stage, phase, p.error_flag);
+                        mbar_wait_traced(bar_full + 8 * stage, phase, p.error_flag, t_smem, tracing);
                         tc_fence_after();
                         const uint32_t a_addr = smem_base + stage * TC_STAGE_BYTES;
                         const uint64_t da = umma_smem_desc(a_addr);
@@ -348,84 +528,115 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
                     if (acc == 0) acc_phase ^= 1;
                 }
             }
+            if (tracing) {
+                atomicAdd(p.trace + 1, t_acc);    // MMA issuer stalled on a free accumulator (epilogue too slow)
+                atomicAdd(p.trace + 2, t_smem);   // MMA issuer stalled on operands (TMA / L2 too slow)
+                atomicAdd(p.trace + 3, (unsigned long long)(clock64() - t_begin));   // MMA issuer total
+            }
         }
     } else {
         // ===================== epilogue: fused candidate filter =====================
-        const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are the ones this warp may read
+        // Warp w reads TMEM lanes [32 * (w % 4), +32) (the hardware's lane window of that warp) and the 128-column
+        // half (w - 2) / 4 of every tile: one thread = one (query row, column half) stream with its own list.
+        const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int row_in_tile = quad * 32 + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
+        unsigned long long t_full = 0, n_trig = 0, n_chunks = 0;
+        const long long t_begin = tracing ? clock64() : 0;
+        EpiCtx<TOPK> cx;
+        cx.p = &p;
+        cx.tracing = tracing;
+        cx.n_trig = 0;
+        cx.n_chunks = 0;
+        if constexpr (TOPK) cx.hist = smem + TC_STAGES * TC_STAGE_BYTES + 256 + half * TC_BM + row_in_tile;
         for (int64_t u = blockIdx.x; u < p.num_units; u += gridDim.x) {
             const int split = (int)(u % p.splits);
             const int64_t row_block = u / p.splits;
             const int64_t ct0 = (int64_t)split * p.tiles_per_split;
             const int64_t ct1 = min(ct0 + p.tiles_per_split, n_col_tiles);
-            const int64_t row = row_block * TC_BM + row_in_tile;
-            const bool row_ok = row < p.nq;
-            const int64_t self_col = (p.self_offset >= 0 && row_ok) ? row + p.self_offset : -1;
-            const int64_t slot = (int64_t)split * p.nq + (row_ok ? row : 0);
-            int* li = p.cand_idx + slot * p.cap;
-            float* ls = p.cand_score + slot * p.cap;
-            typename std::conditional<TOPK, RowStateK, RowState>::type st;
-            float* tk = nullptr;
+            cx.row = row_block * TC_BM + row_in_tile;
+            cx.row_ok = cx.row < p.nq;
+            cx.self_col = (p.self_offset >= 0 && cx.row_ok) ? cx.row + p.self_offset : -1;
+            const int64_t slot = (int64_t)(split * 2 + half) * p.nq + (cx.row_ok ? cx.row : 0);
+            cx.li = p.cand_idx + slot * p.cap;
+            cx.ls = p.cand_score + slot * p.cap;
             if constexpr (TOPK) {
-                tk = reinterpret_cast<float*>(smem + TC_STAGES * TC_STAGE_BYTES + 256) + row_in_tile;
-                for (int i = 0; i < p.topk; ++i) tk[i * TC_BM] = -CUDART_INF_F;
-                st.kth = -CUDART_INF_F;
-                st.kth_pos = 0;
+                for (int i = 0; i < TC_HIST_BINS; ++i) cx.hist[i * TC_HIST_STRIDE] = 0;
+                cx.st.tb = 0;
+                cx.st.cge = 0;
+                cx.st.ctb = 0;
+                cx.st.thr = bin_edge(0) - p.eps;
+                cx.pd.n = 0;
             } else {
-                st.best = -CUDART_INF_F;
+                cx.st.best = -CUDART_INF_F;
+                cx.st.thr = -CUDART_INF_F;
             }
-            st.thr = -CUDART_INF_F;
-            st.cnt = 0;
-            st.flags = 0;
+            cx.st.cnt = 0;
+            cx.st.flags = 0;
             for (int64_t ct = ct0; ct < ct1; ++ct) {
-                mbar_wait(bar_acc_full + 8 * acc, acc_phase, p.error_flag);
+                mbar_wait_traced(bar_acc_full + 8 * acc, acc_phase, p.error_flag, t_full, tracing);
                 tc_fence_after();
-                const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_BN);
+                const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_BN + half * 128);
+                const int64_t col0 = ct * TC_BN + half * 128;
+                uint32_t va[32], vb[32];
+                if constexpr (TOPK) {
+                    cx.count = ct != ct0;
+                    if (ct == ct0) {
+                        // bootstrap: count every column of the stream's first 128 (uniform control flow, nothing is
+                        // listed), which yields the first threshold; the columns are then read again below
 #pragma unroll 1
-                for (int c = 0; c < TC_BN / 32; ++c) {
-                    uint32_t v[32];
-                    tmem_load_32cols(taddr0 + (uint32_t)(c * 32), v);
-                    const int64_t col_base = ct * TC_BN + c * 32;
-                    if (col_base >= p.n) continue;  // whole chunk is padding (warp-uniform)
-                    if (col_base + 32 > p.n || (self_col >= col_base && self_col < col_base + 32)) {
+                        for (int c = 0; c < 4; ++c) {
+                            tmem_ld_issue(tbase + (uint32_t)(c * 32), va);
+                            tmem_ld_wait(va);
+                            const int64_t col_base = col0 + c * 32;
+                            if (col_base >= p.n || !cx.row_ok) continue;
 #pragma unroll
-                        for (int t = 0; t < 32; ++t)
-                            if (col_base + t >= p.n || col_base + t == self_col) v[t] = __float_as_uint(-CUDART_INF_F);
-                    }
-                    if (p.dump && row_ok) {
-#pragma unroll
-                        for (int t = 0; t < 32; ++t)
-                            if (col_base + t < p.n) p.dump[row * p.n + col_base + t] = __uint_as_float(v[t]);
-                    }
-                    float m = __uint_as_float(v[0]);
-#pragma unroll
-                    for (int t = 1; t < 32; ++t) m = fmaxf(m, __uint_as_float(v[t]));
-                    if (row_ok && m >= st.thr) {
-#pragma unroll
-                        for (int t = 0; t < 32; ++t) {
-                            const float s = __uint_as_float(v[t]);
-                            if (s >= st.thr && s > -CUDART_INF_F) {
-                                if constexpr (TOPK)
-                                    st = push_candidate_topk(st, s, (int)(col_base + t), p.eps, p.cap, p.topk, tk, li, ls);
-                                else
-                                    st = push_candidate(st, s, (int)(col_base + t), p.eps, p.cap, li, ls);
+                            for (int t = 0; t < 32; ++t) {
+                                if (col_base + t < p.n && col_base + t != cx.self_col)
+                                    hist_insert(cx.st, cx.hist, __uint_as_float(va[t]), p.topk);
                             }
+                            hist_advance(cx.st, cx.hist, p.topk, p.eps);   // per chunk: bins above tb stay below 96 entries
                         }
                     }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
+                // software pipeline over the 4 chunks of this half: chunk c + 1 is in flight while chunk c is filtered
+                tmem_ld_issue(tbase, vb);
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    tmem_ld_wait(vb);
+#pragma unroll
+                    for (int t = 0; t < 32; ++t) va[t] = vb[t];
+                    if (c < 3) {
+                        tmem_ld_issue(tbase + (uint32_t)(32 * (c + 1)), vb);
+                    } else {
+                        // every TMEM read of this accumulator is complete: hand it back before the last filter
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
+                        acc ^= 1;
+                        if (acc == 0) acc_phase ^= 1;
+                    }
+                    epi_chunk<TOPK>(cx, va, col0 + 32 * c);
+                }
+                if constexpr (TOPK) {
+                    // parked columns of the first tile must be listed before columns start being counted
+                    if (ct == ct0) pend_flush(cx.pd, cx.st, p.eps, p.cap, p.topk, false, cx.hist, cx.li, cx.ls);
+                }
             }
-            if (row_ok) {
-                p.cand_cnt[slot] = st.cnt;
-                p.cand_flags[slot] = st.flags;
-                if constexpr (TOPK) p.cand_kth[slot] = st.kth;
+            if constexpr (TOPK) pend_flush(cx.pd, cx.st, p.eps, p.cap, p.topk, true, cx.hist, cx.li, cx.ls);
+            if (cx.row_ok) {
+                p.cand_cnt[slot] = cx.st.cnt;
+                p.cand_flags[slot] = cx.st.flags;
+                if constexpr (TOPK) p.cand_kth[slot] = bin_edge(cx.st.tb);
             }
+        }
+        if (tracing && lane == 0 && warp == 2) {
+            atomicAdd(p.trace + 4, t_full);    // epilogue warp 0 stalled on a complete accumulator (MMA slower)
+            atomicAdd(p.trace + 5, (unsigned long long)(clock64() - t_begin));   // epilogue warp 0 total
+            atomicAdd(p.trace + 6, cx.n_trig);    // 32-column chunks in which some row had a candidate
+            atomicAdd(p.trace + 7, cx.n_chunks);
         }
     }
 
@@ -506,7 +717,7 @@ __global__ void scatter_rows_kernel(const int* __restrict__ rows, int count, con
 // k-th best screened score (the largest per-split k-th best), evaluates them exactly in T, sorts them by
 // (distance, column) and emits the first k.  Rows that overflowed a list, gathered more than RK_MAX
 // columns or fewer than k go to the exact kernel.
-constexpr int RK_THREADS = 128, RK_MAX = 1024;
+constexpr int RK_THREADS = 128, RK_MAX = 1024, RK_BINS = 1024;
 
 template <typename T>
 __global__ void __launch_bounds__(RK_THREADS) rerank_topk_kernel(const T* __restrict__ q_unit, const T* __restrict__ x_unit,
@@ -520,20 +731,64 @@ __global__ void __launch_bounds__(RK_THREADS) rerank_topk_kernel(const T* __rest
                                                                  int* __restrict__ overflow_rows, int* __restrict__ stats) {
     __shared__ int s_idx[RK_MAX];
     __shared__ T s_dist[RK_MAX];
+    __shared__ int s_hist[RK_BINS];
+    __shared__ int s_part[RK_THREADS];
     __shared__ int s_m, s_flags;
     __shared__ float s_thr;
     const int64_t r = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         float kth = -CUDART_INF_F;
-        int fl = 0;
+        int fl = 0, listed = 0;
         for (int sp = 0; sp < splits; ++sp) {
             kth = fmaxf(kth, cand_kth[(int64_t)sp * nq + r]);
             fl |= cand_flags[(int64_t)sp * nq + r];
+            listed += cand_cnt[(int64_t)sp * nq + r];
         }
+        atomicAdd(&stats[3], listed >> 4);   // columns listed by the screen, in units of 16
         s_thr = kth - eps;
         s_flags = fl;
         s_m = 0;
+    }
+    __syncthreads();
+    // Tighten the threshold: the streams' own bounds are k-th bests of a FRACTION of the columns.  A 1024-bin
+    // histogram (bin width 2^-10) of every listed score above the coarse threshold gives the merged k-th best to
+    // within one bin: edge(bin holding the k-th largest) <= k-th best screened score of the whole row.
+    for (int b = tid; b < RK_BINS; b += RK_THREADS) s_hist[b] = 0;
+    __syncthreads();
+    const float thr0 = s_thr;
+    for (int sp = 0; sp < splits; ++sp) {
+        const int64_t slot = (int64_t)sp * nq + r;
+        const int c = cand_cnt[slot];
+        for (int e = tid; e < c; e += RK_THREADS) {
+            const float sc = cand_score[slot * cap + e];
+            if (sc >= thr0) atomicAdd(&s_hist[min(max(__float2int_rd(sc * (float)RK_BINS), 0), RK_BINS - 1)], 1);
+        }
+    }
+    __syncthreads();
+    {
+        constexpr int PER = RK_BINS / RK_THREADS;   // bins per thread
+        int local = 0;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) local += s_hist[tid * PER + i];
+        s_part[tid] = local;
+        __syncthreads();
+        for (int off = 1; off < RK_THREADS; off <<= 1) {   // inclusive suffix sums over threads
+            const int add = tid + off < RK_THREADS ? s_part[tid + off] : 0;
+            __syncthreads();
+            s_part[tid] += add;
+            __syncthreads();
+        }
+        const int above = tid + 1 < RK_THREADS ? s_part[tid + 1] : 0;   // listed scores in bins owned by later threads
+        if (above < k && s_part[tid] >= k) {   // exactly one thread: the k-th largest lies in one of its bins
+            int cum = above, b = tid * PER + PER - 1;
+            for (; b > tid * PER; --b) {
+                cum += s_hist[b];
+                if (cum >= k) break;
+            }
+            const float edge = b == 0 ? -1.0f : (float)b * (1.0f / (float)RK_BINS);
+            s_thr = fmaxf(thr0, edge - eps);
+        }
     }
     __syncthreads();
     const float thr = s_thr;
@@ -644,6 +899,7 @@ static int make_tmap(CUtensorMap* map, const uint16_t* base, int64_t rows, int d
 
 // optional CUDA-event timing of the screen kernel on its own stream (bench.py's roofline leg)
 static bool g_profile = false, g_have_sample = false;
+static unsigned long long* g_trace = nullptr;   // device [8], allocated by slic_screen_trace(1)
 static cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
 static double g_last_flop = 0.0;
 
@@ -664,6 +920,48 @@ static ScreenPlan plan_screen(int64_t nq, int64_t n) {
     pl.splits = (int)ceil_div(col_tiles, pl.tiles_per_split);
     pl.units = row_blocks * pl.splits;
     return pl;
+}
+
+// Top-k variant: every unit restarts with an empty threshold (its first tile is listed in full and the
+// threshold then tightens like k / columns seen), so units should be as long as the wave structure allows:
+// minimise waves x (tiles per unit + start-up cost in tile times).
+static ScreenPlan plan_screen_topk(int64_t nq, int64_t n, int k) {
+    const int64_t row_blocks = ceil_div(nq, TC_BM), col_tiles = ceil_div(n, TC_BN);
+    const int64_t sms = num_sms();
+    const int64_t startup = 6;   // bootstrap pass + threshold ramp of a unit, in tile times
+    int64_t best_s = 1, best_cost = INT64_MAX;
+    // a stream (half of a unit's tiles) should see >= ~32 k columns, or its own k-th best says little about the row's
+    const int64_t min_tps = ceil_div((int64_t)32 * k, TC_BN / 2);
+    for (int64_t sp = 1; sp <= col_tiles && sp <= 64; ++sp) {
+        const int64_t tps = ceil_div(col_tiles, sp);
+        if (sp > 1 && tps < min_tps) break;
+        const int64_t real = ceil_div(col_tiles, tps);
+        const int64_t waves = ceil_div(row_blocks * real, sms);
+        const int64_t cost = waves * (tps + startup);
+        if (cost < best_cost) {
+            best_cost = cost;
+            best_s = real;
+        }
+    }
+    if (const char* e = getenv("SLIC_TOPK_SPLITS")) {   // experiments only
+        const int64_t v = atoll(e);
+        if (v >= 1 && v <= col_tiles) best_s = v;
+    }
+    ScreenPlan pl;
+    pl.tiles_per_split = (int)ceil_div(col_tiles, best_s);
+    pl.splits = (int)ceil_div(col_tiles, pl.tiles_per_split);
+    pl.units = row_blocks * pl.splits;
+    return pl;
+}
+
+// candidate slots per (split, row) of the top-k variant: the first tile (256) + ~k ln(columns / 256) later
+// listings + the eps band, with a factor 3 of head room; rows that still overflow are compacted, then finished exactly
+static int topk_cap(int k, int64_t cols_per_split) {
+    double later = cols_per_split > 128 ? (double)k * log((double)cols_per_split / 128.0) : 0.0;
+    int64_t want = 128 + (int64_t)(3.0 * later) + 128;
+    int cap = 512;
+    while (cap < want && cap < 4096) cap <<= 1;
+    return cap;
 }
 
 static int launch_screen(const uint16_t* q_bf16, int64_t nq, const uint16_t* x_bf16, int64_t n, int d_pad,
@@ -691,6 +989,7 @@ static int launch_screen(const uint16_t* q_bf16, int64_t nq, const uint16_t* x_b
     p.cand_kth = cand_kth;
     p.dump = dump;
     p.error_flag = error_flag;
+    p.trace = g_trace;
     static bool attr_done[64] = {false};
     int dev = 0;
     SLIC_CUDA_OK(cudaGetDevice(&dev));
@@ -730,7 +1029,7 @@ static int nn_top1_impl(const T* q_unit, const uint16_t* q_bf16, int64_t nq, con
                         int64_t n, int d, int d_pad, int64_t self_offset, float eps, int* idx_out, T* dist_out,
                         int* stats_out, cudaStream_t st) {
     const ScreenPlan pl = plan_screen(nq, n);
-    const int64_t slots = (int64_t)pl.splits * nq;
+    const int64_t slots = (int64_t)pl.splits * 2 * nq;   // one list per (split, 128-column half of the tiles, row)
     Scratch ci, cs, cc, cf, ovr, stats;
     SLIC_CUDA_OK(ci.alloc(slots * TC_CAP * sizeof(int), st));
     SLIC_CUDA_OK(cs.alloc(slots * TC_CAP * sizeof(float), st));
@@ -741,7 +1040,7 @@ static int nn_top1_impl(const T* q_unit, const uint16_t* q_bf16, int64_t nq, con
     SLIC_CUDA_OK(cudaMemsetAsync(stats.ptr, 0, 8 * sizeof(int), st));
     SLIC_PROPAGATE(launch_screen(q_bf16, nq, x_bf16, n, d_pad, self_offset, eps, TC_CAP, pl, ci.as<int>(), cs.as<float>(),
                                  cc.as<int>(), cf.as<int>(), nullptr, stats.as<int>() + 4, st));
-    rerank_top1_kernel<T><<<(unsigned)ceil_div(nq, 8), 256, 0, st>>>(q_unit, x_unit, nq, d, eps, TC_CAP, pl.splits,
+    rerank_top1_kernel<T><<<(unsigned)ceil_div(nq, 8), 256, 0, st>>>(q_unit, x_unit, nq, d, eps, TC_CAP, 2 * pl.splits,
                                                                      ci.as<int>(), cs.as<float>(), cc.as<int>(),
                                                                      cf.as<int>(), idx_out, dist_out, ovr.as<int>(),
                                                                      stats.as<int>());
@@ -768,14 +1067,13 @@ static int nn_top1_impl(const T* q_unit, const uint16_t* q_bf16, int64_t nq, con
     return SLIC_OK;
 }
 
-constexpr int TC_CAP_TOPK = 512;
-
 template <typename T>
 static int topk_tc_impl(const T* q_unit, const uint16_t* q_bf16, int64_t nq, const T* x_unit, const uint16_t* x_bf16,
                         int64_t n, int d, int d_pad, int k, int64_t self_offset, float eps, int* idx_out, T* dist_out,
                         int* stats_out, cudaStream_t st) {
-    const ScreenPlan pl = plan_screen(nq, n);
-    const int64_t slots = (int64_t)pl.splits * nq;
+    const ScreenPlan pl = plan_screen_topk(nq, n, k);
+    const int TC_CAP_TOPK = topk_cap(k, (int64_t)pl.tiles_per_split * (TC_BN / 2));
+    const int64_t slots = (int64_t)pl.splits * 2 * nq;   // one list per (split, 128-column half of the tiles, row)
     Scratch ci, cs, cc, cf, ck, ovr, stats;
     SLIC_CUDA_OK(ci.alloc(slots * TC_CAP_TOPK * sizeof(int), st));
     SLIC_CUDA_OK(cs.alloc(slots * TC_CAP_TOPK * sizeof(float), st));
@@ -788,7 +1086,7 @@ static int topk_tc_impl(const T* q_unit, const uint16_t* q_bf16, int64_t nq, con
     SLIC_PROPAGATE(launch_screen(q_bf16, nq, x_bf16, n, d_pad, self_offset, eps, TC_CAP_TOPK, pl, ci.as<int>(),
                                  cs.as<float>(), cc.as<int>(), cf.as<int>(), nullptr, stats.as<int>() + 4, st, k,
                                  ck.as<float>()));
-    rerank_topk_kernel<T><<<(unsigned)nq, RK_THREADS, 0, st>>>(q_unit, x_unit, nq, d, eps, TC_CAP_TOPK, pl.splits, k,
+    rerank_topk_kernel<T><<<(unsigned)nq, RK_THREADS, 0, st>>>(q_unit, x_unit, nq, d, eps, TC_CAP_TOPK, 2 * pl.splits, k,
                                                                ci.as<int>(), cs.as<float>(), cc.as<int>(), cf.as<int>(),
                                                                ck.as<float>(), idx_out, dist_out, ovr.as<int>(),
                                                                stats.as<int>());
@@ -872,6 +1170,23 @@ int slic_profile_screen(int32_t enable) {
     return SLIC_OK;
 }
 
+int slic_screen_trace(int32_t enable, uint64_t* counters_out_host) {
+    using namespace slic;
+    if (counters_out_host && g_trace) {
+        SLIC_CUDA_OK(cudaDeviceSynchronize());
+        SLIC_CUDA_OK(cudaMemcpy(counters_out_host, g_trace, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    }
+    if (enable && !g_trace) {
+        SLIC_CUDA_OK(cudaMalloc(&g_trace, 8 * sizeof(uint64_t)));
+    } else if (!enable && g_trace) {
+        SLIC_CUDA_OK(cudaDeviceSynchronize());
+        SLIC_CUDA_OK(cudaFree(g_trace));
+        g_trace = nullptr;
+    }
+    if (g_trace) SLIC_CUDA_OK(cudaMemset(g_trace, 0, 8 * sizeof(uint64_t)));
+    return SLIC_OK;
+}
+
 int slic_last_screen_time(float* ms_out, double* flop_out) {
     SLIC_REQUIRE(ms_out && flop_out, "last_screen_time: null pointer");
     if (!slic::g_have_sample) {
@@ -892,7 +1207,7 @@ int slic_screen_scores_debug(const uint16_t* q_bf16_dev, int64_t nq, const uint1
     SLIC_PROPAGATE(slic_require_device());
     cudaStream_t st = as_stream(stream);
     const ScreenPlan pl = plan_screen(nq, n);
-    const int64_t slots = (int64_t)pl.splits * nq;
+    const int64_t slots = (int64_t)pl.splits * 2 * nq;   // one list per (split, 128-column half of the tiles, row)
     Scratch ci, cs, cc, cf, err;
     SLIC_CUDA_OK(ci.alloc(slots * TC_CAP * sizeof(int), st));
     SLIC_CUDA_OK(cs.alloc(slots * TC_CAP * sizeof(float), st));
