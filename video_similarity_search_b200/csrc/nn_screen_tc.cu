@@ -37,13 +37,25 @@
 
 namespace slic {
 
-constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 4, TC_UMMA_K = 16;
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_UMMA_K = 16;
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
-constexpr uint32_t TC_B_BYTES = TC_BN * TC_BK * 2;   // 32 KB
-constexpr uint32_t TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+// NCTA = 1: one CTA per 128 x 256 tile, it stages the whole 256-column B slab (32 KB).
+// NCTA = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) works on a 256 x 256 tile; each CTA stages its own 128
+//           query rows of A and HALF of the B slab (16 KB) and the tensor cores of both SMs read both halves, so
+//           the L2 -> SM operand traffic per flop drops by a third and 6 stages fit instead of 4.
+template <int NCTA> struct TcCfg {
+    static constexpr uint32_t B_ROWS = TC_BN / NCTA;
+    static constexpr uint32_t B_BYTES = B_ROWS * TC_BK * 2;
+    static constexpr uint32_t STAGE_BYTES = TC_A_BYTES + B_BYTES;
+    static constexpr int STAGES = NCTA == 1 ? 4 : 6;
+    static constexpr uint32_t RING_BYTES = STAGES * STAGE_BYTES;   // 192 KB either way
+};
+constexpr uint32_t TC_RING_BYTES = 196608;
+static_assert(TcCfg<1>::RING_BYTES == TC_RING_BYTES && TcCfg<2>::RING_BYTES == TC_RING_BYTES, "operand ring size");
+constexpr int TC_MAX_STAGES = 6;
 constexpr int TC_EPI_WARPS = 8;   // two per TMEM lane quadrant: each takes one 128-column half of every tile
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
-constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
+constexpr uint32_t TC_SMEM_BYTES = TC_RING_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
 constexpr int TC_TMEM_COLS = 512;
 // Screen error allowance: a bf16-rounded operand carries relative error <= 2^-9, a product of two <= 2^-8 (+2^-18),
 // so for unit rows |screened - exact| <= 2^-8 * sum|a_k b_k| <= 2^-8, plus fp32 accumulation (<= d * 2^-24 relative to
@@ -127,6 +139,26 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t dst
         ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
+// shared::cluster address of the same smem offset in the pair's leader CTA (rank 0): clear the peer bit
+constexpr uint32_t TC_PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t dst, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(leader_bar & TC_PEER_BIT_MASK)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & TC_PEER_BIT_MASK) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
@@ -140,6 +172,22 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives (once the MMAs issued so far retire) on the barrier at this smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(bar), "h"((uint16_t)3)
+        : "memory");
 }
 // TMEM -> registers, 32 lanes x 32 columns per warp.  Issue and wait are separate so that the load of the next
 // 32-column chunk is in flight while the current one is filtered; the wait names the registers as in/out operands
@@ -183,6 +231,10 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
 // N >> 3 at bits 17-22, M >> 4 at bits 24-28.
 constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
                               ((uint32_t)(TC_BM >> 4) << 24);
+
+// cta_group::2: the instruction spans both CTAs, M = 256
+constexpr uint32_t TC_IDESC_PAIR = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
+                                   ((uint32_t)((2 * TC_BM) >> 4) << 24);
 
 // ---- candidate list maintenance (slow path, rare) -------------------------------------------
 struct RowState {
@@ -417,69 +469,90 @@ __device__ __forceinline__ void epi_chunk(EpiCtx<TOPK>& cx, uint32_t (&v)[32], i
 }
 
 // ---- the kernel ------------------------------------------------------------------------------
-template <bool TOPK>
+template <bool TOPK, int NCTA>
 __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_constant__ CUtensorMap tmap_q,
                                                                   const __grid_constant__ CUtensorMap tmap_x,
                                                                   const ScreenParams p) {
+    typedef TcCfg<NCTA> Cfg;
+    constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
+    // (the dynamic smem window starts at the same offset in both CTAs of a pair, so the aligned offsets agree)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
-    const uint32_t bar_full = smem_u32(bars);                       // [TC_STAGES]
-    const uint32_t bar_empty = smem_u32(bars + TC_STAGES);          // [TC_STAGES]
-    const uint32_t bar_acc_full = smem_u32(bars + 2 * TC_STAGES);   // [2]
-    const uint32_t bar_acc_empty = smem_u32(bars + 2 * TC_STAGES + 2);  // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_RING_BYTES);
+    const uint32_t bar_full = smem_u32(bars);                              // [STAGES]  (pair: the leader's are used)
+    const uint32_t bar_empty = smem_u32(bars + TC_MAX_STAGES);             // [STAGES]
+    const uint32_t bar_acc_full = smem_u32(bars + 2 * TC_MAX_STAGES);      // [2]
+    const uint32_t bar_acc_empty = smem_u32(bars + 2 * TC_MAX_STAGES + 2); // [2]      (pair: the leader's are used)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 4);
     const uint32_t smem_base = smem_u32(smem);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool tracing = p.trace != nullptr;
+    const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0u;   // 0 = leader: issues the MMAs of the pair
+    const int64_t group = blockIdx.x / NCTA, num_groups = gridDim.x / NCTA;
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
-        for (int s = 0; s < TC_STAGES; ++s) {
-            mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_empty + 8 * s, 1);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);    // the (leader's) producer's arrive.expect_tx
+            mbar_init(bar_empty + 8 * s, 1);   // one tcgen05.commit
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(bar_acc_full + 8 * a, 1);
-            mbar_init(bar_acc_empty + 8 * a, TC_EPI_WARPS);  // one arrive per epilogue warp
+            mbar_init(bar_acc_empty + 8 * a, TC_EPI_WARPS * NCTA);  // one arrive per epilogue warp of the pair
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(TC_TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (NCTA == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"(TC_TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"(TC_TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (NCTA == 2) cluster_sync_all();   // the peer's barriers are initialised before anything remote touches them
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
     const int64_t n_col_tiles = (p.n + TC_BN - 1) / TC_BN;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (every CTA: its own A rows, its share of the B slab) =====================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
             unsigned long long t_wait = 0;
-            for (int64_t u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+            for (int64_t u = group; u < p.num_units; u += num_groups) {
                 const int split = (int)(u % p.splits);
-                const int64_t row_block = u / p.splits;
+                const int64_t row_block = (u / p.splits) * NCTA + cta_rank;
                 const int64_t ct0 = (int64_t)split * p.tiles_per_split;
                 const int64_t ct1 = min(ct0 + p.tiles_per_split, n_col_tiles);
                 for (int64_t ct = ct0; ct < ct1; ++ct) {
                     for (int ks = 0; ks < p.num_k_slabs; ++ks) {
                         mbar_wait_traced(bar_empty + 8 * stage, phase ^ 1, p.error_flag, t_wait, tracing);
-                        const uint32_t a_dst = smem_base + stage * TC_STAGE_BYTES;
+                        const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
                         const uint32_t b_dst = a_dst + TC_A_BYTES;
-                        mbar_expect_tx(bar_full + 8 * stage, TC_STAGE_BYTES);
-                        tma_load_2d(&tmap_q, a_dst, bar_full + 8 * stage, ks * TC_BK, (int)(row_block * TC_BM));
-                        tma_load_2d(&tmap_x, b_dst, bar_full + 8 * stage, ks * TC_BK, (int)(ct * TC_BN));
-                        if (++stage == TC_STAGES) {
+                        if constexpr (NCTA == 2) {
+                            // both CTAs' bytes complete on the LEADER's full barrier
+                            if (cta_rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * Cfg::STAGE_BYTES);
+                            tma_load_2d_pair(&tmap_q, a_dst, bar_full + 8 * stage, ks * TC_BK, (int)(row_block * TC_BM));
+                            tma_load_2d_pair(&tmap_x, b_dst, bar_full + 8 * stage, ks * TC_BK,
+                                             (int)(ct * TC_BN + cta_rank * Cfg::B_ROWS));
+                        } else {
+                            mbar_expect_tx(bar_full + 8 * stage, Cfg::STAGE_BYTES);
+                            tma_load_2d(&tmap_q, a_dst, bar_full + 8 * stage, ks * TC_BK, (int)(row_block * TC_BM));
+                            tma_load_2d(&tmap_x, b_dst, bar_full + 8 * stage, ks * TC_BK, (int)(ct * TC_BN));
+                        }
+                        if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1;
                         }
@@ -489,15 +562,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
             if (tracing) atomicAdd(p.trace + 0, t_wait);   // producer stalled on a free smem stage
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (one thread; in a pair only the leader's) =====================
+        if (lane == 0 && cta_rank == 0) {
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
             unsigned long long t_acc = 0, t_smem = 0;
             const long long t_begin = tracing ? clock64() : 0;
-            for (int64_t u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+            for (int64_t u = group; u < p.num_units; u += num_groups) {
                 const int split = (int)(u % p.splits);
                 const int64_t ct0 = (int64_t)split * p.tiles_per_split;
                 const int64_t ct1 = min(ct0 + p.tiles_per_split, n_col_tiles);
@@ -508,22 +581,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
                     for (int ks = 0; ks < p.num_k_slabs; ++ks) {
                         mbar_wait_traced(bar_full + 8 * stage, phase, p.error_flag, t_smem, tracing);
                         tc_fence_after();
-                        const uint32_t a_addr = smem_base + stage * TC_STAGE_BYTES;
+                        const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
                         const uint64_t da = umma_smem_desc(a_addr);
                         const uint64_t db = umma_smem_desc(a_addr + TC_A_BYTES);
 #pragma unroll
                         for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
                             // advancing 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the address field
-                            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), TC_IDESC,
-                                      (uint32_t)((ks | k) != 0));
+                            if constexpr (NCTA == 2)
+                                umma_bf16_pair(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), TC_IDESC_PAIR,
+                                               (uint32_t)((ks | k) != 0));
+                            else
+                                umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), TC_IDESC,
+                                          (uint32_t)((ks | k) != 0));
                         }
-                        umma_commit(bar_empty + 8 * stage);  // frees the smem stage once these MMAs retire
-                        if (++stage == TC_STAGES) {
+                        // frees the smem stage (in both CTAs of a pair) once these MMAs retire
+                        if constexpr (NCTA == 2) umma_commit_pair(bar_empty + 8 * stage);
+                        else umma_commit(bar_empty + 8 * stage);
+                        if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1;
                         }
                     }
-                    umma_commit(bar_acc_full + 8 * acc);  // accumulator complete -> epilogue
+                    // accumulator complete -> epilogue (of both CTAs)
+                    if constexpr (NCTA == 2) umma_commit_pair(bar_acc_full + 8 * acc);
+                    else umma_commit(bar_acc_full + 8 * acc);
                     acc ^= 1;
                     if (acc == 0) acc_phase ^= 1;
                 }
@@ -550,10 +631,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
         cx.tracing = tracing;
         cx.n_trig = 0;
         cx.n_chunks = 0;
-        if constexpr (TOPK) cx.hist = smem + TC_STAGES * TC_STAGE_BYTES + 256 + half * TC_BM + row_in_tile;
-        for (int64_t u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+        if constexpr (TOPK) cx.hist = smem + TC_RING_BYTES + 256 + half * TC_BM + row_in_tile;
+        for (int64_t u = group; u < p.num_units; u += num_groups) {
             const int split = (int)(u % p.splits);
-            const int64_t row_block = u / p.splits;
+            const int64_t row_block = (u / p.splits) * NCTA + cta_rank;
             const int64_t ct0 = (int64_t)split * p.tiles_per_split;
             const int64_t ct1 = min(ct0 + p.tiles_per_split, n_col_tiles);
             cx.row = row_block * TC_BM + row_in_tile;
@@ -614,7 +695,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
                         // every TMEM read of this accumulator is complete: hand it back before the last filter
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
+                        if (lane == 0) {
+                            if constexpr (NCTA == 2) mbar_arrive_leader(bar_acc_empty + 8 * acc);
+                            else mbar_arrive(bar_acc_empty + 8 * acc);
+                        }
                         acc ^= 1;
                         if (acc == 0) acc_phase ^= 1;
                     }
@@ -642,10 +726,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (NCTA == 2) cluster_sync_all();   // the peer no longer reads this CTA's smem or signals its barriers
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS)
-                     : "memory");
+        if constexpr (NCTA == 2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS)
+                         : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS)
+                         : "memory");
     }
 }
 
@@ -908,9 +997,20 @@ struct ScreenPlan {
     int64_t units;
 };
 
+// CTAs per tile group: 2 (CTA pairs, tcgen05 cta_group::2) unless SLIC_SCREEN_NCTA=1 selects the single-CTA kernel
+static int screen_ncta() {
+    static int cached = 0;
+    if (cached == 0) {
+        const char* e = getenv("SLIC_SCREEN_NCTA");
+        cached = (e && atoi(e) == 1) ? 1 : 2;
+    }
+    return cached;
+}
+
 static ScreenPlan plan_screen(int64_t nq, int64_t n) {
-    const int64_t row_blocks = ceil_div(nq, TC_BM), col_tiles = ceil_div(n, TC_BN);
-    const int64_t sms = num_sms();
+    const int ncta = screen_ncta();
+    const int64_t row_blocks = ceil_div(nq, TC_BM * ncta), col_tiles = ceil_div(n, TC_BN);
+    const int64_t sms = num_sms() / ncta;
     // enough units for >= ~6 waves when the problem allows it, but keep >= 8 tiles per unit
     int64_t want = ceil_div(6 * sms, row_blocks);
     int64_t max_splits = col_tiles / 8 > 0 ? col_tiles / 8 : 1;
@@ -926,8 +1026,9 @@ static ScreenPlan plan_screen(int64_t nq, int64_t n) {
 // threshold then tightens like k / columns seen), so units should be as long as the wave structure allows:
 // minimise waves x (tiles per unit + start-up cost in tile times).
 static ScreenPlan plan_screen_topk(int64_t nq, int64_t n, int k) {
-    const int64_t row_blocks = ceil_div(nq, TC_BM), col_tiles = ceil_div(n, TC_BN);
-    const int64_t sms = num_sms();
+    const int ncta = screen_ncta();
+    const int64_t row_blocks = ceil_div(nq, TC_BM * ncta), col_tiles = ceil_div(n, TC_BN);
+    const int64_t sms = num_sms() / ncta;
     const int64_t startup = 6;   // bootstrap pass + threshold ramp of a unit, in tile times
     int64_t best_s = 1, best_cost = INT64_MAX;
     // a stream (half of a unit's tiles) should see >= ~32 k columns, or its own k-th best says little about the row's
@@ -968,9 +1069,10 @@ static int launch_screen(const uint16_t* q_bf16, int64_t nq, const uint16_t* x_b
                          int64_t self_offset, float eps, int cap, const ScreenPlan& pl, int* cand_idx, float* cand_score,
                          int* cand_cnt, int* cand_flags, float* dump, int* error_flag, cudaStream_t st, int topk = 0,
                          float* cand_kth = nullptr) {
+    const int ncta = screen_ncta();
     CUtensorMap tq, tx;
     SLIC_PROPAGATE(make_tmap(&tq, q_bf16, nq, d_pad, TC_BM));
-    SLIC_PROPAGATE(make_tmap(&tx, x_bf16, n, d_pad, TC_BN));
+    SLIC_PROPAGATE(make_tmap(&tx, x_bf16, n, d_pad, TC_BN / ncta));
     ScreenParams p;
     p.nq = nq;
     p.n = n;
@@ -990,18 +1092,21 @@ static int launch_screen(const uint16_t* q_bf16, int64_t nq, const uint16_t* x_b
     p.dump = dump;
     p.error_flag = error_flag;
     p.trace = g_trace;
-    static bool attr_done[64] = {false};
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const ScreenParams);
+    const bool is_topk = topk > 0;
+    KernelFn fn = ncta == 2 ? (is_topk ? (KernelFn)nn_screen_kernel<true, 2> : (KernelFn)nn_screen_kernel<false, 2>)
+                            : (is_topk ? (KernelFn)nn_screen_kernel<true, 1> : (KernelFn)nn_screen_kernel<false, 1>);
+    const size_t smem_bytes = TC_SMEM_BYTES + (is_topk ? TC_TOPK_SMEM : 0);
+    static bool attr_done[64][4] = {{false}};
     int dev = 0;
     SLIC_CUDA_OK(cudaGetDevice(&dev));
-    bool& attr_set = attr_done[dev & 63];
+    bool& attr_set = attr_done[dev & 63][(ncta == 2 ? 2 : 0) + (is_topk ? 1 : 0)];
     if (!attr_set) {
-        SLIC_CUDA_OK(cudaFuncSetAttribute(nn_screen_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          TC_SMEM_BYTES));
-        SLIC_CUDA_OK(cudaFuncSetAttribute(nn_screen_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          TC_SMEM_BYTES + TC_TOPK_SMEM));
+        SLIC_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         attr_set = true;
     }
-    const int64_t grid = pl.units < num_sms() ? pl.units : num_sms();
+    const int64_t groups = num_sms() / ncta;
+    const int64_t grid = (pl.units < groups ? pl.units : groups) * ncta;
     if (g_profile) {
         if (!g_ev_start) {
             SLIC_CUDA_OK(cudaEventCreate(&g_ev_start));
@@ -1009,10 +1114,19 @@ static int launch_screen(const uint16_t* q_bf16, int64_t nq, const uint16_t* x_b
         }
         SLIC_CUDA_OK(cudaEventRecord(g_ev_start, st));
     }
-    if (topk > 0)
-        nn_screen_kernel<true><<<(unsigned)grid, TC_THREADS, TC_SMEM_BYTES + TC_TOPK_SMEM, st>>>(tq, tx, p);
-    else
-        nn_screen_kernel<false><<<(unsigned)grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tq, tx, p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)ncta;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SLIC_CUDA_OK(cudaLaunchKernelEx(&cfg, fn, tq, tx, p));
     SLIC_LAUNCH_OK();
     if (g_profile) {
         SLIC_CUDA_OK(cudaEventRecord(g_ev_stop, st));
