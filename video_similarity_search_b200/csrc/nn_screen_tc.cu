@@ -43,19 +43,25 @@ constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
 // NCTA = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) works on a 256 x 256 tile; each CTA stages its own 128
 //           query rows of A and HALF of the B slab (16 KB) and the tensor cores of both SMs read both halves, so
 //           the L2 -> SM operand traffic per flop drops by a third and 6 stages fit instead of 4.
-template <int NCTA> struct TcCfg {
+// ARES (pairs only, d_pad <= 512): the unit's A rows (128 x d_pad bf16 <= 128 KB) are loaded ONCE per unit and stay
+//           resident; only B slabs stream through the ring.  A is the one operand no other SM shares, so this removes
+//           most of the L2 -> SM traffic that bounds the streaming variants.
+constexpr int TC_ARES_MAX_SLABS = 8;
+template <int NCTA, bool ARES, bool TOPK> struct TcCfg {
     static constexpr uint32_t B_ROWS = TC_BN / NCTA;
     static constexpr uint32_t B_BYTES = B_ROWS * TC_BK * 2;
-    static constexpr uint32_t STAGE_BYTES = TC_A_BYTES + B_BYTES;
-    static constexpr int STAGES = NCTA == 1 ? 4 : 6;
-    static constexpr uint32_t RING_BYTES = STAGES * STAGE_BYTES;   // 192 KB either way
+    static constexpr uint32_t A_RES_BYTES = ARES ? TC_ARES_MAX_SLABS * TC_A_BYTES : 0;      // 128 KB
+    static constexpr uint32_t STAGE_BYTES = ARES ? B_BYTES : TC_A_BYTES + B_BYTES;
+    static constexpr int STAGES = ARES ? (TOPK ? 4 : 6) : (NCTA == 1 ? 4 : 6);
+    static constexpr uint32_t OPERAND_BYTES = A_RES_BYTES + STAGES * STAGE_BYTES;            // 192 KB, ARES: 192 / 224 KB
+    static constexpr uint32_t SMEM_BYTES = OPERAND_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/ +
+                                           (TOPK ? 32768u : 0u) /*histograms*/;
+    static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
+    static_assert(!ARES || NCTA == 2, "the A-resident variant exists for CTA pairs only");
 };
-constexpr uint32_t TC_RING_BYTES = 196608;
-static_assert(TcCfg<1>::RING_BYTES == TC_RING_BYTES && TcCfg<2>::RING_BYTES == TC_RING_BYTES, "operand ring size");
 constexpr int TC_MAX_STAGES = 6;
 constexpr int TC_EPI_WARPS = 8;   // two per TMEM lane quadrant: each takes one 128-column half of every tile
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
-constexpr uint32_t TC_SMEM_BYTES = TC_RING_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
 constexpr int TC_TMEM_COLS = 512;
 // Screen error allowance: a bf16-rounded operand carries relative error <= 2^-9, a product of two <= 2^-8 (+2^-18),
 // so for unit rows |screened - exact| <= 2^-8 * sum|a_k b_k| <= 2^-8, plus fp32 accumulation (<= d * 2^-24 relative to
@@ -65,6 +71,7 @@ constexpr int TC_TOPK_MAX = 64;  // the top-k variant's per-row score histogram 
 constexpr int TC_HIST_BINS = 128;
 constexpr int TC_HIST_STRIDE = 2 * TC_BM;   // one histogram per (row, column half)
 constexpr uint32_t TC_TOPK_SMEM = TC_HIST_BINS * TC_HIST_STRIDE;  // 128 bins x 256 epilogue threads x uint8 = 32 KB
+static_assert(TC_TOPK_SMEM == 32768, "TcCfg::SMEM_BYTES assumes 32 KB of histograms");
 
 struct ScreenParams {
     int64_t nq, n;
@@ -469,22 +476,25 @@ __device__ __forceinline__ void epi_chunk(EpiCtx<TOPK>& cx, uint32_t (&v)[32], i
 }
 
 // ---- the kernel ------------------------------------------------------------------------------
-template <bool TOPK, int NCTA>
+template <bool TOPK, int NCTA, bool ARES>
 __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_constant__ CUtensorMap tmap_q,
                                                                   const __grid_constant__ CUtensorMap tmap_x,
                                                                   const ScreenParams p) {
-    typedef TcCfg<NCTA> Cfg;
+    typedef TcCfg<NCTA, ARES, TOPK> Cfg;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     // (the dynamic smem window starts at the same offset in both CTAs of a pair, so the aligned offsets agree)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_RING_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OPERAND_BYTES);
     const uint32_t bar_full = smem_u32(bars);                              // [STAGES]  (pair: the leader's are used)
     const uint32_t bar_empty = smem_u32(bars + TC_MAX_STAGES);             // [STAGES]
     const uint32_t bar_acc_full = smem_u32(bars + 2 * TC_MAX_STAGES);      // [2]
     const uint32_t bar_acc_empty = smem_u32(bars + 2 * TC_MAX_STAGES + 2); // [2]      (pair: the leader's are used)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 4);
-    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_a_full = smem_u32(bars + 2 * TC_MAX_STAGES + 4);    // ARES: resident A landed (leader's used)
+    const uint32_t bar_a_empty = smem_u32(bars + 2 * TC_MAX_STAGES + 5);   // ARES: the unit's MMAs retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 6);
+    const uint32_t smem_base = smem_u32(smem);                 // ARES: resident A, slab ks at + ks * 16 KB
+    const uint32_t ring_base = smem_base + Cfg::A_RES_BYTES;   // operand ring
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool tracing = p.trace != nullptr;
@@ -502,6 +512,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
             mbar_init(bar_acc_full + 8 * a, 1);
             mbar_init(bar_acc_empty + 8 * a, TC_EPI_WARPS * NCTA);  // one arrive per epilogue warp of the pair
         }
+        mbar_init(bar_a_full, 1);
+        mbar_init(bar_a_empty, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -529,19 +541,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
         // ===================== TMA producer (every CTA: its own A rows, its share of the B slab) =====================
         if (lane == 0) {
             int stage = 0;
-            uint32_t phase = 0;
+            uint32_t phase = 0, a_phase = 0;
             unsigned long long t_wait = 0;
             for (int64_t u = group; u < p.num_units; u += num_groups) {
                 const int split = (int)(u % p.splits);
                 const int64_t row_block = (u / p.splits) * NCTA + cta_rank;
                 const int64_t ct0 = (int64_t)split * p.tiles_per_split;
                 const int64_t ct1 = min(ct0 + p.tiles_per_split, n_col_tiles);
+                if constexpr (ARES) {
+                    // the previous unit's MMAs have retired -> replace the resident A rows (all K slabs, one barrier)
+                    mbar_wait_traced(bar_a_empty, a_phase ^ 1, p.error_flag, t_wait, tracing);
+                    if (cta_rank == 0) mbar_expect_tx(bar_a_full, 2 * (uint32_t)p.num_k_slabs * TC_A_BYTES);
+                    for (int ks = 0; ks < p.num_k_slabs; ++ks)
+                        tma_load_2d_pair(&tmap_q, smem_base + ks * TC_A_BYTES, bar_a_full, ks * TC_BK,
+                                         (int)(row_block * TC_BM));
+                    a_phase ^= 1;
+                }
                 for (int64_t ct = ct0; ct < ct1; ++ct) {
                     for (int ks = 0; ks < p.num_k_slabs; ++ks) {
                         mbar_wait_traced(bar_empty + 8 * stage, phase ^ 1, p.error_flag, t_wait, tracing);
-                        const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
-                        const uint32_t b_dst = a_dst + TC_A_BYTES;
-                        if constexpr (NCTA == 2) {
+                        const uint32_t a_dst = ring_base + stage * Cfg::STAGE_BYTES;
+                        const uint32_t b_dst = ARES ? a_dst : a_dst + TC_A_BYTES;
+                        if constexpr (ARES) {
+                            if (cta_rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * Cfg::STAGE_BYTES);
+                            tma_load_2d_pair(&tmap_x, b_dst, bar_full + 8 * stage, ks * TC_BK,
+                                             (int)(ct * TC_BN + cta_rank * Cfg::B_ROWS));
+                        } else if constexpr (NCTA == 2) {
                             // both CTAs' bytes complete on the LEADER's full barrier
                             if (cta_rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * Cfg::STAGE_BYTES);
                             tma_load_2d_pair(&tmap_q, a_dst, bar_full + 8 * stage, ks * TC_BK, (int)(row_block * TC_BM));
@@ -567,13 +592,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
-            uint32_t acc_phase = 0;
+            uint32_t acc_phase = 0, a_phase = 0;
             unsigned long long t_acc = 0, t_smem = 0;
             const long long t_begin = tracing ? clock64() : 0;
             for (int64_t u = group; u < p.num_units; u += num_groups) {
                 const int split = (int)(u % p.splits);
                 const int64_t ct0 = (int64_t)split * p.tiles_per_split;
                 const int64_t ct1 = min(ct0 + p.tiles_per_split, n_col_tiles);
+                if constexpr (ARES) {
+                    mbar_wait_traced(bar_a_full, a_phase, p.error_flag, t_smem, tracing);
+                    tc_fence_after();
+                    a_phase ^= 1;
+                }
                 for (int64_t ct = ct0; ct < ct1; ++ct) {
                     mbar_wait_traced(bar_acc_empty + 8 * acc, acc_phase ^ 1, p.error_flag, t_acc, tracing);
                     tc_fence_after();
@@ -581,9 +611,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
                     for (int ks = 0; ks < p.num_k_slabs; ++ks) {
                         mbar_wait_traced(bar_full + 8 * stage, phase, p.error_flag, t_smem, tracing);
                         tc_fence_after();
-                        const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
-                        const uint64_t da = umma_smem_desc(a_addr);
-                        const uint64_t db = umma_smem_desc(a_addr + TC_A_BYTES);
+                        const uint32_t st_addr = ring_base + stage * Cfg::STAGE_BYTES;
+                        const uint64_t da = umma_smem_desc(ARES ? smem_base + ks * TC_A_BYTES : st_addr);
+                        const uint64_t db = umma_smem_desc(ARES ? st_addr : st_addr + TC_A_BYTES);
 #pragma unroll
                         for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
                             // advancing 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the address field
@@ -608,6 +638,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
                     acc ^= 1;
                     if (acc == 0) acc_phase ^= 1;
                 }
+                if constexpr (ARES) umma_commit_pair(bar_a_empty);   // the resident A rows may be replaced (both CTAs)
             }
             if (tracing) {
                 atomicAdd(p.trace + 1, t_acc);    // MMA issuer stalled on a free accumulator (epilogue too slow)
@@ -631,7 +662,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
         cx.tracing = tracing;
         cx.n_trig = 0;
         cx.n_chunks = 0;
-        if constexpr (TOPK) cx.hist = smem + TC_RING_BYTES + 256 + half * TC_BM + row_in_tile;
+        if constexpr (TOPK) cx.hist = smem + Cfg::OPERAND_BYTES + 256 + half * TC_BM + row_in_tile;
         for (int64_t u = group; u < p.num_units; u += num_groups) {
             const int split = (int)(u % p.splits);
             const int64_t row_block = (u / p.splits) * NCTA + cta_rank;
@@ -1007,6 +1038,16 @@ static int screen_ncta() {
     return cached;
 }
 
+// SLIC_SCREEN_ARES=0 keeps A streaming (experiments / fallback)
+static bool screen_ares_allowed() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("SLIC_SCREEN_ARES");
+        cached = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    return cached != 0;
+}
+
 static ScreenPlan plan_screen(int64_t nq, int64_t n) {
     const int ncta = screen_ncta();
     const int64_t row_blocks = ceil_div(nq, TC_BM * ncta), col_tiles = ceil_div(n, TC_BN);
@@ -1094,13 +1135,23 @@ static int launch_screen(const uint16_t* q_bf16, int64_t nq, const uint16_t* x_b
     p.trace = g_trace;
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const ScreenParams);
     const bool is_topk = topk > 0;
-    KernelFn fn = ncta == 2 ? (is_topk ? (KernelFn)nn_screen_kernel<true, 2> : (KernelFn)nn_screen_kernel<false, 2>)
-                            : (is_topk ? (KernelFn)nn_screen_kernel<true, 1> : (KernelFn)nn_screen_kernel<false, 1>);
-    const size_t smem_bytes = TC_SMEM_BYTES + (is_topk ? TC_TOPK_SMEM : 0);
-    static bool attr_done[64][4] = {{false}};
+    const bool ares = ncta == 2 && p.num_k_slabs <= TC_ARES_MAX_SLABS && screen_ares_allowed();
+    KernelFn fn;
+    size_t smem_bytes;
+    if (ares) {
+        fn = is_topk ? (KernelFn)nn_screen_kernel<true, 2, true> : (KernelFn)nn_screen_kernel<false, 2, true>;
+        smem_bytes = is_topk ? TcCfg<2, true, true>::SMEM_BYTES : TcCfg<2, true, false>::SMEM_BYTES;
+    } else if (ncta == 2) {
+        fn = is_topk ? (KernelFn)nn_screen_kernel<true, 2, false> : (KernelFn)nn_screen_kernel<false, 2, false>;
+        smem_bytes = is_topk ? TcCfg<2, false, true>::SMEM_BYTES : TcCfg<2, false, false>::SMEM_BYTES;
+    } else {
+        fn = is_topk ? (KernelFn)nn_screen_kernel<true, 1, false> : (KernelFn)nn_screen_kernel<false, 1, false>;
+        smem_bytes = is_topk ? TcCfg<1, false, true>::SMEM_BYTES : TcCfg<1, false, false>::SMEM_BYTES;
+    }
+    static bool attr_done[64][8] = {{false}};
     int dev = 0;
     SLIC_CUDA_OK(cudaGetDevice(&dev));
-    bool& attr_set = attr_done[dev & 63][(ncta == 2 ? 2 : 0) + (is_topk ? 1 : 0)];
+    bool& attr_set = attr_done[dev & 63][(ares ? 4 : 0) + (ncta == 2 ? 2 : 0) + (is_topk ? 1 : 0)];
     if (!attr_set) {
         SLIC_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         attr_set = true;
