@@ -183,6 +183,19 @@ int slic_compose_labels(const int32_t* prev_dev, const int32_t* u_dev, int64_t n
 int slic_segmented_mean(const float* data_dev, const int32_t* labels_dev, int64_t n, int32_t d,
                         int32_t num_clust, double* out_dev, slic_stream_t stream);
 
+/* The same reduction with the float64 SUMS and the row counts kept, so that the next FINCH level can be formed
+ * from this one instead of from the N original rows: the clusters of level l+1 are unions of clusters of level l
+ * (get_merge composes the labels, finch.py:74-79), hence sums_{l+1}[c] = sum of sums_l[p] over u[p] == c.
+ * means_out_dev (optional) = sums / counts - the matrix cool_mean returns (finch.py:58-71). */
+int slic_cluster_sums(const float* data_dev, const int32_t* labels_dev, int64_t n, int32_t d,
+                      int32_t num_clust, double* sums_out_dev, int32_t* counts_out_dev,
+                      double* means_out_dev, slic_stream_t stream);
+/* labels_dev[p] in [0, num_clust) is the level-(l+1) cluster of level-l cluster p (the `u` of get_clust). */
+int slic_merge_cluster_sums(const double* sums_prev_dev, const int32_t* counts_prev_dev,
+                            const int32_t* labels_dev, int64_t n_prev, int32_t d, int32_t num_clust,
+                            double* sums_out_dev, int32_t* counts_out_dev, double* means_out_dev,
+                            slic_stream_t stream);
+
 /* ---- K4: label-equality masks and grouping ------------------------------------------------ */
 /* models/infoNCE.py:281-283, loss/triplet_loss.py:136-142,254-261,291-297:
  * out[i, prepend + j] = (a[i] == b[j]) ^ negate as one byte per entry (torch.bool layout),

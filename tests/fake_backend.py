@@ -160,6 +160,20 @@ class FakeBackend:
         return torch.from_numpy(out / np.bincount(lab, minlength=num_clust)[:, None])
 
     # K4
+    def cluster_sums(self, data, labels, num_clust):
+        x, lab = _np(data).astype(np.float64), _np(labels).astype(np.int64)
+        sums = np.zeros((num_clust, x.shape[1]))
+        np.add.at(sums, lab, x)
+        counts = np.bincount(lab, minlength=num_clust).astype(np.int32)
+        return torch.from_numpy(sums), torch.from_numpy(counts), torch.from_numpy(sums / counts[:, None])
+
+    def merge_cluster_sums(self, sums_prev, counts_prev, u, num_clust):
+        sp, cp, lab = _np(sums_prev), _np(counts_prev).astype(np.int64), _np(u).astype(np.int64)
+        sums = np.zeros((num_clust, sp.shape[1]))
+        np.add.at(sums, lab, sp)
+        counts = np.bincount(lab, weights=cp, minlength=num_clust).astype(np.int32)
+        return torch.from_numpy(sums), torch.from_numpy(counts), torch.from_numpy(sums / counts[:, None])
+
     def label_mask(self, a, b, prepend_ones=False, negate=False):
         m = (_np(a)[:, None] == _np(b)[None, :]) != negate
         if prepend_ones:

@@ -92,6 +92,27 @@ def test_compose_and_segmented_mean(be):
                                fo.cluster_means(xo, lab), rtol=0, atol=1e-11)
 
 
+def test_cluster_sums_and_hierarchical_merge(be):
+    """slic_cluster_sums / slic_merge_cluster_sums: the level l+1 means formed from the level-l float64 sums equal
+    cool_mean over the original rows (finch.py:58-71) to float64 rounding, at every size of cluster."""
+    x = synth.gaussian_mixture(30000, 256, 40, 11)
+    rng = np.random.default_rng(1)
+    lab0 = np.unique(rng.integers(0, 4000, len(x)), return_inverse=True)[1].astype(np.int32)
+    c0 = int(lab0.max()) + 1
+    sums, counts, means = be.cluster_sums(dev(be, x), dev(be, lab0), c0)
+    assert np.array_equal(counts.cpu().numpy(), np.bincount(lab0, minlength=c0))
+    np.testing.assert_allclose(means.cpu().numpy(), fo.cluster_means(x, lab0), rtol=0, atol=1e-11)
+    cur = lab0
+    for c_next in (300, 7, 1):
+        u = np.unique(rng.integers(0, c_next, int(cur.max()) + 1), return_inverse=True)[1].astype(np.int32)
+        k = int(u.max()) + 1
+        sums, counts, means = be.merge_cluster_sums(sums, counts, dev(be, u), k)
+        cur = u[cur]
+        assert np.array_equal(counts.cpu().numpy(), np.bincount(cur, minlength=k))
+        np.testing.assert_allclose(means.cpu().numpy(), fo.cluster_means(x, cur), rtol=0, atol=1e-11)
+        np.testing.assert_allclose(sums.cpu().numpy(), fo.cluster_means(x, cur) * np.bincount(cur)[:, None], rtol=1e-12)
+
+
 def test_label_masks(be):
     rng = np.random.default_rng(4)
     for (na, nb) in [(1, 1), (37, 301), (64, 64), (1024, 65536), (5, 4099)]:

@@ -35,6 +35,8 @@ SIGNATURES = {
     "slic_finch_closest_link": [_ptr, _i64, _ptr, _i32, _i32, _ptr, _ptr, _ptr],
     "slic_compose_labels": [_ptr, _ptr, _i64, _ptr, _ptr],
     "slic_segmented_mean": [_ptr, _ptr, _i64, _i32, _i32, _ptr, _ptr],
+    "slic_cluster_sums": [_ptr, _ptr, _i64, _i32, _i32, _ptr, _ptr, _ptr, _ptr],
+    "slic_merge_cluster_sums": [_ptr, _ptr, _ptr, _i64, _i32, _i32, _ptr, _ptr, _ptr, _ptr],
     "slic_label_mask_u8": [_ptr, _i64, _ptr, _i64, _i32, _i32, _ptr, _ptr],
     "slic_label_mask_bits": [_ptr, _i64, _ptr, _i64, _i32, _ptr, _ptr],
     "slic_group_by_label": [_ptr, _i64, _i32, _ptr, _ptr, _ptr],

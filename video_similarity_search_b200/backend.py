@@ -37,6 +37,7 @@ class CudaBackend:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.slic_require_device(), "slic_require_device")
         self.last_stats = None
+        self._stage = None
 
     # -- plumbing ------------------------------------------------------------------------------
     def _stream(self):
@@ -54,10 +55,13 @@ class CudaBackend:
     def to_host(self, t):
         """Device -> numpy through a pinned staging buffer (a pageable D2H of the [N, P] label matrix costs
         milliseconds; pinned it is PCIe-bound)."""
-        if t.numel() * t.element_size() < (1 << 16):
+        nbytes = t.numel() * t.element_size()
+        if nbytes < (1 << 16):
             return t.cpu().numpy()
         t = t.contiguous()
-        stage = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        if self._stage is None or self._stage.numel() < nbytes:      # grow-only pinned staging (cudaHostAlloc is ~1 ms)
+            self._stage = torch.empty(max(nbytes, 1 << 22), dtype=torch.uint8, pin_memory=True)
+        stage = self._stage[:nbytes].view(t.dtype).view(t.shape)
         stage.copy_(t, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return stage.numpy().copy()
@@ -202,6 +206,26 @@ class CudaBackend:
         out = torch.empty((num_clust, d), dtype=torch.float64, device=data.device)
         _lib.call("slic_segmented_mean", _p(data), _p(labels), n, d, num_clust, _p(out), self._stream())
         return out
+
+    def cluster_sums(self, data, labels, num_clust):
+        """-> (sums f64 [C,d], counts int32 [C], means f64 [C,d]) of the float32 rows (slic_cluster_sums)."""
+        n, d = data.shape
+        sums = torch.empty((num_clust, d), dtype=torch.float64, device=data.device)
+        means = torch.empty((num_clust, d), dtype=torch.float64, device=data.device)
+        counts = torch.empty(num_clust, dtype=torch.int32, device=data.device)
+        _lib.call("slic_cluster_sums", _p(data), _p(labels), n, d, num_clust, _p(sums), _p(counts), _p(means),
+                  self._stream())
+        return sums, counts, means
+
+    def merge_cluster_sums(self, sums_prev, counts_prev, u, num_clust):
+        """Sums / counts / means of the next level from those of this one (slic_merge_cluster_sums)."""
+        n_prev, d = sums_prev.shape
+        sums = torch.empty((num_clust, d), dtype=torch.float64, device=sums_prev.device)
+        means = torch.empty((num_clust, d), dtype=torch.float64, device=sums_prev.device)
+        counts = torch.empty(num_clust, dtype=torch.int32, device=sums_prev.device)
+        _lib.call("slic_merge_cluster_sums", _p(sums_prev), _p(counts_prev), _p(u), n_prev, d, num_clust, _p(sums),
+                  _p(counts), _p(means), self._stream())
+        return sums, counts, means
 
     # -- K4 --------------------------------------------------------------------------------------
     def label_mask(self, a, b, prepend_ones=False, negate=False):

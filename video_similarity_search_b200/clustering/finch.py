@@ -62,15 +62,30 @@ def _clust(be, lvl, min_sim):
     return be.components(lvl.nn)
 
 
-def _merge(be, prev, u, data, num_clust):
-    """finch.py:74-82: compose the labels, recompute the float64 centroids of the ORIGINAL rows."""
+class _Sums:
+    """float64 row sums and row counts of the current partition's clusters (device)."""
+
+    def __init__(self, sums, counts):
+        self.sums, self.counts = sums, counts
+
+
+def _merge(be, prev, u, data, num_clust, state=None):
+    """finch.py:74-82: compose the labels and return the float64 centroids of the ORIGINAL rows.
+    The reference re-reads all N rows at every level (cool_mean, :58-71).  The clusters of a level are unions
+    of the previous level's clusters, so here only level 0 reads the rows; later levels add the previous level's
+    per-cluster float64 sums (slic_merge_cluster_sums) - the same means to float64 rounding.
+    Returns (labels [N], means [C, D], _Sums)."""
     cur = be.compose_labels(prev, u)
-    return cur, be.segmented_mean(data, cur, num_clust)
+    if state is None:
+        sums, counts, means = be.cluster_sums(data, cur, num_clust)
+    else:
+        sums, counts, means = be.merge_cluster_sums(state.sums, state.counts, u, num_clust)
+    return cur, means, _Sums(sums, counts)
 
 
 def _req_numclust(be, labels, n_labels, data, req_clust):
     """finch.py:97-105: merge the closest linked pair until req_clust clusters remain."""
-    cur, mat = _merge(be, None, labels, data, n_labels)
+    cur, mat, state = _merge(be, None, labels, data, n_labels)
     for _ in range(n_labels - req_clust):
         n = mat.shape[0]
         lvl = _rank(be, mat, None)
@@ -78,7 +93,7 @@ def _req_numclust(be, labels, n_labels, data, req_clust):
         link = torch.arange(n, dtype=torch.int32, device=mat.device)
         link[j] = i                                                 # the single surviving link
         u, cnt = be.components(link)
-        cur, mat = _merge(be, cur, u, data, cnt)
+        cur, mat, state = _merge(be, cur, u, data, cnt, state)
     return cur
 
 
@@ -111,7 +126,7 @@ def FINCH(data, initial_rank=None, req_clust=None, distance='cosine', ensure_ear
     min_sim = None
     lvl = _rank(be, data, initial_rank, first_neighbors)            # finch.py:134
     group, n0 = _clust(be, lvl, None)                               # finch.py:136
-    c_, mat = _merge(be, None, group, data, n0)                     # finch.py:137
+    c_, mat, state = _merge(be, None, group, data, n0)              # finch.py:137
     if verbose:
         print('Partition 0: {} clusters'.format(n0))
     if ensure_early_exit and lvl.dense and lvl.dist is not None and data.shape[0] > 1:
@@ -124,7 +139,7 @@ def FINCH(data, initial_rank=None, req_clust=None, distance='cosine', ensure_ear
     while exit_clust > 1:                                           # finch.py:151
         lvl = _rank(be, mat, None)
         u, cur = _clust(be, lvl, min_sim)
-        c_, mat = _merge(be, c_, u, data, cur)
+        c_, mat, state = _merge(be, c_, u, data, cur, state)
         num_clust.append(cur)
         columns.append(c_)
         exit_clust = num_clust[-2] - cur
