@@ -37,6 +37,14 @@ def _worker(rank, world, port, name, golden_dir, out_dir):
         assert torch.equal(nn, full_nn) and torch.equal(d, full_d)
         # only this rank's shard was searched locally
         assert [c[3] for c in be.calls if c[0] == "first_neighbors"] == [(r0, r1)]
+        # query-sharded retrieval top-k: identical to the unsharded search on every rank (ragged last shard included)
+        from video_similarity_search_b200.sharded import topk_neighbors_sharded
+        xt = be.to_device(x, torch.float32)
+        qt = xt[: max(7, n // 3)].clone()
+        for same, qq in ((False, qt), (True, xt)):
+            gi, gd = topk_neighbors_sharded(qq, xt, 5, same=same, backend=be)
+            ei, ed = FakeBackend().topk_neighbors(qq, xt, 5, same=same)
+            assert torch.equal(gi, ei) and torch.equal(gd, ed)
         c, num_clust, _ = FINCH_sharded(x, backend=FakeBackend(), verbose=False)
         np.save(os.path.join(out_dir, "c_rank%d.npy" % rank), c)
         g = np.load(os.path.join(golden_dir, name + ".npz"))

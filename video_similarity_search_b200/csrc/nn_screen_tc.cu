@@ -51,8 +51,12 @@ template <int NCTA, bool ARES, bool TOPK> struct TcCfg {
     static constexpr uint32_t B_ROWS = TC_BN / NCTA;
     static constexpr uint32_t B_BYTES = B_ROWS * TC_BK * 2;
     static constexpr uint32_t A_RES_BYTES = ARES ? TC_ARES_MAX_SLABS * TC_A_BYTES : 0;      // 128 KB
-    static constexpr uint32_t STAGE_BYTES = ARES ? B_BYTES : TC_A_BYTES + B_BYTES;
-    static constexpr int STAGES = ARES ? (TOPK ? 4 : 6) : (NCTA == 1 ? 4 : 6);
+    // K slabs per ring stage: the A-resident top-1 kernel moves two (32 KB of B per CTA and barrier round trip,
+    // 8 MMAs per wait / commit); the top-k variant has 32 KB less shared memory and keeps four single-slab stages
+    static constexpr int SPS = NCTA == 2 ? 2 : 1;
+    static constexpr uint32_t SLAB_BYTES = ARES ? B_BYTES : TC_A_BYTES + B_BYTES;   // one K slab of a stage
+    static constexpr uint32_t STAGE_BYTES = SPS * SLAB_BYTES;
+    static constexpr int STAGES = ARES ? (TOPK ? 2 : 3) : (NCTA == 1 ? 4 : 3);
     static constexpr uint32_t OPERAND_BYTES = A_RES_BYTES + STAGES * STAGE_BYTES;            // 192 KB, ARES: 192 / 224 KB
     static constexpr uint32_t SMEM_BYTES = OPERAND_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/ +
                                            (TOPK ? 32768u : 0u) /*histograms*/;
@@ -558,20 +562,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
                     a_phase ^= 1;
                 }
                 for (int64_t ct = ct0; ct < ct1; ++ct) {
-                    for (int ks = 0; ks < p.num_k_slabs; ++ks) {
+                    for (int ks = 0; ks < p.num_k_slabs; ks += Cfg::SPS) {
                         mbar_wait_traced(bar_empty + 8 * stage, phase ^ 1, p.error_flag, t_wait, tracing);
                         const uint32_t a_dst = ring_base + stage * Cfg::STAGE_BYTES;
                         const uint32_t b_dst = ARES ? a_dst : a_dst + TC_A_BYTES;
                         if constexpr (ARES) {
-                            if (cta_rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * Cfg::STAGE_BYTES);
-                            tma_load_2d_pair(&tmap_x, b_dst, bar_full + 8 * stage, ks * TC_BK,
-                                             (int)(ct * TC_BN + cta_rank * Cfg::B_ROWS));
+                            const int nsl = min(Cfg::SPS, p.num_k_slabs - ks);
+                            if (cta_rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * (uint32_t)nsl * Cfg::B_BYTES);
+                            for (int j = 0; j < nsl; ++j)
+                                tma_load_2d_pair(&tmap_x, b_dst + j * Cfg::SLAB_BYTES, bar_full + 8 * stage, (ks + j) * TC_BK,
+                                                 (int)(ct * TC_BN + cta_rank * Cfg::B_ROWS));
                         } else if constexpr (NCTA == 2) {
                             // both CTAs' bytes complete on the LEADER's full barrier
-                            if (cta_rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * Cfg::STAGE_BYTES);
-                            tma_load_2d_pair(&tmap_q, a_dst, bar_full + 8 * stage, ks * TC_BK, (int)(row_block * TC_BM));
-                            tma_load_2d_pair(&tmap_x, b_dst, bar_full + 8 * stage, ks * TC_BK,
-                                             (int)(ct * TC_BN + cta_rank * Cfg::B_ROWS));
+                            const int nsl = min(Cfg::SPS, p.num_k_slabs - ks);
+                            if (cta_rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * (uint32_t)nsl * Cfg::SLAB_BYTES);
+                            for (int j = 0; j < nsl; ++j) {
+                                tma_load_2d_pair(&tmap_q, a_dst + j * Cfg::SLAB_BYTES, bar_full + 8 * stage, (ks + j) * TC_BK,
+                                                 (int)(row_block * TC_BM));
+                                tma_load_2d_pair(&tmap_x, b_dst + j * Cfg::SLAB_BYTES, bar_full + 8 * stage, (ks + j) * TC_BK,
+                                                 (int)(ct * TC_BN + cta_rank * Cfg::B_ROWS));
+                            }
                         } else {
                             mbar_expect_tx(bar_full + 8 * stage, Cfg::STAGE_BYTES);
                             tma_load_2d(&tmap_q, a_dst, bar_full + 8 * stage, ks * TC_BK, (int)(row_block * TC_BM));
@@ -608,21 +618,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
                     mbar_wait_traced(bar_acc_empty + 8 * acc, acc_phase ^ 1, p.error_flag, t_acc, tracing);
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TC_BN);
-                    for (int ks = 0; ks < p.num_k_slabs; ++ks) {
+                    for (int ks = 0; ks < p.num_k_slabs; ks += Cfg::SPS) {
                         mbar_wait_traced(bar_full + 8 * stage, phase, p.error_flag, t_smem, tracing);
                         tc_fence_after();
                         const uint32_t st_addr = ring_base + stage * Cfg::STAGE_BYTES;
-                        const uint64_t da = umma_smem_desc(ARES ? smem_base + ks * TC_A_BYTES : st_addr);
-                        const uint64_t db = umma_smem_desc(ARES ? st_addr : st_addr + TC_A_BYTES);
 #pragma unroll
-                        for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
-                            // advancing 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the address field
-                            if constexpr (NCTA == 2)
-                                umma_bf16_pair(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), TC_IDESC_PAIR,
-                                               (uint32_t)((ks | k) != 0));
-                            else
-                                umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), TC_IDESC,
-                                          (uint32_t)((ks | k) != 0));
+                        for (int j = 0; j < Cfg::SPS; ++j) {
+                            if (ks + j < p.num_k_slabs) {
+                                const uint32_t sl_addr = st_addr + j * Cfg::SLAB_BYTES;
+                                const uint64_t da = umma_smem_desc(ARES ? smem_base + (ks + j) * TC_A_BYTES : sl_addr);
+                                const uint64_t db = umma_smem_desc(ARES ? sl_addr : sl_addr + TC_A_BYTES);
+#pragma unroll
+                                for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+                                    // advancing 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the address field
+                                    if constexpr (NCTA == 2)
+                                        umma_bf16_pair(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), TC_IDESC_PAIR,
+                                                       (uint32_t)((ks | j | k) != 0));
+                                    else
+                                        umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), TC_IDESC,
+                                                  (uint32_t)((ks | j | k) != 0));
+                                }
+                            }
                         }
                         // frees the smem stage (in both CTAs of a pair) once these MMAs retire
                         if constexpr (NCTA == 2) umma_commit_pair(bar_empty + 8 * stage);

@@ -55,6 +55,36 @@ def FINCH_sharded(data, group=None, backend=None, **kwargs):
     return FINCH(data, backend=be, first_neighbors=sharded_first_neighbors(be, group), **kwargs)
 
 
+def topk_neighbors_sharded(q, x, k, same=False, group=None, backend=None):
+    """Retrieval top-k (iic_retrieve_clips.py:295-296, evaluate.py:226-231) with the QUERY rows sharded over
+    the process group and the database replicated: rank r searches rows [r * ceil(Q / G), ...) against all of
+    x, then the [Q, k] ids and distances are all-gathered (8 * Q * k bytes in total).  same=True: q is x and
+    every row excludes itself.  Every rank must pass the same q and x; every rank returns the same result."""
+    be = backend or _backend.default_backend()
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return be.topk_neighbors(q, x, k, same=same)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    nq = q.shape[0]
+    r0, r1, per = shard_range(nq, rank, world)
+    idx_pad = torch.full((per, k), -1, dtype=torch.int32, device=x.device)
+    d_pad = torch.zeros((per, k), dtype=x.dtype, device=x.device)
+    if r1 > r0:
+        use_screen = x.shape[0] >= _backend.SCREEN_MIN_ROWS and k <= _backend.TOPK_SCREEN_MAX_K
+        ux, xb = be.normalize_rows(x, want_bf16=use_screen)
+        if same:
+            uq, qb = ux[r0:r1], (xb[r0:r1] if xb is not None else None)
+        else:
+            uq, qb = be.normalize_rows(q[r0:r1].contiguous(), want_bf16=use_screen)
+        idx, d = be.topk_cosine(uq, ux, k, self_offset=r0 if same else -1, q_bf16=qb, x_bf16=xb)
+        idx_pad[: r1 - r0] = idx
+        d_pad[: r1 - r0] = d
+    idx_all = torch.empty((per * world, k), dtype=torch.int32, device=x.device)
+    d_all = torch.empty((per * world, k), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(idx_all, idx_pad, group=group)
+    dist.all_gather_into_tensor(d_all, d_pad, group=group)
+    return idx_all[:nq].contiguous(), d_all[:nq].contiguous()
+
+
 def replicate(data, src=0, group=None, backend=None):
     """Broadcast the [N, D] float32 matrix held by rank `src` to every rank's GPU (NCCL over NVLink)."""
     be = backend or _backend.default_backend()
