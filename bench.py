@@ -51,6 +51,12 @@ def parse_args():
     return ap.parse_args()
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed
+# `ncu --set full` capture (profiles/r1_screen_kernel_ncu_full.txt); keyed by (workload, ranks).  Not measured live:
+# a number taken under the profiler's replay is evidence of traffic, never of time.
+NCU_TRAFFIC_BYTES = {("C3", 1): 4.493117e9 + 159.316224e6}
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -145,6 +151,8 @@ def run_reference(args):
 # GPU side
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled from a thread every ~10 ms
+    (nvidia-smi -lms 100 as the fallback when pynvml cannot initialise)."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -152,16 +160,62 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.gpu_index = gpu_index
         self.proc = None
+        self.thread = None
+        self.stop_flag = False
+        self.sm, self.power, self.reasons, self.max_mhz = [], [], set(), None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.gpu_index < len(ids) and ids[self.gpu_index].isdigit():
+                return int(ids[self.gpu_index])
+        return self.gpu_index
+
+    def _poll(self, nv, handle):
+        names = [("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
+                 ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
+                 ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap),
+                 ("hw_power_brake_slowdown", nv.nvmlClocksEventReasonHwPowerBrakeSlowdown)]
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(handle) / 1000.0)
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                for name, bit in names:
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY,
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            handle = nv.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, args=(nv, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self._physical_index()), "--query-gpu=" + self.QUERY,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                    "samples": len(self.sm), "power_w_max": max(self.power) if self.power else None,
+                    "reasons": sorted(self.reasons), "how": "NVML polled every 10 ms during the timed steps"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -185,7 +239,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "how": "nvidia-smi -lms 100 during the timed steps"}
 
 
 def run_b200(args):
@@ -305,7 +359,8 @@ def run_b200(args):
                      "bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                      "frac": achieved_tf / peaks["bf16_tflops"], "peak_source": peaks["source"] + " burst bf16",
                      "frac_of_sustained": (achieved_tf / peaks["bf16_tflops_sustained"]) if peaks.get("bf16_tflops_sustained") else None,
-                     "kernel_ms": screen_ms_avg, "flop_per_launch": flop.value, "traffic": None},
+                     "kernel_ms": screen_ms_avg, "flop_per_launch": flop.value,
+                     "traffic": NCU_TRAFFIC_BYTES.get((args.workload, world)), "traffic_unit": "bytes/launch (ncu dram read+write)"},
     }
     if world == 1 and not args.no_cpu_baseline:
         nn_dev, _, _ = be.first_neighbors(x_dev)

@@ -214,10 +214,50 @@ int slic_label_mask_bits(const int64_t* a_dev, int64_t na, const int64_t* b_dev,
 int slic_group_by_label(const int32_t* labels_dev, int64_t n, int32_t num_labels,
                         int32_t* order_out_dev, int32_t* offsets_out_dev, slic_stream_t stream);
 
+/* ---- the whole hierarchy in one call ---------------------------------------------------------- */
+/* clustering/finch.py:108-167 (FINCH without the req_clust refinement): level loop, exit rules
+ * (:151-163), min_sim mode (:142-144, only when level 0 had dense distances), label composition
+ * and float64 centroids, all on `stream`; the host reads one int per level.
+ *   nn0_dev == NULL : level 0 is searched here (normalise + tcgen05 screen + exact re-rank, or the
+ *                     exact kernel below 2048 rows); dense distances "exist" iff n <= 70 000 (:30).
+ *   nn0_dev != NULL : level-0 first neighbours supplied - FINCH's initial_rank (dist0/unit0 NULL,
+ *                     level0_dense 0) or an external search such as the row-sharded multi-GPU one
+ *                     (dist0_dev [n] float32, unit0_dev [n, d] float32, level0_dense as above).
+ * labels_out_dev: room for [n, capacity] int32; on return its first n * P entries are the [n, P]
+ * C-contiguous matrix `c` of the reference (column l = partition l).  num_clust_out_host [capacity],
+ * *num_levels_out_host = P.  SLIC_ERR_OVERFLOW if the hierarchy has more than `capacity` levels. */
+/* clustering/finch.py:19 (FLANN_THRESHOLD = 70000, a module constant): the row count above which the
+ * reference holds no dense distances (no min_sim filter at that level).  Default 70000. */
+int slic_set_flann_threshold(int64_t rows);
+
+int slic_finch(const float* data_dev, int64_t n, int32_t d,
+               const int32_t* nn0_dev, const float* dist0_dev, const float* unit0_dev,
+               int32_t level0_dense, int32_t ensure_early_exit, int32_t capacity,
+               int32_t* labels_out_dev, int32_t* num_clust_out_host, int32_t* num_levels_out_host,
+               float* min_sim_out_host /* or NULL */, int32_t* has_min_sim_out_host /* or NULL */,
+               slic_stream_t stream);
+
 /* ---- host-buffer entry points (do their own H2D / D2H; block until the result is in place) -- */
 /* clustering/finch.py:22-29 for a float32/float64 host matrix: first neighbour + distance. */
 int slic_first_neighbors_host(const void* x_host, int64_t n, int32_t d, int32_t dtype,
                               int32_t* nn_out_host, void* dist_out_host);
+
+
+/* FINCH(data, initial_rank, distance='cosine', ensure_early_exit) for a float32 host matrix
+ * (numpy memory, pageable or pinned): the call a binding makes in place of clustering/finch.py:108.
+ * The host -> device copy is cut into row chunks that are normalised as they land while the
+ * level-0 tensor-core screen, launched first, consumes them (see csrc/finch_driver.cu), so the
+ * PCIe transfer is hidden behind the O(N^2 D) stage.  initial_rank_host: NULL or [n] int64.
+ * labels_out_host: room for [n, capacity] int32 (capacity <= 64); filled as [n, P] C-contiguous.
+ * Blocks until the labels are in place. */
+int slic_finch_host(const float* x_host, int64_t n, int32_t d, const int64_t* initial_rank_host,
+                    int32_t ensure_early_exit, int32_t capacity, int32_t* labels_out_host,
+                    int32_t* num_clust_out_host, int32_t* num_levels_out_host,
+                    float* min_sim_out_host /* or NULL */, int32_t* has_min_sim_out_host /* or NULL */);
+
+/* Diagnostic timeline of slic_finch_host (CUDA events): enable, run a call, then read ms_out_host[4] =
+ * {start -> first copy begins, upload duration, start -> level-0 search done, start -> labels copied back}. */
+int slic_host_trace(int32_t enable, float* ms_out_host);
 
 #ifdef __cplusplus
 }

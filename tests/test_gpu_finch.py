@@ -122,3 +122,61 @@ def test_retrieval_c2_matches_oracle(be):
         dm = ev.get_distance_matrix(xte, xtr, backend=be)
         acc = ev.get_topk_acc(dm, yte.tolist(), ytr.tolist())
         np.testing.assert_array_equal(acc, ro.topk_acc(d, yte.tolist(), ytr.tolist()))
+
+
+# ---- native driver (csrc/finch_driver.cu): slic_finch / slic_finch_host --------------------------------------
+def test_native_driver_equals_python_level_loop(be):
+    """The C++ level loop (slic_finch) and the Python-orchestrated loop (one C-ABI call per step) implement the same
+    reference lines; same inputs -> identical label matrices, in both min_sim modes."""
+    from video_similarity_search_b200.clustering import finch as fm
+    for n, d, k, seed, early in ((3000, 128, 30, 7, True), (3000, 128, 30, 7, False), (6000, 32, 50, 3, True), (1, 16, 1, 0, True),
+                                 (2, 16, 1, 0, True), (37, 8, 3, 1, True)):
+        x = synth.gaussian_mixture(n, d, k, seed)
+        dev = be.to_device(x)
+        cols, num_loop = fm._finch_loop(be, dev, None, early, False, None)
+        c_loop = torch.stack(cols, dim=1).cpu().numpy()
+        c_dev, num_dev, _ = be.finch_native(dev, ensure_early_exit=early)
+        c_host, num_host, _ = be.finch_host(x, ensure_early_exit=early)
+        assert num_loop == num_dev == num_host
+        assert np.array_equal(c_loop, c_dev.cpu().numpy()) and np.array_equal(c_loop, c_host)
+
+
+def test_host_entry_pipelined_upload_matches_resident_path(be):
+    """slic_finch_host above 32 768 rows launches the level-0 screen BEFORE the embeddings have arrived and feeds it
+    chunk by chunk (gates).  Result must equal the resident path bit for bit - pageable and pinned source, a row count
+    that is not a multiple of the chunk size, and the first neighbours must equal the oracle's on sampled rows."""
+    n, d = 100003, 128
+    x = synth.gaussian_mixture(n, d, 150, 23)
+    dev = be.to_device(x)
+    c_dev, num_dev, _ = be.finch_native(dev)
+    c_dev = c_dev.cpu().numpy()
+    c_pageable, num_pageable, _ = be.finch_host(x)
+    pinned = torch.from_numpy(x).pin_memory()
+    c_pinned, num_pinned, _ = be.finch_host(pinned.numpy())
+    assert num_dev == num_pageable == num_pinned
+    assert np.array_equal(c_dev, c_pageable) and np.array_equal(c_dev, c_pinned)
+    rows = np.arange(0, n, 97)
+    enn, _, gap = fo.first_neighbors_blocked(x, rows=rows)
+    nn, _, _ = be.first_neighbors(dev)
+    clear = gap > TIE_MARGIN_F32
+    assert np.array_equal(nn.cpu().numpy()[rows][clear], enn[clear])
+    co, no, _ = fo.finch(x, initial_rank=nn.cpu().numpy())
+    assert no == num_pinned and np.array_equal(co, c_pinned)
+
+
+def test_host_entry_initial_rank_and_overflow_path(be, monkeypatch):
+    """initial_rank through the host entry; and a label buffer that is too small (SLIC_ERR_OVERFLOW) makes FINCH
+    continue with the Python-orchestrated loop instead of failing."""
+    from video_similarity_search_b200.backend import CudaBackend
+    from video_similarity_search_b200.clustering.finch import FINCH
+    x = synth.gaussian_mixture(3000, 128, 30, 7)
+    nn, _, _ = be.first_neighbors(be.to_device(x))
+    rank = nn.cpu().numpy().astype(np.int64)
+    c, num, _ = FINCH(x, initial_rank=rank, backend=be, verbose=False)
+    co, no, _ = fo.finch(x, initial_rank=rank)
+    assert num == no and np.array_equal(c, co)
+    monkeypatch.setattr(CudaBackend, "FINCH_CAPACITY", 2)
+    c2, num2, _ = FINCH(x, initial_rank=rank, backend=be, verbose=False)
+    assert num2 == no and np.array_equal(c2, co)
+    c3, num3, _ = FINCH(torch.from_numpy(x).cuda(), initial_rank=rank, backend=be, verbose=False)
+    assert num3 == no and np.array_equal(c3, co)

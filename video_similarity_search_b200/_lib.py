@@ -41,6 +41,10 @@ SIGNATURES = {
     "slic_label_mask_bits": [_ptr, _i64, _ptr, _i64, _i32, _ptr, _ptr],
     "slic_group_by_label": [_ptr, _i64, _i32, _ptr, _ptr, _ptr],
     "slic_first_neighbors_host": [_ptr, _i64, _i32, _i32, _ptr, _ptr],
+    "slic_set_flann_threshold": [_i64],
+    "slic_host_trace": [_i32, _ptr],
+    "slic_finch": [_ptr, _i64, _i32, _ptr, _ptr, _ptr, _i32, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    "slic_finch_host": [_ptr, _i64, _i32, _ptr, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr],
 }
 _RESTYPES = {"slic_last_error": _c.c_char_p, "slic_launch_count": _c.c_int64}
 

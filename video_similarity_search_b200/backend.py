@@ -6,6 +6,9 @@ raises.  (tests/fake_backend.py provides a numpy stand-in with the same method n
 host logic in clustering/finch.py can be exercised on a box without a GPU; it is test
 infrastructure and is never selected by the product code.)
 """
+import ctypes
+
+import numpy as np
 import torch
 
 from . import _lib
@@ -226,6 +229,45 @@ class CudaBackend:
         _lib.call("slic_merge_cluster_sums", _p(sums_prev), _p(counts_prev), _p(u), n_prev, d, num_clust, _p(sums),
                   _p(counts), _p(means), self._stream())
         return sums, counts, means
+
+    # -- whole hierarchy (csrc/finch_driver.cu) ------------------------------------------------------
+    FINCH_CAPACITY = 32   # label columns provided to the native driver (a FINCH level at least halves the clusters
+                          # unless the min_sim cut intervenes; more levels -> SlicError status -5, see FINCH())
+
+    def finch_native(self, data, nn0=None, dist0=None, unit0=None, dense0=False, ensure_early_exit=True):
+        """slic_finch on a device-resident float32 matrix.  -> (c int32 [N, P] device, num_clust list, min_sim or None)."""
+        n, d = data.shape
+        cap = self.FINCH_CAPACITY
+        labels = torch.empty(n * cap, dtype=torch.int32, device=data.device)
+        num = (ctypes.c_int32 * cap)()
+        levels, has = ctypes.c_int32(0), ctypes.c_int32(0)
+        ms = ctypes.c_float(0)
+        _lib.call("slic_finch", _p(data), n, d, _p(nn0), _p(dist0), _p(unit0), int(bool(dense0)), int(bool(ensure_early_exit)),
+                  cap, _p(labels), ctypes.addressof(num), ctypes.addressof(levels), ctypes.addressof(ms),
+                  ctypes.addressof(has), self._stream())
+        p = levels.value
+        return labels[: n * p].view(n, p), [int(v) for v in num[:p]], (np.float32(ms.value) if has.value else None)
+
+    def finch_host(self, x, initial_rank=None, ensure_early_exit=True):
+        """slic_finch_host on a C-contiguous float32 numpy matrix (pageable or pinned): chunked upload hidden behind the
+        level-0 screen.  -> (c int32 [N, P] numpy, num_clust list, min_sim or None)."""
+        n, d = x.shape
+        cap = self.FINCH_CAPACITY
+        out = np.empty(n * cap, dtype=np.int32)
+        num = (ctypes.c_int32 * cap)()
+        levels, has = ctypes.c_int32(0), ctypes.c_int32(0)
+        ms = ctypes.c_float(0)
+        rank = None
+        if initial_rank is not None:
+            rank = np.ascontiguousarray(np.asarray(initial_rank), dtype=np.int64)
+            if rank.shape != (n,):
+                raise ValueError("initial_rank must have one entry per row of data")
+        with torch.cuda.device(self.device):
+            _lib.call("slic_finch_host", x.ctypes.data, n, d, None if rank is None else rank.ctypes.data,
+                      int(bool(ensure_early_exit)), cap, out.ctypes.data, ctypes.addressof(num), ctypes.addressof(levels),
+                      ctypes.addressof(ms), ctypes.addressof(has))
+        p = levels.value
+        return out[: n * p].reshape(n, p), [int(v) for v in num[:p]], (np.float32(ms.value) if has.value else None)
 
     # -- K4 --------------------------------------------------------------------------------------
     def label_mask(self, a, b, prepend_ones=False, negate=False):

@@ -25,6 +25,7 @@ Differences from the reference, all deliberate:
 import numpy as np
 import torch
 
+from .. import _lib
 from .. import backend as _backend
 
 FLANN_THRESHOLD = 70000  # finch.py:19 - above it the reference has no dense distance matrix
@@ -97,32 +98,10 @@ def _req_numclust(be, labels, n_labels, data, req_clust):
     return cur
 
 
-def FINCH(data, initial_rank=None, req_clust=None, distance='cosine', ensure_early_exit=True, verbose=True,
-          backend=None, first_neighbors=None):
-    """FINCH clustering (reference: clustering/finch.py:108-178).
-
-    :param data: [N, D] features in rows - numpy array or torch tensor (CPU or CUDA), any float dtype;
-                 cast to float32 as the reference does (finch.py:131).
-    :param initial_rank: optional [N] first-neighbour indices (skips the level-0 search and, as in the
-                 reference, disables the min_sim filter).
-    :param req_clust: optional exact number of clusters to refine to.
-    :param distance: only 'cosine'.
-    :param ensure_early_exit: apply the min_sim purity filter when level 0 had dense distances.
-    :param verbose: print 'Partition k: n clusters' lines like the reference.
-    :param backend: device backend (default: the process-wide CudaBackend).
-    :param first_neighbors: optional callable mat -> (nn, dist, unit) overriding the level-0 search
-                 (the multi-GPU row-sharded search in sharded.py plugs in here).
-    :return: c int32 [N, P] (numpy), num_clust list[int], req_c int32 [N] or None.
-    """
-    if distance != 'cosine':
-        raise NotImplementedError("only distance='cosine' is implemented (the value every reference caller passes)")
-    be = backend if backend is not None else _backend.default_backend()
-    if isinstance(data, torch.Tensor):
-        data = data.detach()
-    data = be.to_device(data, torch.float32)                        # finch.py:131
-    if data.dim() != 2 or data.shape[0] < 1:
-        raise ValueError("data must be a non-empty [N, D] matrix")
-
+def _finch_loop(be, data, initial_rank, ensure_early_exit, verbose, first_neighbors):
+    """The level loop of finch.py:134-167 driven from Python, one backend call per step.  Used with stand-in
+    backends (tests) and as the continuation when the native driver's label buffer is too small.
+    -> (columns list of device [N] labels, num_clust list)."""
     min_sim = None
     lvl = _rank(be, data, initial_rank, first_neighbors)            # finch.py:134
     group, n0 = _clust(be, lvl, None)                               # finch.py:136
@@ -150,14 +129,92 @@ def FINCH(data, initial_rank=None, req_clust=None, distance='cosine', ensure_ear
         if verbose:
             print('Partition {}: {} clusters'.format(k, num_clust[k]))
         k += 1
+    return columns, num_clust
+
+
+def _is_host_matrix(data):
+    return isinstance(data, np.ndarray) or (isinstance(data, torch.Tensor) and not data.is_cuda)
+
+
+def _finch_native(be, data, initial_rank, ensure_early_exit, first_neighbors):
+    """The hierarchy through the native driver (csrc/finch_driver.cu): ONE C-ABI call.
+    -> (c numpy [N, P], num_clust, data on the device or None)."""
+    _lib.call("slic_set_flann_threshold", int(FLANN_THRESHOLD))    # finch.py:19 is a module constant; keep it one here
+    if _is_host_matrix(data) and first_neighbors is None:
+        # the reference-facing call: host matrix in, host labels out; the upload is pipelined behind the level-0
+        # screen inside slic_finch_host
+        x = data.numpy() if isinstance(data, torch.Tensor) else data
+        x = np.ascontiguousarray(x, dtype=np.float32)               # finch.py:131
+        if x.ndim != 2 or x.shape[0] < 1:
+            raise ValueError("data must be a non-empty [N, D] matrix")
+        c, num_clust, _ = be.finch_host(x, initial_rank, ensure_early_exit)
+        return c, num_clust, None
+    dev = be.to_device(data, torch.float32)                         # finch.py:131
+    if dev.dim() != 2 or dev.shape[0] < 1:
+        raise ValueError("data must be a non-empty [N, D] matrix")
+    n = dev.shape[0]
+    nn0 = dist0 = unit0 = None
+    dense0 = False
+    if initial_rank is not None:
+        nn0 = be.to_device(np.asarray(initial_rank).astype(np.int32, copy=False), torch.int32)
+        if nn0.shape[0] != n:
+            raise ValueError("initial_rank must have one entry per row of data")
+    elif first_neighbors is not None and n > 1:
+        nn0, dist0, unit0 = first_neighbors(dev)
+        dense0 = n <= FLANN_THRESHOLD
+    c_dev, num_clust, _ = be.finch_native(dev, nn0, dist0, unit0, dense0, ensure_early_exit)
+    return be.to_host(c_dev), num_clust, dev
+
+
+def FINCH(data, initial_rank=None, req_clust=None, distance='cosine', ensure_early_exit=True, verbose=True,
+          backend=None, first_neighbors=None):
+    """FINCH clustering (reference: clustering/finch.py:108-178).
+
+    :param data: [N, D] features in rows - numpy array or torch tensor (CPU or CUDA), any float dtype;
+                 cast to float32 as the reference does (finch.py:131).
+    :param initial_rank: optional [N] first-neighbour indices (skips the level-0 search and, as in the
+                 reference, disables the min_sim filter).
+    :param req_clust: optional exact number of clusters to refine to.
+    :param distance: only 'cosine'.
+    :param ensure_early_exit: apply the min_sim purity filter when level 0 had dense distances.
+    :param verbose: print 'Partition k: n clusters' lines like the reference.
+    :param backend: device backend (default: the process-wide CudaBackend).
+    :param first_neighbors: optional callable mat -> (nn, dist, unit) overriding the level-0 search
+                 (the multi-GPU row-sharded search in sharded.py plugs in here).
+    :return: c int32 [N, P] (numpy), num_clust list[int], req_c int32 [N] or None.
+    """
+    if distance != 'cosine':
+        raise NotImplementedError("only distance='cosine' is implemented (the value every reference caller passes)")
+    be = backend if backend is not None else _backend.default_backend()
+    if isinstance(data, torch.Tensor):
+        data = data.detach()
+
+    c = None
+    dev = None
+    if hasattr(be, "finch_native"):
+        try:
+            c, num_clust, dev = _finch_native(be, data, initial_rank, ensure_early_exit, first_neighbors)
+            if verbose:
+                for k, v in enumerate(num_clust):
+                    print('Partition {}: {} clusters'.format(k, v))
+        except _lib.SlicError as e:
+            if "status -5" not in str(e):   # SLIC_ERR_OVERFLOW: more levels than the driver's label buffer holds
+                raise
+    if c is None:
+        dev = be.to_device(data, torch.float32)                     # finch.py:131
+        if dev.dim() != 2 or dev.shape[0] < 1:
+            raise ValueError("data must be a non-empty [N, D] matrix")
+        columns, num_clust = _finch_loop(be, dev, initial_rank, ensure_early_exit, verbose, first_neighbors)
+        c = be.to_host(torch.stack(columns, dim=1))
 
     req_c = None
     if req_clust is not None:                                       # finch.py:169-176
         if req_clust not in num_clust:
+            if dev is None:
+                dev = be.to_device(data, torch.float32)
             ind = [i for i, v in enumerate(num_clust) if v >= req_clust]
-            req_c = be.to_host(_req_numclust(be, columns[ind[-1]], num_clust[ind[-1]], data, req_clust))
+            col = be.to_device(np.ascontiguousarray(c[:, ind[-1]]), torch.int32)
+            req_c = be.to_host(_req_numclust(be, col, num_clust[ind[-1]], dev, req_clust))
         else:
-            req_c = be.to_host(columns[num_clust.index(req_clust)])
-
-    c = be.to_host(torch.stack(columns, dim=1))
+            req_c = np.ascontiguousarray(c[:, num_clust.index(req_clust)])
     return c, num_clust, req_c

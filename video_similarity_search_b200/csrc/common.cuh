@@ -69,6 +69,20 @@ int num_sms();
 int exact_topk_cosine_rows(const void* q, const int* q_rows, int64_t nq, const void* x, int64_t n, int d, int dtype, int k,
                            int64_t self_offset, int* idx_out, void* dist_out, cudaStream_t st);
 
+// nn_screen_tc.cu: level-0 first-neighbour search whose database is still being uploaded (finch_driver.cu).
+// gates[c] (device int32, zero-initialised) becomes non-zero once rows [c * chunk_rows, (c + 1) * chunk_rows) of the
+// bf16 matrix are in place; `after` runs on the host right after the screen kernel has been launched.
+struct GateSpec {
+    const int* gates;
+    int num_chunks;
+    int64_t chunk_rows;   // multiple of 256
+};
+typedef int (*AfterScreenFn)(void* ctx);
+int nn_top1_f32_gated(const float* q_unit, const uint16_t* q_bf16, int64_t nq, const float* x_unit,
+                      const uint16_t* x_bf16, int64_t n, int d, int d_pad, int64_t self_offset, float eps, int* idx_out,
+                      float* dist_out, int* stats_out, const GateSpec* gate, AfterScreenFn after, void* after_ctx,
+                      cudaStream_t st);
+
 __host__ __device__ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- device helpers ---------------------------------------------------------------------

@@ -32,6 +32,7 @@
 #include <math_constants.h>
 
 #include <type_traits>
+#include <vector>
 
 #include "common.cuh"
 
@@ -95,7 +96,31 @@ struct ScreenParams {
     float* dump;           // debug: raw scores [nq][n] or nullptr
     int* error_flag;       // set when a barrier wait times out
     unsigned long long* trace;  // optional [8] cycle counters summed over CTAs (diagnostic, see slic_screen_trace)
+    // Optional explicit unit order (gated launches): entry u = {row unit, split | gate << 16}.  A unit whose gate is
+    // g may only start once gates[g] != 0 - the rows of database chunk g (and of every earlier chunk) have landed in
+    // HBM and been normalised by another stream while this kernel is already running (see GateSpec below).
+    const int2* unit_table;
+    const int* gates;
 };
+
+struct UnitInfo {
+    int split, gate;
+    int64_t row_unit;   // index of the unit's row block (single CTA) or row-block pair
+};
+__device__ __forceinline__ UnitInfo unit_info(const ScreenParams& p, int64_t u) {
+    UnitInfo ui;
+    if (p.unit_table) {
+        const int2 e = __ldg(p.unit_table + u);
+        ui.row_unit = e.x;
+        ui.split = e.y & 0xffff;
+        ui.gate = e.y >> 16;
+    } else {
+        ui.split = (int)(u % p.splits);
+        ui.row_unit = u / p.splits;
+        ui.gate = -1;
+    }
+    return ui;
+}
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -143,6 +168,28 @@ __device__ __forceinline__ void mbar_wait_traced(uint32_t bar, uint32_t parity, 
     const long long t0 = clock64();
     mbar_wait(bar, parity, error_flag);
     acc += (unsigned long long)(clock64() - t0);
+}
+// Block until another stream has published database chunk `g` (a 32-bit flag written after the chunk's normalise
+// kernel completed).  The acquire orders the flag read before this thread's later operations in the generic proxy;
+// the proxy fence extends that to the TMA (async proxy) reads of the chunk that follow.  Bounded like mbar_wait.
+__device__ __forceinline__ void gate_wait(const int* gate, int* error_flag) {
+    long long t0 = 0;
+    uint32_t polls = 0;
+    while (true) {
+        int v;
+        asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(gate) : "memory");
+        if (v != 0) break;
+        __nanosleep(256);
+        if ((++polls & 0xff) == 0) {
+            long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 20000000000ll) {   // ~10 s: the upload died
+                if (error_flag) atomicExch(error_flag, 1);
+                __trap();
+            }
+        }
+    }
+    asm volatile("fence.proxy.async.global;" ::: "memory");
 }
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1) {
     asm volatile(
@@ -548,10 +595,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
             uint32_t phase = 0, a_phase = 0;
             unsigned long long t_wait = 0;
             for (int64_t u = group; u < p.num_units; u += num_groups) {
-                const int split = (int)(u % p.splits);
-                const int64_t row_block = (u / p.splits) * NCTA + cta_rank;
+                const UnitInfo ui = unit_info(p, u);
+                const int split = ui.split;
+                const int64_t row_block = ui.row_unit * NCTA + cta_rank;
                 const int64_t ct0 = (int64_t)split * p.tiles_per_split;
                 const int64_t ct1 = min(ct0 + p.tiles_per_split, n_col_tiles);
+                if (ui.gate >= 0) gate_wait(p.gates + ui.gate, p.error_flag);
                 if constexpr (ARES) {
                     // the previous unit's MMAs have retired -> replace the resident A rows (all K slabs, one barrier)
                     mbar_wait_traced(bar_a_empty, a_phase ^ 1, p.error_flag, t_wait, tracing);
@@ -606,7 +655,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
             unsigned long long t_acc = 0, t_smem = 0;
             const long long t_begin = tracing ? clock64() : 0;
             for (int64_t u = group; u < p.num_units; u += num_groups) {
-                const int split = (int)(u % p.splits);
+                const int split = unit_info(p, u).split;
                 const int64_t ct0 = (int64_t)split * p.tiles_per_split;
                 const int64_t ct1 = min(ct0 + p.tiles_per_split, n_col_tiles);
                 if constexpr (ARES) {
@@ -680,8 +729,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
         cx.n_chunks = 0;
         if constexpr (TOPK) cx.hist = smem + Cfg::OPERAND_BYTES + 256 + half * TC_BM + row_in_tile;
         for (int64_t u = group; u < p.num_units; u += num_groups) {
-            const int split = (int)(u % p.splits);
-            const int64_t row_block = (u / p.splits) * NCTA + cta_rank;
+            const UnitInfo ui = unit_info(p, u);
+            const int split = ui.split;
+            const int64_t row_block = ui.row_unit * NCTA + cta_rank;
             const int64_t ct0 = (int64_t)split * p.tiles_per_split;
             const int64_t ct1 = min(ct0 + p.tiles_per_split, n_col_tiles);
             cx.row = row_block * TC_BM + row_in_tile;
@@ -1125,7 +1175,7 @@ static int topk_cap(int k, int64_t cols_per_split) {
 static int launch_screen(const uint16_t* q_bf16, int64_t nq, const uint16_t* x_bf16, int64_t n, int d_pad,
                          int64_t self_offset, float eps, int cap, const ScreenPlan& pl, int* cand_idx, float* cand_score,
                          int* cand_cnt, int* cand_flags, float* dump, int* error_flag, cudaStream_t st, int topk = 0,
-                         float* cand_kth = nullptr) {
+                         float* cand_kth = nullptr, const int2* unit_table = nullptr, const int* gates = nullptr) {
     const int ncta = screen_ncta();
     CUtensorMap tq, tx;
     SLIC_PROPAGATE(make_tmap(&tq, q_bf16, nq, d_pad, TC_BM));
@@ -1149,6 +1199,8 @@ static int launch_screen(const uint16_t* q_bf16, int64_t nq, const uint16_t* x_b
     p.dump = dump;
     p.error_flag = error_flag;
     p.trace = g_trace;
+    p.unit_table = unit_table;
+    p.gates = gates;
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const ScreenParams);
     const bool is_topk = topk > 0;
     const bool ares = ncta == 2 && p.num_k_slabs <= TC_ARES_MAX_SLABS && screen_ares_allowed();
@@ -1205,11 +1257,56 @@ static int launch_screen(const uint16_t* q_bf16, int64_t nq, const uint16_t* x_b
 
 constexpr int TC_CAP = 32;
 
+// Gated launch: the database arrives in `num_chunks` row chunks (host -> device copy + normalise on another stream).
+// Column split s = chunk s; the unit (row unit r, split s) needs chunk max(chunk of r's last row, s), and units are
+// ordered by that gate so that the persistent CTAs consume the triangle of chunk pairs as it fills:
+//   gate 0: rows of chunk 0 x columns of chunk 0;  gate g: (rows of chunks <= g) x chunk g  and  chunk g x (chunks < g).
+// Inside a gate the units of one column range are adjacent, so concurrent CTAs still share their B slabs through L2.
+static int plan_screen_gated(int64_t nq, int64_t n, int64_t self_offset, const GateSpec& g, ScreenPlan* pl,
+                             std::vector<int2>* table) {
+    const int ncta = screen_ncta();
+    const int64_t rows_per_unit = (int64_t)TC_BM * ncta;
+    SLIC_REQUIRE(g.gates && g.num_chunks >= 1 && g.num_chunks < 32768 && g.chunk_rows > 0 && g.chunk_rows % TC_BN == 0,
+                 "gated screen: chunk_rows must be a positive multiple of 256");
+    SLIC_REQUIRE(ceil_div(n, g.chunk_rows) == g.num_chunks, "gated screen: chunks do not tile the database");
+    SLIC_REQUIRE(self_offset >= 0 && self_offset + nq <= n, "gated screen: queries must be database rows");
+    const int64_t row_units = ceil_div(nq, rows_per_unit);
+    pl->tiles_per_split = (int)(g.chunk_rows / TC_BN);
+    pl->splits = g.num_chunks;
+    pl->units = row_units * pl->splits;
+    table->clear();
+    table->reserve((size_t)pl->units);
+    for (int gate = 0; gate < g.num_chunks; ++gate)
+        for (int s = 0; s <= gate; ++s)
+            for (int64_t r = 0; r < row_units; ++r) {
+                int64_t last = (r + 1) * rows_per_unit - 1;
+                if (last > nq - 1) last = nq - 1;
+                const int rc = (int)((last + self_offset) / g.chunk_rows);
+                const int need = rc > s ? rc : s;
+                if (need != gate) continue;
+                int2 e;
+                e.x = (int)r;
+                e.y = s | (gate << 16);
+                table->push_back(e);
+            }
+    SLIC_REQUIRE((int64_t)table->size() == pl->units, "gated screen: internal unit count mismatch");
+    return SLIC_OK;
+}
+
 template <typename T>
 static int nn_top1_impl(const T* q_unit, const uint16_t* q_bf16, int64_t nq, const T* x_unit, const uint16_t* x_bf16,
                         int64_t n, int d, int d_pad, int64_t self_offset, float eps, int* idx_out, T* dist_out,
-                        int* stats_out, cudaStream_t st) {
-    const ScreenPlan pl = plan_screen(nq, n);
+                        int* stats_out, cudaStream_t st, const GateSpec* gate = nullptr, AfterScreenFn after = nullptr,
+                        void* after_ctx = nullptr) {
+    ScreenPlan pl = plan_screen(nq, n);
+    std::vector<int2> table;
+    Scratch table_dev;
+    if (gate) {
+        SLIC_PROPAGATE(plan_screen_gated(nq, n, self_offset, *gate, &pl, &table));
+        SLIC_CUDA_OK(table_dev.alloc(table.size() * sizeof(int2), st));
+        // pageable source: the runtime stages the bytes before returning, the vector may go out of scope
+        SLIC_CUDA_OK(cudaMemcpyAsync(table_dev.ptr, table.data(), table.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+    }
     const int64_t slots = (int64_t)pl.splits * 2 * nq;   // one list per (split, 128-column half of the tiles, row)
     Scratch ci, cs, cc, cf, ovr, stats;
     SLIC_CUDA_OK(ci.alloc(slots * TC_CAP * sizeof(int), st));
@@ -1220,7 +1317,10 @@ static int nn_top1_impl(const T* q_unit, const uint16_t* q_bf16, int64_t nq, con
     SLIC_CUDA_OK(stats.alloc(8 * sizeof(int), st));
     SLIC_CUDA_OK(cudaMemsetAsync(stats.ptr, 0, 8 * sizeof(int), st));
     SLIC_PROPAGATE(launch_screen(q_bf16, nq, x_bf16, n, d_pad, self_offset, eps, TC_CAP, pl, ci.as<int>(), cs.as<float>(),
-                                 cc.as<int>(), cf.as<int>(), nullptr, stats.as<int>() + 4, st));
+                                 cc.as<int>(), cf.as<int>(), nullptr, stats.as<int>() + 4, st, 0, nullptr,
+                                 gate ? table_dev.as<int2>() : nullptr, gate ? gate->gates : nullptr));
+    // gated: the caller now enqueues the upload that feeds the running kernel and makes `st` wait for its end
+    if (after) SLIC_PROPAGATE(after(after_ctx));
     rerank_top1_kernel<T><<<(unsigned)ceil_div(nq, 8), 256, 0, st>>>(q_unit, x_unit, nq, d, eps, TC_CAP, 2 * pl.splits,
                                                                      ci.as<int>(), cs.as<float>(), cc.as<int>(),
                                                                      cf.as<int>(), idx_out, dist_out, ovr.as<int>(),
@@ -1293,6 +1393,15 @@ static int topk_tc_impl(const T* q_unit, const uint16_t* q_bf16, int64_t nq, con
     }
     if (stats_out) SLIC_CUDA_OK(cudaMemcpyAsync(stats_out, stats.ptr, 4 * sizeof(int), cudaMemcpyDeviceToDevice, st));
     return SLIC_OK;
+}
+
+int nn_top1_f32_gated(const float* q_unit, const uint16_t* q_bf16, int64_t nq, const float* x_unit,
+                      const uint16_t* x_bf16, int64_t n, int d, int d_pad, int64_t self_offset, float eps, int* idx_out,
+                      float* dist_out, int* stats_out, const GateSpec* gate, AfterScreenFn after, void* after_ctx,
+                      cudaStream_t st) {
+    if (eps <= 0.f) eps = TC_DEFAULT_EPS;
+    return nn_top1_impl<float>(q_unit, q_bf16, nq, x_unit, x_bf16, n, d, d_pad, self_offset, eps, idx_out, dist_out,
+                               stats_out, st, gate, after, after_ctx);
 }
 
 }  // namespace slic
