@@ -319,12 +319,13 @@ def run_b200(args):
     # small levels, so time the level-0 search alone, K launches, events recorded around the kernel on its stream)
     import ctypes
     screen_ms = []
-    flop = ctypes.c_double(0)
+    flop, exec_flop = ctypes.c_double(0), ctypes.c_double(0)
     for _ in range(args.steps):
         step_nn_only()
         # the level-0 call is the only screen launch in step_nn_only
         ms = ctypes.c_float(0)
         _lib.check(lib.slic_last_screen_time(ctypes.byref(ms), ctypes.byref(flop)), "slic_last_screen_time")
+        _lib.check(lib.slic_last_screen_exec_flop(ctypes.byref(exec_flop)), "slic_last_screen_exec_flop")
         screen_ms.append(ms.value)
     lib.slic_profile_screen(0)
     screen_ms_avg = max_over_ranks(statistics.mean(screen_ms))
@@ -340,6 +341,7 @@ def run_b200(args):
 
     peaks = load_peaks()
     achieved_tf = flop.value / (screen_ms_avg * 1e-3) / 1e12
+    executed_tf = exec_flop.value / (screen_ms_avg * 1e-3) / 1e12
     d_pad = (d + 63) // 64 * 64
     line = {
         "metric": METRIC, "value": n / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -360,6 +362,12 @@ def run_b200(args):
                      "frac": achieved_tf / peaks["bf16_tflops"], "peak_source": peaks["source"] + " burst bf16",
                      "frac_of_sustained": (achieved_tf / peaks["bf16_tflops_sustained"]) if peaks.get("bf16_tflops_sustained") else None,
                      "kernel_ms": screen_ms_avg, "flop_per_launch": flop.value,
+                     # the self-search computes only the tiles on or right of the diagonal of the symmetric score matrix
+                     # (each filtered along rows AND columns): `achieved` counts the ALGORITHMIC 2 n^2 d flop of SURVEY.md
+                     # section 8(d) (full square, no symmetry discount) and may therefore exceed the peak; `executed` is
+                     # what the tensor cores actually did, and `frac_executed` its fraction of the measured peak
+                     "executed_flop_per_launch": exec_flop.value, "executed": executed_tf,
+                     "frac_executed": executed_tf / peaks["bf16_tflops"],
                      "traffic": NCU_TRAFFIC_BYTES.get((args.workload, world)), "traffic_unit": "bytes/launch (ncu dram read+write)"},
     }
     if world == 1 and not args.no_cpu_baseline:

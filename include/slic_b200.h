@@ -61,6 +61,10 @@ int64_t slic_launch_count(void);
  * one and returns its duration and its algorithmic work (2 * nq * n * d_pad flop). */
 int slic_profile_screen(int32_t enable);
 int slic_last_screen_time(float* ms_out, double* flop_out);
+/* Flop the tensor cores EXECUTED in that launch: equal to the algorithmic figure for rectangular searches; about
+ * half of it for self-searches, which compute only the tiles on or right of the diagonal of the symmetric score
+ * matrix (plus a small pre-pass) and filter each of them along rows and along columns. */
+int slic_last_screen_exec_flop(double* flop_out);
 
 /* Pipeline trace of the screen kernel (diagnostic): while enabled every launch adds, summed over its CTAs,
  * [0] cycles the TMA producer waited for a free smem stage, [1] cycles the MMA issuer waited for a free

@@ -320,3 +320,53 @@ def test_host_buffer_entry_point(be):
     _lib.call("slic_first_neighbors_host", x.ctypes.data_as(ctypes.c_void_p), 3000, 128, 0,
               nn.ctypes.data_as(ctypes.c_void_p), d.ctypes.data_as(ctypes.c_void_p))
     _check_nn(nn, d, x, TIE_MARGIN_F32)
+
+
+# ---- symmetric self-search (upper-triangular tiles, row + column filters) -----------------------------------
+@pytest.mark.parametrize("dtype,n,d,k,seed", [
+    (np.float32, 16384, 64, 40, 1),       # exactly at the switch-over, T = 64 tiles = one column chunk
+    (np.float32, 20011, 96, 0, 2),        # iid rows (no cluster structure: weak pre-pass thresholds), ragged tail
+    (np.float32, 50000, 512, 300, 3),     # several column chunks, the A-resident kernel
+    (np.float64, 33000, 128, 100, 4),     # float64 re-rank (FINCH levels >= 1)
+    (np.float32, 24000, 640, 50, 5),      # d_pad > 512: the streaming (non-resident) pair kernel
+])
+def test_symmetric_screen_equals_exact(be, dtype, n, d, k, seed):
+    """Self-searches of >= 16 384 rows run the symmetric screen: only tiles on or right of the diagonal are computed
+    and each is filtered along rows and along columns.  The result must be that of the exact kernel on every row."""
+    if k:
+        x = synth.gaussian_mixture(n, d, k, seed).astype(dtype)
+    else:
+        x = np.random.default_rng(seed).standard_normal((n, d)).astype(dtype)
+    xd = be.to_device(x)
+    unit, ub = be.normalize_rows(xd)
+    idx_tc, dist_tc = be.nn_top1(unit, ub, unit, ub, self_offset=0)
+    stats = be.last_stats.cpu().numpy()
+    idx_ex, dist_ex = be.nn_exact_top1(unit, unit, self_offset=0)
+    assert torch.equal(idx_tc, idx_ex)
+    # the two kernels add the float64 products in different orders: equal to rounding of the reference dtype
+    np.testing.assert_allclose(dist_tc.cpu().numpy(), dist_ex.cpu().numpy(), rtol=0, atol=1.2e-7 if dtype == np.float32 else 1e-14)
+    assert stats[1] < n // 100          # rows handed to the exact finisher stay rare
+    lib = be.lib
+    import ctypes
+    lib.slic_profile_screen(1)
+    be.nn_top1(unit, ub, unit, ub, self_offset=0)
+    ms, fl, ex = ctypes.c_float(0), ctypes.c_double(0), ctypes.c_double(0)
+    assert lib.slic_last_screen_time(ctypes.byref(ms), ctypes.byref(fl)) == 0
+    assert lib.slic_last_screen_exec_flop(ctypes.byref(ex)) == 0
+    lib.slic_profile_screen(0)
+    assert ex.value < (0.6 if n >= 50000 else 0.8) * fl.value   # about half of the square was computed (plus the pre-pass)
+
+
+def test_symmetric_screen_dense_cluster_rows_overflow_to_exact(be):
+    """Many rows within eps of each other: lists overflow, the exact kernel must take over - same result."""
+    rng = np.random.default_rng(9)
+    base = rng.standard_normal((1, 64)).astype(np.float32)
+    x = np.concatenate([base + 1e-3 * rng.standard_normal((600, 64)).astype(np.float32),
+                        rng.standard_normal((17000, 64)).astype(np.float32)])
+    xd = be.to_device(x)
+    unit, ub = be.normalize_rows(xd)
+    idx_tc, dist_tc = be.nn_top1(unit, ub, unit, ub, self_offset=0)
+    idx_ex, dist_ex = be.nn_exact_top1(unit, unit, self_offset=0)
+    assert torch.equal(idx_tc, idx_ex)
+    np.testing.assert_allclose(dist_tc.cpu().numpy(), dist_ex.cpu().numpy(), rtol=0, atol=1.2e-7)
+    assert int(be.last_stats[1]) >= 600

@@ -78,6 +78,8 @@ struct GateSpec {
     int64_t chunk_rows;   // multiple of 256
 };
 typedef int (*AfterScreenFn)(void* ctx);
+// true: a self-search of n rows runs the symmetric screen (upper-triangular tiles, row + column filters)
+bool screen_self_search_is_symmetric(int64_t n);
 int nn_top1_f32_gated(const float* q_unit, const uint16_t* q_bf16, int64_t nq, const float* x_unit,
                       const uint16_t* x_bf16, int64_t n, int d, int d_pad, int64_t self_offset, float eps, int* idx_out,
                       float* dist_out, int* stats_out, const GateSpec* gate, AfterScreenFn after, void* after_ctx,

@@ -31,6 +31,7 @@
 #include <stdlib.h>
 #include <math_constants.h>
 
+#include <algorithm>
 #include <type_traits>
 #include <vector>
 
@@ -61,6 +62,10 @@ template <int NCTA, bool ARES, bool TOPK> struct TcCfg {
     static constexpr uint32_t OPERAND_BYTES = A_RES_BYTES + STAGES * STAGE_BYTES;            // 192 KB, ARES: 192 / 224 KB
     static constexpr uint32_t SMEM_BYTES = OPERAND_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/ +
                                            (TOPK ? 32768u : 0u) /*histograms*/;
+    // symmetric variant: + 2 KB of column thresholds; the A-resident layout then leaves 768 bytes of alignment slack
+    static constexpr uint32_t SYM_THR_BYTES = 2 * 2 * 128 * 4;   // [2 parities][2 halves][128 columns]
+    static constexpr uint32_t SYM_SMEM_BYTES = OPERAND_BYTES + 256 + SYM_THR_BYTES + (ARES ? 768u : 1024u);
+    static_assert(TOPK || SYM_SMEM_BYTES <= 232448, "symmetric variant exceeds the shared memory of a CTA");
     static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
     static_assert(!ARES || NCTA == 2, "the A-resident variant exists for CTA pairs only");
 };
@@ -96,31 +101,67 @@ struct ScreenParams {
     float* dump;           // debug: raw scores [nq][n] or nullptr
     int* error_flag;       // set when a barrier wait times out
     unsigned long long* trace;  // optional [8] cycle counters summed over CTAs (diagnostic, see slic_screen_trace)
-    // Optional explicit unit order (gated launches): entry u = {row unit, split | gate << 16}.  A unit whose gate is
-    // g may only start once gates[g] != 0 - the rows of database chunk g (and of every earlier chunk) have landed in
-    // HBM and been normalised by another stream while this kernel is already running (see GateSpec below).
-    const int2* unit_table;
+    // Optional explicit unit list (gated and symmetric launches): entry u = {row unit, first column tile,
+    // tile count | tile stride << 16, (gate + 1) | stream << 12 | column-direction flag << 28}.
+    // A unit with gate g may only start once gates[g] != 0 - the rows of database chunk g (and of every earlier
+    // chunk) have landed in HBM and been normalised by another stream while this kernel is already running.
+    const int4* unit_table;
     const int* gates;
+    // Symmetric self-search (SYM kernels): best_enc[r] = order-preserving encoding of the best screened score any CTA
+    // has seen so far for row r.  Candidates go to a log: cand_idx = neighbour, cand_score = score, log_q = query row,
+    // one region of log_region records per epilogue warp; cand_cnt[region] = records written, cand_flags[0] = overflow.
+    unsigned int* best_enc;
+    int* log_q;
+    int log_region;
+    // pre-pass -> triangle hand-over: every epilogue warp adds 1 to sync_counter when it finishes a pre-pass unit; a
+    // triangle unit with gate g starts once the counter has reached sync_targets[g + 1] (all pre-pass units of the
+    // chunks it touches), so that the column thresholds it reads are in place.  Affects speed only, never results.
+    int* sync_counter;
+    const int* sync_targets;
 };
 
 struct UnitInfo {
-    int split, gate;
     int64_t row_unit;   // index of the unit's row block (single CTA) or row-block pair
+    int64_t ct0;        // first column tile
+    int count, stride;  // tiles ct0 + k * stride, k < count
+    int gate;           // -1: none
+    int stream;         // candidate stream (column split) of the non-symmetric kernels
+    bool coldir;        // SYM: tiles right of the diagonal also serve their columns as queries
 };
-__device__ __forceinline__ UnitInfo unit_info(const ScreenParams& p, int64_t u) {
+__device__ __forceinline__ UnitInfo unit_info(const ScreenParams& p, int64_t u, int64_t n_col_tiles) {
     UnitInfo ui;
     if (p.unit_table) {
-        const int2 e = __ldg(p.unit_table + u);
+        const int4 e = __ldg(p.unit_table + u);
         ui.row_unit = e.x;
-        ui.split = e.y & 0xffff;
-        ui.gate = e.y >> 16;
+        ui.ct0 = e.y;
+        ui.count = e.z & 0xffff;
+        ui.stride = (int)((unsigned)e.z >> 16);
+        ui.gate = (e.w & 0xfff) - 1;
+        ui.stream = (e.w >> 12) & 0xffff;
+        ui.coldir = ((e.w >> 28) & 1) != 0;
     } else {
-        ui.split = (int)(u % p.splits);
+        const int split = (int)(u % p.splits);
         ui.row_unit = u / p.splits;
+        ui.ct0 = (int64_t)split * p.tiles_per_split;
+        const int64_t left = n_col_tiles - ui.ct0;
+        ui.count = (int)(left < p.tiles_per_split ? (left > 0 ? left : 0) : p.tiles_per_split);
+        ui.stride = 1;
         ui.gate = -1;
+        ui.stream = split;
+        ui.coldir = false;
     }
     return ui;
 }
+
+// order-preserving map float -> uint32 (atomicMax / warp-reduce on scores of either sign); enc(-inf) = 0x007fffff
+__device__ __forceinline__ unsigned enc_score(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float dec_score(unsigned e) {
+    return __uint_as_float((e & 0x80000000u) ? (e & 0x7fffffffu) : ~e);
+}
+constexpr unsigned ENC_NEG_INF = 0x007fffffu;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -190,6 +231,24 @@ __device__ __forceinline__ void gate_wait(const int* gate, int* error_flag) {
         }
     }
     asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+__device__ __forceinline__ void counter_wait(const int* counter, int target, int* error_flag) {
+    long long t0 = 0;
+    uint32_t polls = 0;
+    while (true) {
+        int v;
+        asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        if (v >= target) break;
+        __nanosleep(128);
+        if ((++polls & 0xff) == 0) {
+            long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 20000000000ll) {
+                if (error_flag) atomicExch(error_flag, 1);
+                __trap();
+            }
+        }
+    }
 }
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1) {
     asm volatile(
@@ -330,6 +389,36 @@ __device__ __noinline__ RowState push_candidate(RowState st, float s, int col, f
     return st;
 }
 
+// ---- symmetric self-search: candidate log ---------------------------------------------------------------
+// A row is met by many CTAs (as a row of its own units, as a column of every row unit left of it), so its candidates
+// cannot live in one thread's private list.  Every epilogue warp instead appends (query, neighbour, score) records to
+// its own region of a global log with plain stores - the slot comes from a shared-memory counter, nothing waits for
+// HBM - and publishes improved row bests with a fire-and-forget atomic max.  The re-rank kernels then keep the records
+// within eps of the row's final best.  A full region raises a flag and the caller repeats the search on the full square.
+struct LogCtx {
+    int* q;            // this warp's region of the log
+    int* nb;
+    float* s;
+    unsigned int* cnt; // shared-memory record counter of this warp
+    int region;        // records per region
+    int* overflow;
+};
+// (arguments by value: a reference would force the caller's whole epilogue context into local memory)
+__device__ __noinline__ void log_append_raw(int* lq, int* lnb, float* ls, unsigned int* cnt, int region, int* overflow,
+                                            unsigned int* best_enc, int q, int nb, float s) {
+    const unsigned pos = atomicAdd(cnt, 1u);
+    if (pos < (unsigned)region) {
+        lq[pos] = q;
+        lnb[pos] = nb;
+        ls[pos] = s;
+    } else {
+        *overflow = 1;
+    }
+    if (best_enc) atomicMax(best_enc + q, enc_score(s));   // result unused: compiles to RED, no round trip
+}
+__device__ __forceinline__ void log_append(const LogCtx& lg, unsigned int* best_enc, int q, int nb, float s) {
+    log_append_raw(lg.q, lg.nb, lg.s, lg.cnt, lg.region, lg.overflow, best_enc, q, nb, s);
+}
 // Top-k variant of the row state.  Instead of the k running best scores themselves the row keeps a 128-bin
 // histogram of the scores it has seen or listed (shared memory, uint8, h[bin * TC_HIST_STRIDE]; bin b >= 1 covers
 // [b / 128, (b + 1) / 128), bin 0 everything below 2^-7).  tb is the highest bin with at least k listed scores at or
@@ -448,21 +537,25 @@ struct EpiCtx {
     int64_t row, self_col;
     bool row_ok, count, tracing;
     unsigned long long n_trig, n_chunks;
+    LogCtx lg;           // SYM only
 };
 
-template <bool TOPK>
-__device__ __forceinline__ void epi_chunk(EpiCtx<TOPK>& cx, uint32_t (&v)[32], int64_t col_base) {
+template <bool TOPK, bool SYM>
+__device__ __forceinline__ void epi_chunk(EpiCtx<TOPK>& cx, uint32_t (&v)[32], int64_t col_base, bool plain,
+                                          bool cdir = false, uint32_t thr_s = 0u /* shared-memory address */) {
     const ScreenParams& p = *cx.p;
-    if (col_base >= p.n) return;  // whole chunk is padding (warp-uniform)
-    if (col_base + 32 > p.n || (cx.self_col >= col_base && cx.self_col < col_base + 32)) {
+    if (!plain) {   // warp-uniform: the tile touches the end of the database, holds the rows' own columns, or is dumped
+        if (col_base >= p.n) return;  // whole chunk is padding
+        if (col_base + 32 > p.n || (cx.self_col >= col_base && cx.self_col < col_base + 32)) {
 #pragma unroll
-        for (int t = 0; t < 32; ++t)
-            if (col_base + t >= p.n || col_base + t == cx.self_col) v[t] = __float_as_uint(-CUDART_INF_F);
-    }
-    if (p.dump && cx.row_ok) {
+            for (int t = 0; t < 32; ++t)
+                if (col_base + t >= p.n || col_base + t == cx.self_col) v[t] = __float_as_uint(-CUDART_INF_F);
+        }
+        if (p.dump && cx.row_ok) {
 #pragma unroll
-        for (int t = 0; t < 32; ++t)
-            if (col_base + t < p.n) p.dump[cx.row * p.n + col_base + t] = __uint_as_float(v[t]);
+            for (int t = 0; t < 32; ++t)
+                if (col_base + t < p.n) p.dump[cx.row * p.n + col_base + t] = __uint_as_float(v[t]);
+        }
     }
     if constexpr (TOPK) {
         float g[4];
@@ -512,30 +605,90 @@ __device__ __forceinline__ void epi_chunk(EpiCtx<TOPK>& cx, uint32_t (&v)[32], i
         if (__any_sync(0xffffffffu, cx.pd.n >= 3))
             pend_flush(cx.pd, cx.st, p.eps, p.cap, p.topk, cx.count, cx.hist, cx.li, cx.ls);
     } else {
-        float m = __uint_as_float(v[0]);
+        // group maxima (8 columns each) first: the rare paths below only look inside groups that qualify
+        float g[4];
 #pragma unroll
-        for (int t = 1; t < 32; ++t) m = fmaxf(m, __uint_as_float(v[t]));
+        for (int q = 0; q < 4; ++q) {
+            g[q] = __uint_as_float(v[8 * q]);
+#pragma unroll
+            for (int t = 1; t < 8; ++t) g[q] = fmaxf(g[q], __uint_as_float(v[8 * q + t]));
+        }
+        const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
         if (cx.row_ok && m >= cx.st.thr) {
 #pragma unroll
-            for (int t = 0; t < 32; ++t) {
-                const float s = __uint_as_float(v[t]);
-                if (s >= cx.st.thr && s > -CUDART_INF_F)
-                    cx.st = push_candidate(cx.st, s, (int)(col_base + t), p.eps, p.cap, cx.li, cx.ls);
+            for (int q = 0; q < 4; ++q) {
+                if (g[q] < cx.st.thr) continue;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const float s = __uint_as_float(v[8 * q + t]);
+                    if (s >= cx.st.thr && s > -CUDART_INF_F) {
+                        if constexpr (SYM) {
+                            if (s > cx.st.best) {
+                                cx.st.best = s;
+                                cx.st.thr = s - p.eps;
+                            }
+                            log_append(cx.lg, nullptr, (int)cx.row, (int)(col_base + 8 * q + t), s);   // best published at unit end
+                        } else {
+                            cx.st = push_candidate(cx.st, s, (int)(col_base + 8 * q + t), p.eps, p.cap, cx.li, cx.ls);
+                        }
+                    }
+                }
+            }
+        }
+        if constexpr (SYM) {
+            if (cdir) {
+                // column role.  thr[t] (shared memory, written once per tile) = threshold of column col_base + t.  Every
+                // thread takes the maximum of (score - column threshold) over its row's 32 columns - the exact test, so that
+                // the per-column spread of the thresholds cancels (block-level tests against the lowest threshold of a
+                // group of columns were measured: they fire for 40-56 % of the blocks) - and only a row with a
+                // non-negative margin looks closer.
+                float mc = -CUDART_INF_F;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 t4;   // (explicit ld.shared: a generic load would go the slow way round)
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(t4.x), "=f"(t4.y), "=f"(t4.z), "=f"(t4.w)
+                                 : "r"(thr_s + 16u * j));
+                    mc = fmaxf(mc, fmaxf(__uint_as_float(v[4 * j]) - t4.x, __uint_as_float(v[4 * j + 1]) - t4.y));
+                    mc = fmaxf(mc, fmaxf(__uint_as_float(v[4 * j + 2]) - t4.z, __uint_as_float(v[4 * j + 3]) - t4.w));
+                }
+                const bool hit = cx.row_ok && mc >= 0.f;
+                if (cx.tracing) {
+                    ++cx.n_chunks;
+                    cx.n_trig += __any_sync(0xffffffffu, hit) ? 1 : 0;
+                }
+                if (hit) {
+#pragma unroll
+                    for (int t = 0; t < 32; ++t) {
+                        const float s = __uint_as_float(v[t]);
+                        float th;
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(th) : "r"(thr_s + 4u * t));
+                        if (s >= th) log_append(cx.lg, p.best_enc, (int)(col_base + t), (int)cx.row, s);
+                    }
+                }
             }
         }
     }
 }
 
 // ---- the kernel ------------------------------------------------------------------------------
-template <bool TOPK, int NCTA, bool ARES>
+template <bool TOPK, int NCTA, bool ARES, bool SYM = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_constant__ CUtensorMap tmap_q,
                                                                   const __grid_constant__ CUtensorMap tmap_x,
                                                                   const ScreenParams p) {
     typedef TcCfg<NCTA, ARES, TOPK> Cfg;
     constexpr int STAGES = Cfg::STAGES;
+    static_assert(!SYM || (NCTA == 2 && !TOPK), "the symmetric variant exists for the top-1 CTA-pair kernels only");
     extern __shared__ uint8_t smem_raw[];
     // (the dynamic smem window starts at the same offset in both CTAs of a pair, so the aligned offsets agree)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    if constexpr (SYM) {
+        // the layout below needs OPERAND + 256 + 2048 bytes behind the aligned base (uniform across the grid)
+        if ((uint32_t)(smem - smem_raw) + Cfg::OPERAND_BYTES + 256 + Cfg::SYM_THR_BYTES > Cfg::SYM_SMEM_BYTES) {
+            if (threadIdx.x == 0 && p.error_flag) atomicExch(p.error_flag, 2);
+            return;
+        }
+    }
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OPERAND_BYTES);
     const uint32_t bar_full = smem_u32(bars);                              // [STAGES]  (pair: the leader's are used)
     const uint32_t bar_empty = smem_u32(bars + TC_MAX_STAGES);             // [STAGES]
@@ -595,12 +748,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
             uint32_t phase = 0, a_phase = 0;
             unsigned long long t_wait = 0;
             for (int64_t u = group; u < p.num_units; u += num_groups) {
-                const UnitInfo ui = unit_info(p, u);
-                const int split = ui.split;
+                const UnitInfo ui = unit_info(p, u, n_col_tiles);
                 const int64_t row_block = ui.row_unit * NCTA + cta_rank;
-                const int64_t ct0 = (int64_t)split * p.tiles_per_split;
-                const int64_t ct1 = min(ct0 + p.tiles_per_split, n_col_tiles);
                 if (ui.gate >= 0) gate_wait(p.gates + ui.gate, p.error_flag);
+                if constexpr (SYM) {
+                    if (ui.coldir && p.sync_counter)
+                        counter_wait(p.sync_counter, __ldg(p.sync_targets + ui.gate + 1), p.error_flag);
+                }
                 if constexpr (ARES) {
                     // the previous unit's MMAs have retired -> replace the resident A rows (all K slabs, one barrier)
                     mbar_wait_traced(bar_a_empty, a_phase ^ 1, p.error_flag, t_wait, tracing);
@@ -610,7 +764,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
                                          (int)(row_block * TC_BM));
                     a_phase ^= 1;
                 }
-                for (int64_t ct = ct0; ct < ct1; ++ct) {
+                for (int kt = 0; kt < ui.count; ++kt) {
+                    const int64_t ct = ui.ct0 + (int64_t)kt * ui.stride;
                     for (int ks = 0; ks < p.num_k_slabs; ks += Cfg::SPS) {
                         mbar_wait_traced(bar_empty + 8 * stage, phase ^ 1, p.error_flag, t_wait, tracing);
                         const uint32_t a_dst = ring_base + stage * Cfg::STAGE_BYTES;
@@ -655,15 +810,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
             unsigned long long t_acc = 0, t_smem = 0;
             const long long t_begin = tracing ? clock64() : 0;
             for (int64_t u = group; u < p.num_units; u += num_groups) {
-                const int split = unit_info(p, u).split;
-                const int64_t ct0 = (int64_t)split * p.tiles_per_split;
-                const int64_t ct1 = min(ct0 + p.tiles_per_split, n_col_tiles);
+                const int n_tiles = unit_info(p, u, n_col_tiles).count;
                 if constexpr (ARES) {
                     mbar_wait_traced(bar_a_full, a_phase, p.error_flag, t_smem, tracing);
                     tc_fence_after();
                     a_phase ^= 1;
                 }
-                for (int64_t ct = ct0; ct < ct1; ++ct) {
+                for (int kt = 0; kt < n_tiles; ++kt) {
                     mbar_wait_traced(bar_acc_empty + 8 * acc, acc_phase ^ 1, p.error_flag, t_acc, tracing);
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TC_BN);
@@ -728,16 +881,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
         cx.n_trig = 0;
         cx.n_chunks = 0;
         if constexpr (TOPK) cx.hist = smem + Cfg::OPERAND_BYTES + 256 + half * TC_BM + row_in_tile;
+        unsigned int* s_logcnt = reinterpret_cast<unsigned int*>(bars + 20) + (warp - 2);   // spare bytes of the barrier block
+        float* thr_buf = reinterpret_cast<float*>(smem + Cfg::OPERAND_BYTES + 256);         // SYM: [2 parities][2 halves][128]
+        unsigned tile_seq = 0;
+        unsigned nbc0 = 0u, nbc1 = 0u, nbc2 = 0u, nbc3 = 0u;   // SYM, first warp of a half: next tile's published column bests
+        const int64_t log_region_id = (int64_t)blockIdx.x * TC_EPI_WARPS + (warp - 2);
+        if constexpr (SYM) {
+            if (lane == 0) *s_logcnt = 0u;
+            __syncwarp();
+            cx.lg.q = p.log_q + log_region_id * p.log_region;
+            cx.lg.nb = p.cand_idx + log_region_id * p.log_region;
+            cx.lg.s = p.cand_score + log_region_id * p.log_region;
+            cx.lg.cnt = s_logcnt;
+            cx.lg.region = p.log_region;
+            cx.lg.overflow = p.cand_flags;
+        }
         for (int64_t u = group; u < p.num_units; u += num_groups) {
-            const UnitInfo ui = unit_info(p, u);
-            const int split = ui.split;
+            const UnitInfo ui = unit_info(p, u, n_col_tiles);
             const int64_t row_block = ui.row_unit * NCTA + cta_rank;
-            const int64_t ct0 = (int64_t)split * p.tiles_per_split;
-            const int64_t ct1 = min(ct0 + p.tiles_per_split, n_col_tiles);
             cx.row = row_block * TC_BM + row_in_tile;
             cx.row_ok = cx.row < p.nq;
             cx.self_col = (p.self_offset >= 0 && cx.row_ok) ? cx.row + p.self_offset : -1;
-            const int64_t slot = (int64_t)(split * 2 + half) * p.nq + (cx.row_ok ? cx.row : 0);
+            const int64_t slot = SYM ? 0 : (int64_t)(ui.stream * 2 + half) * p.nq + (cx.row_ok ? cx.row : 0);
             cx.li = p.cand_idx + slot * p.cap;
             cx.ls = p.cand_score + slot * p.cap;
             if constexpr (TOPK) {
@@ -747,21 +912,73 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
                 cx.st.ctb = 0;
                 cx.st.thr = bin_edge(0) - p.eps;
                 cx.pd.n = 0;
+            } else if constexpr (SYM) {
+                // a triangle unit reads published thresholds: not before every pre-pass unit it depends on has finished
+                // (the producer waits for the same counter, but this warp runs ahead of the first accumulator)
+                if (ui.coldir && p.sync_counter) {
+                    if (lane == 0) counter_wait(p.sync_counter, __ldg(p.sync_targets + ui.gate + 1), p.error_flag);
+                    __syncwarp();
+                }
+                // start from the best score any CTA has published for this row (pre-pass, earlier units, column roles)
+                cx.st.best = cx.row_ok ? dec_score(__ldcg(p.best_enc + cx.row)) : -CUDART_INF_F;
+                cx.st.thr = cx.st.best - p.eps;
             } else {
                 cx.st.best = -CUDART_INF_F;
                 cx.st.thr = -CUDART_INF_F;
             }
             cx.st.cnt = 0;
             cx.st.flags = 0;
-            for (int64_t ct = ct0; ct < ct1; ++ct) {
+            for (int kt = 0; kt < ui.count; ++kt) {
+                const int64_t ct = ui.ct0 + (int64_t)kt * ui.stride;
+                const int64_t col0 = ct * TC_BN + half * 128;
+                // SYM: tiles strictly right of the diagonal also serve their columns as queries; fetch the columns'
+                // published bests now, the accumulator wait below hides the latency
+                bool cdir = false;
+                uint32_t thr_tile = 0u;   // shared-memory address of this tile's 128 column thresholds
+                if constexpr (SYM) {
+                    // column thresholds of this tile's 128-column half: written to shared memory by the half's first warp
+                    // (double-buffered by tile parity), then one named barrier of the half's four warps.  The writer fetched
+                    // the published bests one tile ahead (nbc*), so that no L2 round trip sits in front of the barrier.
+                    cdir = ui.coldir && ct != ui.row_unit;
+                    float* tb = thr_buf + (((tile_seq & 1) * 2 + half) * 128);
+                    if (quad == 0) {
+                        constexpr unsigned ENC_POS_INF = 0xff800000u;
+                        if (kt == 0 && cdir) {   // first tile of the unit: nothing was prefetched
+                            const int64_t c = col0 + lane;
+                            nbc0 = c < p.n ? __ldcg(p.best_enc + c) : ENC_POS_INF;
+                            nbc1 = c + 32 < p.n ? __ldcg(p.best_enc + c + 32) : ENC_POS_INF;
+                            nbc2 = c + 64 < p.n ? __ldcg(p.best_enc + c + 64) : ENC_POS_INF;
+                            nbc3 = c + 96 < p.n ? __ldcg(p.best_enc + c + 96) : ENC_POS_INF;
+                        }
+                        if (cdir) {
+                            // finite lower bound: a masked (-inf) score minus the threshold stays -inf, never NaN
+                            float t0 = fmaxf(dec_score(nbc0) - p.eps, -3.0e38f), t1 = fmaxf(dec_score(nbc1) - p.eps, -3.0e38f);
+                            float t2 = fmaxf(dec_score(nbc2) - p.eps, -3.0e38f), t3 = fmaxf(dec_score(nbc3) - p.eps, -3.0e38f);
+                            const uint32_t ta = smem_u32(tb) + 4u * lane;
+                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(ta), "f"(t0) : "memory");
+                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(ta + 128u), "f"(t1) : "memory");
+                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(ta + 256u), "f"(t2) : "memory");
+                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(ta + 384u), "f"(t3) : "memory");
+                        }
+                        if (ui.coldir && kt + 1 < ui.count) {   // next tile of this unit (never the diagonal: ct grows)
+                            const int64_t c = col0 + (int64_t)ui.stride * TC_BN + lane;
+                            nbc0 = c < p.n ? __ldcg(p.best_enc + c) : ENC_POS_INF;
+                            nbc1 = c + 32 < p.n ? __ldcg(p.best_enc + c + 32) : ENC_POS_INF;
+                            nbc2 = c + 64 < p.n ? __ldcg(p.best_enc + c + 64) : ENC_POS_INF;
+                            nbc3 = c + 96 < p.n ? __ldcg(p.best_enc + c + 96) : ENC_POS_INF;
+                        }
+                    }
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+                    thr_tile = smem_u32(tb);
+                    ++tile_seq;
+                }
                 mbar_wait_traced(bar_acc_full + 8 * acc, acc_phase, p.error_flag, t_full, tracing);
                 tc_fence_after();
                 const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_BN + half * 128);
-                const int64_t col0 = ct * TC_BN + half * 128;
                 uint32_t va[32], vb[32];
                 if constexpr (TOPK) {
-                    cx.count = ct != ct0;
-                    if (ct == ct0) {
+                    cx.count = kt != 0;
+                    if (kt == 0) {
                         // bootstrap: count every column of the stream's first 128 (uniform control flow, nothing is
                         // listed), which yields the first threshold; the columns are then read again below
 #pragma unroll 1
@@ -779,39 +996,82 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
                         }
                     }
                 }
-                // software pipeline over the 4 chunks of this half: chunk c + 1 is in flight while chunk c is filtered
-                tmem_ld_issue(tbase, vb);
+                // warp-uniform: no column of this 128-column half needs masking (inside the database, not the rows' own
+                // columns, no debug dump) - the filter then skips all per-column checks
+                const bool plain = col0 + 128 <= p.n && !p.dump &&
+                                   (p.self_offset < 0 || row_block * TC_BM + p.self_offset + TC_BM <= col0 ||
+                                    row_block * TC_BM + p.self_offset >= col0 + 128);
+                if constexpr (TOPK) {
+                    // software pipeline over the 4 chunks of this half: chunk c + 1 is in flight while chunk c is filtered
+                    tmem_ld_issue(tbase, vb);
 #pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    tmem_ld_wait(vb);
+                    for (int c = 0; c < 4; ++c) {
+                        tmem_ld_wait(vb);
 #pragma unroll
-                    for (int t = 0; t < 32; ++t) va[t] = vb[t];
-                    if (c < 3) {
-                        tmem_ld_issue(tbase + (uint32_t)(32 * (c + 1)), vb);
-                    } else {
-                        // every TMEM read of this accumulator is complete: hand it back before the last filter
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) {
-                            if constexpr (NCTA == 2) mbar_arrive_leader(bar_acc_empty + 8 * acc);
-                            else mbar_arrive(bar_acc_empty + 8 * acc);
+                        for (int t = 0; t < 32; ++t) va[t] = vb[t];
+                        if (c < 3) {
+                            tmem_ld_issue(tbase + (uint32_t)(32 * (c + 1)), vb);
+                        } else {
+                            // every TMEM read of this accumulator is complete: hand it back before the last filter
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) {
+                                if constexpr (NCTA == 2) mbar_arrive_leader(bar_acc_empty + 8 * acc);
+                                else mbar_arrive(bar_acc_empty + 8 * acc);
+                            }
+                            acc ^= 1;
+                            if (acc == 0) acc_phase ^= 1;
                         }
-                        acc ^= 1;
-                        if (acc == 0) acc_phase ^= 1;
+                        epi_chunk<TOPK, false>(cx, va, col0 + 32 * c, plain);
                     }
-                    epi_chunk<TOPK>(cx, va, col0 + 32 * c);
+                } else {
+                    // the same pipeline with the two register buffers swapping roles (no copies): two chunks per trip
+                    tmem_ld_issue(tbase, va);
+#pragma unroll 1
+                    for (int h = 0; h < 2; ++h) {
+                        tmem_ld_wait(va);
+                        tmem_ld_issue(tbase + (uint32_t)(64 * h + 32), vb);
+                        epi_chunk<false, SYM>(cx, va, col0 + 64 * h, plain, cdir, thr_tile + 256u * h);
+                        tmem_ld_wait(vb);
+                        if (h == 0) {
+                            tmem_ld_issue(tbase + 64u, va);
+                        } else {
+                            // every TMEM read of this accumulator is complete: hand it back before the last filter
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) {
+                                if constexpr (NCTA == 2) mbar_arrive_leader(bar_acc_empty + 8 * acc);
+                                else mbar_arrive(bar_acc_empty + 8 * acc);
+                            }
+                            acc ^= 1;
+                            if (acc == 0) acc_phase ^= 1;
+                        }
+                        epi_chunk<false, SYM>(cx, vb, col0 + 64 * h + 32, plain, cdir, thr_tile + 256u * h + 128u);
+                    }
                 }
                 if constexpr (TOPK) {
                     // parked columns of the first tile must be listed before columns start being counted
-                    if (ct == ct0) pend_flush(cx.pd, cx.st, p.eps, p.cap, p.topk, false, cx.hist, cx.li, cx.ls);
+                    if (kt == 0) pend_flush(cx.pd, cx.st, p.eps, p.cap, p.topk, false, cx.hist, cx.li, cx.ls);
                 }
             }
             if constexpr (TOPK) pend_flush(cx.pd, cx.st, p.eps, p.cap, p.topk, true, cx.hist, cx.li, cx.ls);
-            if (cx.row_ok) {
+            if constexpr (SYM) {
+                // publish this unit's best for the row; the shared list is already in place
+                if (cx.row_ok && cx.st.best > -CUDART_INF_F) atomicMax(p.best_enc + cx.row, enc_score(cx.st.best));
+                if (!ui.coldir && p.sync_counter) {   // pre-pass unit done: its rows' thresholds are published
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) atomicAdd(p.sync_counter, 1);
+                }
+            } else if (cx.row_ok) {
                 p.cand_cnt[slot] = cx.st.cnt;
                 p.cand_flags[slot] = cx.st.flags;
                 if constexpr (TOPK) p.cand_kth[slot] = bin_edge(cx.st.tb);
             }
+        }
+        if constexpr (SYM) {
+            __syncwarp();
+            if (lane == 0) p.cand_cnt[log_region_id] = (int)min(*s_logcnt, (unsigned)p.log_region);
         }
         if (tracing && lane == 0 && warp == 2) {
             atomicAdd(p.trace + 4, t_full);    // epilogue warp 0 stalled on a complete accumulator (MMA slower)
@@ -852,7 +1112,7 @@ __global__ void __launch_bounds__(256) rerank_top1_kernel(const T* __restrict__ 
     int flags = 0;
     for (int sp = 0; sp < splits; ++sp) {
         const int64_t slot = (int64_t)sp * nq + r;
-        const int c = cand_cnt[slot];
+        const int c = min(cand_cnt[slot], cap);   // (the symmetric kernel counts appends past the end)
         flags |= cand_flags[slot];
         for (int e = lane; e < c; e += 32) gbest = fmaxf(gbest, cand_score[slot * cap + e]);
     }
@@ -864,7 +1124,7 @@ __global__ void __launch_bounds__(256) rerank_top1_kernel(const T* __restrict__ 
     int best_j = 0x7fffffff, reranked = 0;
     for (int sp = 0; sp < splits; ++sp) {
         const int64_t slot = (int64_t)sp * nq + r;
-        const int c = cand_cnt[slot];
+        const int c = min(cand_cnt[slot], cap);
         for (int e = 0; e < c; ++e) {
             if (cand_score[slot * cap + e] < thr) continue;  // warp-uniform
             const int j = cand_idx[slot * cap + e];
@@ -1087,7 +1347,7 @@ static int make_tmap(CUtensorMap* map, const uint16_t* base, int64_t rows, int d
 static bool g_profile = false, g_have_sample = false;
 static unsigned long long* g_trace = nullptr;   // device [8], allocated by slic_screen_trace(1)
 static cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
-static double g_last_flop = 0.0;
+static double g_last_flop = 0.0, g_last_exec_flop = 0.0;
 
 struct ScreenPlan {
     int splits, tiles_per_split;
@@ -1175,7 +1435,9 @@ static int topk_cap(int k, int64_t cols_per_split) {
 static int launch_screen(const uint16_t* q_bf16, int64_t nq, const uint16_t* x_bf16, int64_t n, int d_pad,
                          int64_t self_offset, float eps, int cap, const ScreenPlan& pl, int* cand_idx, float* cand_score,
                          int* cand_cnt, int* cand_flags, float* dump, int* error_flag, cudaStream_t st, int topk = 0,
-                         float* cand_kth = nullptr, const int2* unit_table = nullptr, const int* gates = nullptr) {
+                         float* cand_kth = nullptr, const int4* unit_table = nullptr, const int* gates = nullptr,
+                         unsigned int* best_enc = nullptr, int64_t exec_tiles = 0, int* log_q = nullptr,
+                         int log_region = 0, int* sync_counter = nullptr, const int* sync_targets = nullptr) {
     const int ncta = screen_ncta();
     CUtensorMap tq, tx;
     SLIC_PROPAGATE(make_tmap(&tq, q_bf16, nq, d_pad, TC_BM));
@@ -1201,12 +1463,25 @@ static int launch_screen(const uint16_t* q_bf16, int64_t nq, const uint16_t* x_b
     p.trace = g_trace;
     p.unit_table = unit_table;
     p.gates = gates;
+    p.best_enc = best_enc;
+    p.log_q = log_q;
+    p.log_region = log_region;
+    p.sync_counter = sync_counter;
+    p.sync_targets = sync_targets;
+    const bool sym = best_enc != nullptr;
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const ScreenParams);
     const bool is_topk = topk > 0;
     const bool ares = ncta == 2 && p.num_k_slabs <= TC_ARES_MAX_SLABS && screen_ares_allowed();
     KernelFn fn;
     size_t smem_bytes;
-    if (ares) {
+    if (sym) {
+        if (ncta != 2 || is_topk || !unit_table) {
+            set_error("symmetric screen: needs the CTA-pair top-1 kernel and a unit list");
+            return SLIC_ERR_UNSUPPORTED;
+        }
+        fn = ares ? (KernelFn)nn_screen_kernel<false, 2, true, true> : (KernelFn)nn_screen_kernel<false, 2, false, true>;
+        smem_bytes = ares ? TcCfg<2, true, false>::SYM_SMEM_BYTES : TcCfg<2, false, false>::SYM_SMEM_BYTES;
+    } else if (ares) {
         fn = is_topk ? (KernelFn)nn_screen_kernel<true, 2, true> : (KernelFn)nn_screen_kernel<false, 2, true>;
         smem_bytes = is_topk ? TcCfg<2, true, true>::SMEM_BYTES : TcCfg<2, true, false>::SMEM_BYTES;
     } else if (ncta == 2) {
@@ -1216,10 +1491,10 @@ static int launch_screen(const uint16_t* q_bf16, int64_t nq, const uint16_t* x_b
         fn = is_topk ? (KernelFn)nn_screen_kernel<true, 1, false> : (KernelFn)nn_screen_kernel<false, 1, false>;
         smem_bytes = is_topk ? TcCfg<1, false, true>::SMEM_BYTES : TcCfg<1, false, false>::SMEM_BYTES;
     }
-    static bool attr_done[64][8] = {{false}};
+    static bool attr_done[64][16] = {{false}};
     int dev = 0;
     SLIC_CUDA_OK(cudaGetDevice(&dev));
-    bool& attr_set = attr_done[dev & 63][(ares ? 4 : 0) + (ncta == 2 ? 2 : 0) + (is_topk ? 1 : 0)];
+    bool& attr_set = attr_done[dev & 63][(sym ? 8 : 0) + (ares ? 4 : 0) + (ncta == 2 ? 2 : 0) + (is_topk ? 1 : 0)];
     if (!attr_set) {
         SLIC_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         attr_set = true;
@@ -1250,6 +1525,7 @@ static int launch_screen(const uint16_t* q_bf16, int64_t nq, const uint16_t* x_b
     if (g_profile) {
         SLIC_CUDA_OK(cudaEventRecord(g_ev_stop, st));
         g_last_flop = 2.0 * (double)nq * (double)n * (double)d_pad;
+        g_last_exec_flop = exec_tiles > 0 ? 2.0 * (double)exec_tiles * TC_BN * TC_BN * (double)d_pad : g_last_flop;
         g_have_sample = true;
     }
     return SLIC_OK;
@@ -1262,8 +1538,74 @@ constexpr int TC_CAP = 32;
 // ordered by that gate so that the persistent CTAs consume the triangle of chunk pairs as it fills:
 //   gate 0: rows of chunk 0 x columns of chunk 0;  gate g: (rows of chunks <= g) x chunk g  and  chunk g x (chunks < g).
 // Inside a gate the units of one column range are adjacent, so concurrent CTAs still share their B slabs through L2.
+static int4 unit_entry(int64_t row_unit, int64_t ct0, int count, int stride, int gate, int stream, bool coldir) {
+    int4 e;
+    e.x = (int)row_unit;
+    e.y = (int)ct0;
+    e.z = (count & 0xffff) | (stride << 16);
+    e.w = ((gate + 1) & 0xfff) | ((stream & 0xffff) << 12) | (coldir ? (1 << 28) : 0);
+    return e;
+}
+
+// Symmetric self-search (Q == X): S = X X^T is symmetric, so only tiles on or right of the diagonal are computed
+// (T (T + 1) / 2 of T^2 256 x 256 tiles) and every off-diagonal tile is filtered twice: along its rows for the row
+// block's queries and along its columns for the column block's.
+//   pre-pass  every row unit x SYM_SAMPLE_TILES column tiles spread over the (already available) database, rows only:
+//             gives every row a first threshold before it is met as a column.  ~2 * SAMPLE / T of extra work.
+//   triangle  column chunks of SYM_CHUNK_TILES tiles, chunk-major: the units of one chunk are adjacent in the list,
+//             so the ~74 concurrently running CTA pairs stream the same 16 MB of B tiles and share them through L2
+//             (row-major orders were measured: each pair then streams its own column range from HBM and the kernel
+//             becomes DRAM-bound).
+// part / parts: this process takes every parts-th triangle unit (multi-GPU); the pre-pass is done by everyone.
+constexpr int SYM_CHUNK_TILES = 64;
+constexpr int SYM_SAMPLE_TILES = 16;
+static int plan_screen_sym(int64_t n, int part, int parts, const GateSpec* g, ScreenPlan* pl, std::vector<int4>* table) {
+    const int64_t T = ceil_div(n, TC_BN);
+    SLIC_REQUIRE(T < 65536, "symmetric screen: more than 16.7 M rows");
+    SLIC_REQUIRE(parts >= 1 && part >= 0 && part < parts, "symmetric screen: bad partition");
+    int64_t chunk_tiles_gate = 0;
+    if (g) {
+        SLIC_REQUIRE(g->gates && g->num_chunks >= 1 && g->num_chunks < 4095 && g->chunk_rows > 0 && g->chunk_rows % TC_BN == 0,
+                     "gated screen: chunk_rows must be a positive multiple of 256");
+        SLIC_REQUIRE(ceil_div(n, g->chunk_rows) == g->num_chunks, "gated screen: chunks do not tile the database");
+        chunk_tiles_gate = g->chunk_rows / TC_BN;
+    }
+    static int nocol = -1;   // experiments: SLIC_SYM_NOCOL=1 (wrong results, timing only)
+    if (nocol < 0) {
+        const char* f = getenv("SLIC_SYM_NOCOL");
+        nocol = f && atoi(f) == 1 ? 1 : 0;
+    }
+    table->clear();
+    // pre-pass sample: tiles spread over the whole matrix, or over the first upload chunk when the rest is in flight
+    const int64_t span = g ? (chunk_tiles_gate < T ? chunk_tiles_gate : T) : T;
+    int samples = SYM_SAMPLE_TILES / parts;
+    if (samples < 4) samples = 4;
+    if (samples > span) samples = (int)span;
+    const int stride = (int)(span / samples);
+    for (int64_t r = 0; r < T; ++r) {
+        const int gate = g ? (int)(r / chunk_tiles_gate) : -1;
+        table->push_back(unit_entry(r, 0, samples, stride, gate, 0, false));
+    }
+    int64_t tri = 0;
+    for (int64_t c0 = 0; c0 < T; c0 += SYM_CHUNK_TILES) {
+        const int64_t c1 = c0 + SYM_CHUNK_TILES < T ? c0 + SYM_CHUNK_TILES : T;
+        for (int64_t r = 0; r < c1; ++r) {
+            const int64_t ct0 = r > c0 ? r : c0;
+            if ((tri++ % parts) != part) continue;
+            const int gate = g ? (int)((c1 - 1) / chunk_tiles_gate) : -1;   // column chunk >= row chunk
+            table->push_back(unit_entry(r, ct0, (int)(c1 - ct0), 1, gate, 0, nocol == 0));
+        }
+    }
+    if (g)   // consume the upload in arrival order: (pre-pass, triangle) of gate 0, then of gate 1, ...
+        std::stable_sort(table->begin(), table->end(), [](const int4& a, const int4& b) { return (a.w & 0xfff) < (b.w & 0xfff); });
+    pl->splits = 1;
+    pl->tiles_per_split = (int)T;
+    pl->units = (int64_t)table->size();
+    return SLIC_OK;
+}
+
 static int plan_screen_gated(int64_t nq, int64_t n, int64_t self_offset, const GateSpec& g, ScreenPlan* pl,
-                             std::vector<int2>* table) {
+                             std::vector<int4>* table) {
     const int ncta = screen_ncta();
     const int64_t rows_per_unit = (int64_t)TC_BM * ncta;
     SLIC_REQUIRE(g.gates && g.num_chunks >= 1 && g.num_chunks < 32768 && g.chunk_rows > 0 && g.chunk_rows % TC_BN == 0,
@@ -1284,28 +1626,45 @@ static int plan_screen_gated(int64_t nq, int64_t n, int64_t self_offset, const G
                 const int rc = (int)((last + self_offset) / g.chunk_rows);
                 const int need = rc > s ? rc : s;
                 if (need != gate) continue;
-                int2 e;
-                e.x = (int)r;
-                e.y = s | (gate << 16);
-                table->push_back(e);
+                const int64_t ct0 = (int64_t)s * pl->tiles_per_split;
+                int64_t cnt = ceil_div(n, TC_BN) - ct0;
+                if (cnt > pl->tiles_per_split) cnt = pl->tiles_per_split;
+                table->push_back(unit_entry(r, ct0, (int)cnt, 1, gate, s, false));
             }
     SLIC_REQUIRE((int64_t)table->size() == pl->units, "gated screen: internal unit count mismatch");
     return SLIC_OK;
 }
 
 template <typename T>
+static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d, int d_pad, float eps, int* idx_out,
+                            T* dist_out, int* stats_out, cudaStream_t st, int part, int parts, const GateSpec* gate,
+                            AfterScreenFn after, void* after_ctx, bool* overflowed);
+static bool screen_sym_allowed();
+constexpr int64_t SYM_MIN_ROWS_FWD = 16384;   // below: too few tiles to fill the machine with half of them
+
+template <typename T>
 static int nn_top1_impl(const T* q_unit, const uint16_t* q_bf16, int64_t nq, const T* x_unit, const uint16_t* x_bf16,
                         int64_t n, int d, int d_pad, int64_t self_offset, float eps, int* idx_out, T* dist_out,
                         int* stats_out, cudaStream_t st, const GateSpec* gate = nullptr, AfterScreenFn after = nullptr,
                         void* after_ctx = nullptr) {
+    if (q_bf16 == x_bf16 && q_unit == x_unit && nq == n && self_offset == 0 && n >= SYM_MIN_ROWS_FWD && screen_sym_allowed()) {
+        bool overflowed = false;
+        SLIC_PROPAGATE(nn_top1_sym_impl<T>(x_unit, x_bf16, n, d, d_pad, eps, idx_out, dist_out, stats_out, st, 0, 1, gate,
+                                           after, after_ctx, &overflowed));
+        if (!overflowed) return SLIC_OK;
+        // (degenerate input: almost every pair within eps of the best) - the full square with per-row lists and the
+        // exact finisher handles it; the upload, if any, has been enqueued and joined already
+        gate = nullptr;
+        after = nullptr;
+    }
     ScreenPlan pl = plan_screen(nq, n);
-    std::vector<int2> table;
+    std::vector<int4> table;
     Scratch table_dev;
     if (gate) {
         SLIC_PROPAGATE(plan_screen_gated(nq, n, self_offset, *gate, &pl, &table));
-        SLIC_CUDA_OK(table_dev.alloc(table.size() * sizeof(int2), st));
+        SLIC_CUDA_OK(table_dev.alloc(table.size() * sizeof(int4), st));
         // pageable source: the runtime stages the bytes before returning, the vector may go out of scope
-        SLIC_CUDA_OK(cudaMemcpyAsync(table_dev.ptr, table.data(), table.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+        SLIC_CUDA_OK(cudaMemcpyAsync(table_dev.ptr, table.data(), table.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
     }
     const int64_t slots = (int64_t)pl.splits * 2 * nq;   // one list per (split, 128-column half of the tiles, row)
     Scratch ci, cs, cc, cf, ovr, stats;
@@ -1318,7 +1677,7 @@ static int nn_top1_impl(const T* q_unit, const uint16_t* q_bf16, int64_t nq, con
     SLIC_CUDA_OK(cudaMemsetAsync(stats.ptr, 0, 8 * sizeof(int), st));
     SLIC_PROPAGATE(launch_screen(q_bf16, nq, x_bf16, n, d_pad, self_offset, eps, TC_CAP, pl, ci.as<int>(), cs.as<float>(),
                                  cc.as<int>(), cf.as<int>(), nullptr, stats.as<int>() + 4, st, 0, nullptr,
-                                 gate ? table_dev.as<int2>() : nullptr, gate ? gate->gates : nullptr));
+                                 gate ? table_dev.as<int4>() : nullptr, gate ? gate->gates : nullptr));
     // gated: the caller now enqueues the upload that feeds the running kernel and makes `st` wait for its end
     if (after) SLIC_PROPAGATE(after(after_ctx));
     rerank_top1_kernel<T><<<(unsigned)ceil_div(nq, 8), 256, 0, st>>>(q_unit, x_unit, nq, d, eps, TC_CAP, 2 * pl.splits,
@@ -1389,6 +1748,233 @@ static int topk_tc_impl(const T* q_unit, const uint16_t* q_bf16, int64_t nq, con
                                               st));
         scatter_topk_rows_kernel<T><<<(unsigned)ceil_div((int64_t)n_over * k, 256), 256, 0, st>>>(
             ovr.as<int>(), n_over, k, oi.as<int>(), od.as<T>(), idx_out, dist_out);
+        SLIC_LAUNCH_OK();
+    }
+    if (stats_out) SLIC_CUDA_OK(cudaMemcpyAsync(stats_out, stats.ptr, 4 * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    return SLIC_OK;
+}
+
+// ---- symmetric self-search ------------------------------------------------------------------------
+constexpr int SYM_LOG_PER_ROW = 96;       // log capacity in records per database row (12 bytes + sizeof(T) each)
+constexpr int64_t SYM_LOG_MIN = (int64_t)1 << 23;
+
+// SLIC_SCREEN_SYM=0 keeps the full-square screen for self-searches (experiments / fallback)
+static bool screen_sym_allowed();
+bool screen_self_search_is_symmetric(int64_t n) { return n >= SYM_MIN_ROWS_FWD && screen_sym_allowed(); }
+static bool screen_sym_allowed() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("SLIC_SCREEN_SYM");
+        cached = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    return cached != 0 && screen_ncta() == 2;
+}
+
+__global__ void fill_u32_kernel(unsigned int* out, int64_t n, unsigned int v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = v;
+}
+
+template <typename T> struct DistBits;
+template <> struct DistBits<float> {
+    typedef unsigned int type;
+    static __device__ __forceinline__ type of(float d) { return __float_as_uint(d); }        // d >= 0: monotone
+    static __device__ __forceinline__ float back(type b) { return __uint_as_float(b); }
+};
+template <> struct DistBits<double> {
+    typedef unsigned long long type;
+    static __device__ __forceinline__ type of(double d) { return (type)__double_as_longlong(d); }
+    static __device__ __forceinline__ double back(type b) { return __longlong_as_double((long long)b); }
+};
+
+// Re-rank, pass 1: one CTA per log region.  A record survives iff its screened score is within eps of its row's FINAL
+// best; survivors are evaluated exactly (one warp per record, float64 accumulation) and the row keeps the smallest
+// distance (rounded to T as the reference holds it).  edist[record] = that distance, or -1 for a dropped record.
+template <typename T>
+__global__ void __launch_bounds__(256) sym_rerank_dist_kernel(const T* __restrict__ unit, int d, float eps, int region,
+                                                              const int* __restrict__ log_q, const int* __restrict__ log_nb,
+                                                              const float* __restrict__ log_s,
+                                                              const int* __restrict__ log_cnt,
+                                                              const unsigned int* __restrict__ best_enc,
+                                                              typename DistBits<T>::type* __restrict__ row_min,
+                                                              T* __restrict__ edist, int* __restrict__ stats) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int64_t base = (int64_t)blockIdx.x * region;
+    const int cnt = log_cnt[blockIdx.x];
+    if (threadIdx.x == 0) {
+        atomicAdd(&stats[3], cnt >> 4);   // records logged by the screen, in units of 16
+        atomicMax(&stats[6], cnt);        // fullest region
+    }
+    int reranked = 0;
+    for (int e0 = warp * 32; e0 < cnt; e0 += nwarps * 32) {
+        const int e = e0 + lane;
+        int q = 0, nb = 0;
+        bool keep = false;
+        if (e < cnt) {
+            q = log_q[base + e];
+            nb = log_nb[base + e];
+            keep = log_s[base + e] >= dec_score(best_enc[q]) - eps;
+            if (!keep) edist[base + e] = (T)-1;
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, keep);
+        while (mask) {
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int qq = __shfl_sync(0xffffffffu, q, src), nn = __shfl_sync(0xffffffffu, nb, src);
+            const double sim = warp_dot<T>(unit + (int64_t)qq * d, unit + (int64_t)nn * d, d, lane);
+            if (lane == 0) {
+                const T dist = cosine_distance_from_sim<T>(sim);
+                edist[base + e0 + src] = dist;
+                atomicMin(row_min + qq, DistBits<T>::of(dist));
+            }
+            ++reranked;
+        }
+    }
+    if (lane == 0 && reranked) atomicAdd(&stats[0], reranked);
+}
+
+// pass 2: among the records that attain the row's smallest distance the lowest neighbour index wins (np.argmin)
+template <typename T>
+__global__ void __launch_bounds__(256) sym_rerank_pick_kernel(int region, const int* __restrict__ log_q,
+                                                              const int* __restrict__ log_nb,
+                                                              const int* __restrict__ log_cnt,
+                                                              const typename DistBits<T>::type* __restrict__ row_min,
+                                                              const T* __restrict__ edist, int* __restrict__ idx_out,
+                                                              T* __restrict__ dist_out) {
+    const int64_t base = (int64_t)blockIdx.x * region;
+    const int cnt = log_cnt[blockIdx.x];
+    for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
+        const T dist = edist[base + e];
+        if (dist < (T)0) continue;
+        const int q = log_q[base + e];
+        if (DistBits<T>::of(dist) == row_min[q]) {
+            atomicMin(idx_out + q, log_nb[base + e]);
+            if (dist_out) dist_out[q] = dist;
+        }
+    }
+}
+
+// rows that received no record at all (cannot happen unless the log overflowed) are reported for the exact kernel
+__global__ void sym_unsettled_rows_kernel(int* __restrict__ idx_out, int64_t n, int* __restrict__ rows, int* __restrict__ stats) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && idx_out[i] == 0x7fffffff) rows[atomicAdd(&stats[1], 1)] = (int)i;
+}
+
+template <typename T>
+static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d, int d_pad, float eps, int* idx_out,
+                            T* dist_out, int* stats_out, cudaStream_t st, int part, int parts, const GateSpec* gate,
+                            AfterScreenFn after, void* after_ctx, bool* overflowed) {
+    typedef typename DistBits<T>::type Bits;
+    *overflowed = false;
+    ScreenPlan pl;
+    std::vector<int4> table;
+    SLIC_PROPAGATE(plan_screen_sym(n, part, parts, gate, &pl, &table));
+    int64_t exec_tiles = 0;
+    for (const int4& e : table) exec_tiles += e.z & 0xffff;
+    // sync_targets[g + 1] = epilogue-warp arrivals of all pre-pass units with gate <= g (index 0: ungated)
+    const int num_gates = gate ? gate->num_chunks : 0;
+    std::vector<int> targets(num_gates + 1, 0);
+    for (const int4& e : table) {
+        if ((e.w >> 28) & 1) continue;          // triangle unit
+        const int g = (e.w & 0xfff) - 1;
+        for (int k = g + 1; k <= num_gates; ++k) targets[k] += 2 * TC_EPI_WARPS;   // g = -1 (ungated): index 0
+    }
+    const int64_t groups = num_sms() / 2;
+    const int64_t grid = (pl.units < groups ? pl.units : groups) * 2;
+    const int64_t regions = grid * TC_EPI_WARPS;
+    // (small inputs log more per row - every row starts from scratch in the pre-pass - and spread it less evenly)
+    const int64_t capacity = (int64_t)SYM_LOG_PER_ROW * n > SYM_LOG_MIN ? (int64_t)SYM_LOG_PER_ROW * n : SYM_LOG_MIN;
+    const int64_t region = ceil_div(capacity, regions);
+    SLIC_REQUIRE(region < ((int64_t)1 << 31), "symmetric screen: log region too large");
+    Scratch table_dev, lq, lnb, ls, lcnt, flag, best, rmin, edist, ovr, stats, sync;
+    SLIC_CUDA_OK(table_dev.alloc(table.size() * sizeof(int4), st));
+    SLIC_CUDA_OK(cudaMemcpyAsync(table_dev.ptr, table.data(), table.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+    SLIC_CUDA_OK(sync.alloc((targets.size() + 1) * sizeof(int), st));   // [0] counter, [1..] targets
+    SLIC_CUDA_OK(cudaMemsetAsync(sync.ptr, 0, sizeof(int), st));
+    SLIC_CUDA_OK(cudaMemcpyAsync(sync.as<int>() + 1, targets.data(), targets.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    SLIC_CUDA_OK(lq.alloc(regions * region * sizeof(int), st));
+    SLIC_CUDA_OK(lnb.alloc(regions * region * sizeof(int), st));
+    SLIC_CUDA_OK(ls.alloc(regions * region * sizeof(float), st));
+    SLIC_CUDA_OK(edist.alloc(regions * region * sizeof(T), st));
+    SLIC_CUDA_OK(lcnt.alloc(regions * sizeof(int), st));
+    SLIC_CUDA_OK(flag.alloc(sizeof(int), st));
+    SLIC_CUDA_OK(best.alloc(n * sizeof(unsigned int), st));
+    SLIC_CUDA_OK(rmin.alloc(n * sizeof(Bits), st));
+    SLIC_CUDA_OK(ovr.alloc(n * sizeof(int), st));
+    SLIC_CUDA_OK(stats.alloc(8 * sizeof(int), st));
+    SLIC_CUDA_OK(cudaMemsetAsync(stats.ptr, 0, 8 * sizeof(int), st));
+    SLIC_CUDA_OK(cudaMemsetAsync(lcnt.ptr, 0, regions * sizeof(int), st));
+    SLIC_CUDA_OK(cudaMemsetAsync(flag.ptr, 0, sizeof(int), st));
+    SLIC_CUDA_OK(cudaMemsetAsync(rmin.ptr, 0xff, n * sizeof(Bits), st));   // all-ones: above every distance's bits
+    fill_u32_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(best.as<unsigned int>(), n, ENC_NEG_INF);
+    SLIC_LAUNCH_OK();
+    fill_u32_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>((unsigned int*)idx_out, n, 0x7fffffffu);
+    SLIC_LAUNCH_OK();
+    SLIC_PROPAGATE(launch_screen(ub, n, ub, n, d_pad, 0, eps, 0, pl, lnb.as<int>(), ls.as<float>(), lcnt.as<int>(),
+                                 flag.as<int>(), nullptr, stats.as<int>() + 4, st, 0, nullptr, table_dev.as<int4>(),
+                                 gate ? gate->gates : nullptr, best.as<unsigned int>(), exec_tiles, lq.as<int>(),
+                                 (int)region, sync.as<int>(), sync.as<int>() + 1));
+    if (after) SLIC_PROPAGATE(after(after_ctx));
+    sym_rerank_dist_kernel<T><<<(unsigned)regions, 256, 0, st>>>(unit, d, eps, (int)region, lq.as<int>(), lnb.as<int>(),
+                                                                 ls.as<float>(), lcnt.as<int>(), best.as<unsigned int>(),
+                                                                 rmin.as<Bits>(), edist.as<T>(), stats.as<int>());
+    SLIC_LAUNCH_OK();
+    sym_rerank_pick_kernel<T><<<(unsigned)regions, 256, 0, st>>>((int)region, lq.as<int>(), lnb.as<int>(), lcnt.as<int>(),
+                                                                 rmin.as<Bits>(), edist.as<T>(), idx_out, dist_out);
+    SLIC_LAUNCH_OK();
+    sym_unsettled_rows_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(idx_out, n, ovr.as<int>(), stats.as<int>());
+    SLIC_LAUNCH_OK();
+    SLIC_CUDA_OK(cudaMemcpyAsync(stats.as<int>() + 5, flag.ptr, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    int host_stats[8];
+    SLIC_CUDA_OK(cudaMemcpyAsync(host_stats, stats.ptr, sizeof(host_stats), cudaMemcpyDeviceToHost, st));
+    SLIC_CUDA_OK(cudaStreamSynchronize(st));
+    if (host_stats[4] == 2) {
+        set_error("nn_screen_kernel: shared-memory window is not aligned as the symmetric layout assumes (set SLIC_SCREEN_SYM=0)");
+        return SLIC_ERR_UNSUPPORTED;
+    }
+    if (host_stats[4] != 0) {
+        set_error("nn_screen_kernel: pipeline barrier timed out");
+        return SLIC_ERR_CUDA;
+    }
+    if (const char* dbg = getenv("SLIC_SYM_DEBUG")) {
+        if (atoi(dbg) == 2) {   // dump the candidate log for offline analysis (scripts/sym_log_stats.py)
+            std::vector<int> hq((size_t)(regions * region)), hnb((size_t)(regions * region)), hc((size_t)regions);
+            std::vector<float> hs((size_t)(regions * region));
+            cudaMemcpy(hq.data(), lq.ptr, hq.size() * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(hnb.data(), lnb.ptr, hnb.size() * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(hs.data(), ls.ptr, hs.size() * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(hc.data(), lcnt.ptr, hc.size() * 4, cudaMemcpyDeviceToHost);
+            FILE* f = fopen("/tmp/slic_sym_log.bin", "wb");
+            if (f) {
+                long long hdr[3] = {(long long)n, (long long)regions, (long long)region};
+                fwrite(hdr, sizeof(hdr), 1, f);
+                fwrite(hc.data(), 4, hc.size(), f);
+                fwrite(hq.data(), 4, hq.size(), f);
+                fwrite(hnb.data(), 4, hnb.size(), f);
+                fwrite(hs.data(), 4, hs.size(), f);
+                fclose(f);
+            }
+        }
+    }
+    if (host_stats[5] != 0) {   // a log region filled up: records are missing, the caller repeats on the full square
+        if (getenv("SLIC_SYM_DEBUG"))
+            fprintf(stderr, "[slic] symmetric screen: log overflow, n=%lld regions=%lld region=%lld records=%d fullest=%d\n",
+                    (long long)n, (long long)regions, (long long)region, host_stats[3] * 16, host_stats[6]);
+        *overflowed = true;
+        return SLIC_OK;
+    }
+    if (getenv("SLIC_SYM_DEBUG"))
+        fprintf(stderr, "[slic] symmetric screen: n=%lld regions=%lld region=%lld records=%d fullest=%d\n", (long long)n,
+                (long long)regions, (long long)region, host_stats[3] * 16, host_stats[6]);
+    const int n_over = host_stats[1];
+    if (n_over > 0) {
+        Scratch oi, od;
+        SLIC_CUDA_OK(oi.alloc((int64_t)n_over * sizeof(int), st));
+        SLIC_CUDA_OK(od.alloc((int64_t)n_over * sizeof(T), st));
+        SLIC_PROPAGATE(slic_nn_exact_top1(unit, ovr.as<int>(), n_over, unit, n, d, sizeof(T) == 4 ? SLIC_F32 : SLIC_F64, 0,
+                                          oi.as<int>(), od.ptr, st));
+        scatter_rows_kernel<T><<<(unsigned)ceil_div(n_over, 256), 256, 0, st>>>(ovr.as<int>(), n_over, oi.as<int>(),
+                                                                                od.as<T>(), idx_out, dist_out);
         SLIC_LAUNCH_OK();
     }
     if (stats_out) SLIC_CUDA_OK(cudaMemcpyAsync(stats_out, stats.ptr, 4 * sizeof(int), cudaMemcpyDeviceToDevice, st));
@@ -1486,6 +2072,12 @@ int slic_last_screen_time(float* ms_out, double* flop_out) {
     SLIC_CUDA_OK(cudaEventSynchronize(slic::g_ev_stop));
     SLIC_CUDA_OK(cudaEventElapsedTime(ms_out, slic::g_ev_start, slic::g_ev_stop));
     *flop_out = slic::g_last_flop;
+    return SLIC_OK;
+}
+
+int slic_last_screen_exec_flop(double* flop_out) {
+    SLIC_REQUIRE(flop_out, "last_screen_exec_flop: null pointer");
+    *flop_out = slic::g_have_sample ? slic::g_last_exec_flop : 0.0;
     return SLIC_OK;
 }
 
