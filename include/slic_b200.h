@@ -108,6 +108,23 @@ int slic_nn_top1(const void* q_unit_dev, const uint16_t* q_bf16_dev, int64_t nq,
                  candidates re-ranked, rows finished by the exact kernel, list compactions, 0 */,
                  slic_stream_t stream);
 
+/* Multi-GPU share of the level-0 self-search (clustering/finch.py:27-29 on N rows, spread over the GPUs of one box).
+ * The score matrix of a self-search is symmetric: only the 256 x 256 tiles on or right of its diagonal are computed
+ * and each is filtered along its rows and along its columns.  Process `part` of `parts` screens every parts-th unit of
+ * that triangle (plus a small pre-pass over all rows) and re-ranks its candidates exactly, so it holds, for EVERY row,
+ * the best neighbour among the pairs it saw.  keys_out_dev [n + 1] (uint64):
+ *   keys[i] = (float32 distance bits << 32) | neighbour index   (0x7fffffff7fffffff: no candidate seen for row i)
+ *   keys[n] = 1, or 0 if this part's candidate log overflowed (its keys are then incomplete)
+ * An element-wise MIN over the parts' arrays - one all-reduce over NCCL / NVLink - yields every row's first
+ * neighbour with np.argmin's tie rule (smallest distance, then lowest index) and tells every process whether the
+ * result is complete; slic_unpack_neighbor_keys splits it.  Needs n >= 16384 (SLIC_ERR_UNSUPPORTED below). */
+int slic_nn_top1_sym_part(const float* unit_dev, const uint16_t* unit_bf16_dev, int64_t n, int32_t d,
+                          int32_t d_pad, int32_t part, int32_t parts, float eps, uint64_t* keys_out_dev,
+                          int32_t* stats_out_dev /* [4] or NULL, as slic_nn_top1 */, slic_stream_t stream);
+/* keys [n] (merged) -> idx_out [n] int32, dist_out [n] float32; status_out_dev[0] = rows without a neighbour. */
+int slic_unpack_neighbor_keys(const uint64_t* keys_dev, int64_t n, int32_t* idx_out_dev,
+                              float* dist_out_dev, int32_t* status_out_dev, slic_stream_t stream);
+
 /* Debug / test hook: raw bf16-screen scores of one 128 x 256 tile region, written as float
  * [nq, n] (small shapes only).  Lets the tests check the tcgen05 path element by element. */
 int slic_screen_scores_debug(const uint16_t* q_bf16_dev, int64_t nq, const uint16_t* x_bf16_dev,

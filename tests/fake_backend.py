@@ -65,6 +65,47 @@ class FakeBackend:
         nn, d = self.nn_exact_top1(unit[r0:r1], unit, self_offset=r0)
         return nn, d, unit
 
+    # multi-process share of the symmetric self-search (slic_nn_top1_sym_part / slic_unpack_neighbor_keys)
+    PART_BLOCK = 64
+    SYM_MIN_ROWS = 256          # (the CUDA backend: 16384)
+    KEY_NONE = 0x7fffffff7fffffff
+
+    def supports_triangle_parts(self, x):
+        return x.dtype == torch.float32 and x.shape[0] >= self.SYM_MIN_ROWS
+
+    def first_neighbors_part(self, x, part, parts):
+        """Block pairs (bi <= bj) of the distance matrix are dealt round-robin to the parts; a part evaluates its pairs
+        in both directions and keeps, per row, the smallest (distance bits, neighbour) key."""
+        self.calls.append(("first_neighbors_part", tuple(x.shape), part, parts))
+        unit, _ = self.normalize_rows(x, want_bf16=False)
+        u = _np(unit)
+        n, b = len(u), self.PART_BLOCK
+        keys = np.full(n + 1, self.KEY_NONE, dtype=np.int64)
+        keys[n] = 1
+        nb = (n + b - 1) // b
+        t = 0
+        for bi in range(nb):
+            for bj in range(bi, nb):
+                t += 1
+                if (t - 1) % parts != part:
+                    continue
+                ri, rj = np.arange(bi * b, min(n, bi * b + b)), np.arange(bj * b, min(n, bj * b + b))
+                s = u[ri].astype(np.float64) @ u[rj].astype(np.float64).T
+                dm = np.clip(np.float32(1) - s.astype(np.float32), 0, 2).astype(np.float32)
+                for rows, cols, m in ((ri, rj, dm), (rj, ri, dm.T)):
+                    k = (m.view(np.uint32).astype(np.int64) << 32) | cols[None, :].astype(np.int64)
+                    k[rows[:, None] == cols[None, :]] = self.KEY_NONE
+                    keys[rows] = np.minimum(keys[rows], k.min(axis=1))
+        return torch.from_numpy(keys), unit
+
+    def unpack_neighbor_keys(self, keys):
+        k = _np(keys)
+        n = len(k) - 1
+        nn = (k[:n] & 0xffffffff).astype(np.int32)
+        d = (k[:n] >> 32).astype(np.uint32).view(np.float32)
+        complete = bool(k[n] == 1 and not (k[:n] == self.KEY_NONE).any())
+        return torch.from_numpy(nn), torch.from_numpy(d.copy()), complete
+
     def distance_matrix(self, q, x, metric="cosine", same=False):
         dt = _np(x).dtype
         if metric == "cosine":

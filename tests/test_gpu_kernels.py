@@ -370,3 +370,42 @@ def test_symmetric_screen_dense_cluster_rows_overflow_to_exact(be):
     assert torch.equal(idx_tc, idx_ex)
     np.testing.assert_allclose(dist_tc.cpu().numpy(), dist_ex.cpu().numpy(), rtol=0, atol=1.2e-7)
     assert int(be.last_stats[1]) >= 600
+
+
+@pytest.mark.parametrize("n,d,k,seed,parts", [(16384, 64, 40, 1, 2), (50000, 512, 300, 3, 3), (41003, 200, 0, 6, 8)])
+def test_symmetric_screen_parts_merge_to_the_full_search(be, n, d, k, seed, parts):
+    """Multi-GPU share of the self-search (slic_nn_top1_sym_part): each part screens every parts-th unit of the
+    triangle; the element-wise MIN of the parts' (distance, neighbour) keys - what the all-reduce over the ranks
+    computes - must be the exact first neighbour of every row, and every part must be complete."""
+    if k:
+        x = synth.gaussian_mixture(n, d, k, seed)
+    else:
+        x = np.random.default_rng(seed).standard_normal((n, d)).astype(np.float32)
+    xd = be.to_device(x)
+    assert be.supports_triangle_parts(xd)
+    merged = None
+    for part in range(parts):
+        keys, unit = be.first_neighbors_part(xd, part, parts)
+        assert int(keys[n]) == 1
+        merged = keys if merged is None else torch.minimum(merged, keys)
+    nn, dist, complete = be.unpack_neighbor_keys(merged)
+    assert complete
+    idx_ex, dist_ex = be.nn_exact_top1(unit, unit, self_offset=0)
+    assert torch.equal(nn, idx_ex)
+    np.testing.assert_allclose(dist.cpu().numpy(), dist_ex.cpu().numpy(), rtol=0, atol=1.2e-7)
+    # a single part alone is NOT the answer (it saw a fraction of the pairs) - the merge is doing real work
+    if parts > 1:
+        nn0, _, _ = be.unpack_neighbor_keys(keys)
+        assert not torch.equal(nn0, idx_ex)
+    # parts = 1 is the whole triangle
+    keys1, _ = be.first_neighbors_part(xd, 0, 1)
+    nn1, _, complete1 = be.unpack_neighbor_keys(keys1)
+    assert complete1 and torch.equal(nn1, idx_ex)
+
+
+def test_symmetric_screen_part_rejects_small_inputs(be):
+    from video_similarity_search_b200 import _lib
+    xd = be.to_device(synth.gaussian_mixture(4000, 64, 10, 1))
+    assert not be.supports_triangle_parts(xd)
+    with pytest.raises(_lib.SlicError, match="status -3"):
+        be.first_neighbors_part(xd, 0, 2)

@@ -32,11 +32,30 @@ def _worker(rank, world, port, name, golden_dir, out_dir):
         n = len(x)
         r0, r1, per = shard_range(n, rank, world)
         assert per * world >= n and 0 <= r0 <= r1 <= n
-        nn, d, _ = sharded_first_neighbors(be)(be.to_device(x, torch.float32))
+        nn, d, _ = sharded_first_neighbors(be, triangle=False)(be.to_device(x, torch.float32))
         full_nn, full_d, _ = FakeBackend().first_neighbors(torch.from_numpy(x))
         assert torch.equal(nn, full_nn) and torch.equal(d, full_d)
         # only this rank's shard was searched locally
         assert [c[3] for c in be.calls if c[0] == "first_neighbors"] == [(r0, r1)]
+        # triangle parts: every rank screens every world-th block pair, one all-reduce (MIN) of the keys merges them
+        be2 = FakeBackend()
+        nn2, d2, _ = sharded_first_neighbors(be2)(be2.to_device(x, torch.float32))
+        assert torch.equal(nn2, full_nn) and torch.equal(d2, full_d)
+        assert [c[2:] for c in be2.calls if c[0] == "first_neighbors_part"] == [(rank, world)]
+        assert not [c for c in be2.calls if c[0] == "first_neighbors"]
+        # an incomplete part (candidate log overflow on one rank) sends every rank to the row-sharded search
+        be3 = FakeBackend()
+        part = be3.first_neighbors_part
+
+        def overflowing(mat, p, ps):
+            keys, unit = part(mat, p, ps)
+            if p == ps - 1:
+                keys[-1] = 0
+            return keys, unit
+        be3.first_neighbors_part = overflowing
+        nn3, d3, _ = sharded_first_neighbors(be3)(be3.to_device(x, torch.float32))
+        assert torch.equal(nn3, full_nn) and torch.equal(d3, full_d)
+        assert [c[3] for c in be3.calls if c[0] == "first_neighbors"] == [(r0, r1)]
         # query-sharded retrieval top-k: identical to the unsharded search on every rank (ragged last shard included)
         from video_similarity_search_b200.sharded import topk_neighbors_sharded
         xt = be.to_device(x, torch.float32)

@@ -25,6 +25,8 @@ SIGNATURES = {
     "slic_normalize_rows": [_ptr, _i64, _i32, _i32, _ptr, _ptr, _ptr, _i32, _ptr],
     "slic_nn_exact_top1": [_ptr, _ptr, _i64, _ptr, _i64, _i32, _i32, _i64, _ptr, _ptr, _ptr],
     "slic_nn_top1": [_ptr, _ptr, _i64, _ptr, _ptr, _i64, _i32, _i32, _i32, _i64, _f32, _ptr, _ptr, _ptr, _ptr],
+    "slic_nn_top1_sym_part": [_ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _f32, _ptr, _ptr, _ptr],
+    "slic_unpack_neighbor_keys": [_ptr, _i64, _ptr, _ptr, _ptr, _ptr],
     "slic_screen_scores_debug": [_ptr, _i64, _ptr, _i64, _i32, _ptr, _ptr],
     "slic_distance_matrix": [_ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _i32, _ptr, _i64, _ptr],
     "slic_rows_topk": [_ptr, _i64, _i64, _i64, _i32, _i32, _ptr, _ptr, _ptr],

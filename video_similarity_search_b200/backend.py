@@ -116,6 +116,36 @@ class CudaBackend:
             nn, dist = self.nn_exact_top1(unit[r0:r1], unit, self_offset=r0)
         return nn, dist, unit
 
+    # rows from which the self-search runs on the symmetric screen (SYM_MIN_ROWS_FWD in csrc/nn_screen_tc.cu)
+    SYM_MIN_ROWS = 16384
+
+    def supports_triangle_parts(self, x):
+        """True when the multi-process share of the symmetric self-search applies (level 0: float32, large n)."""
+        return x.dtype == torch.float32 and x.shape[0] >= self.SYM_MIN_ROWS
+
+    def first_neighbors_part(self, x, part, parts):
+        """This process's share of the symmetric first-neighbour search of all rows of x (slic_nn_top1_sym_part).
+        -> (keys int64 [n + 1], unit): keys[i] = (distance bits << 32) | neighbour for the best pair this part saw,
+        keys[n] = completeness flag; an element-wise MIN over the parts merges them."""
+        n, d = x.shape
+        unit, ub = self.normalize_rows(x, want_bf16=True)
+        keys = torch.empty(n + 1, dtype=torch.int64, device=x.device)
+        stats = torch.zeros(4, dtype=torch.int32, device=x.device)
+        _lib.call("slic_nn_top1_sym_part", _p(unit), _p(ub), n, d, ub.shape[1], int(part), int(parts), 0.0, _p(keys),
+                  _p(stats), self._stream())
+        self.last_stats = stats
+        return keys, unit
+
+    def unpack_neighbor_keys(self, keys):
+        """Merged keys [n + 1] -> (nn int32 [n], dist float32 [n], complete bool).  One host read-back."""
+        n = keys.shape[0] - 1
+        nn = torch.empty(n, dtype=torch.int32, device=keys.device)
+        dist = torch.empty(n, dtype=torch.float32, device=keys.device)
+        status = torch.empty(1, dtype=torch.int32, device=keys.device)
+        _lib.call("slic_unpack_neighbor_keys", _p(keys), n, _p(nn), _p(dist), _p(status), self._stream())
+        flags = torch.stack((keys[n], status[0].to(torch.int64))).tolist()
+        return nn, dist, flags[0] == 1 and flags[1] == 0
+
     def screen_scores_debug(self, q_bf16, x_bf16):
         nq, n = q_bf16.shape[0], x_bf16.shape[0]
         out = torch.zeros((nq, n), dtype=torch.float32, device=x_bf16.device)

@@ -27,6 +27,7 @@
 // Bound: tensor pipe.  Algorithmic work 2 * nq * n * d_pad flop; HBM traffic ~ (nq + n) * d_pad * 2 bytes.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
 #include <math_constants.h>
@@ -62,10 +63,17 @@ template <int NCTA, bool ARES, bool TOPK> struct TcCfg {
     static constexpr uint32_t OPERAND_BYTES = A_RES_BYTES + STAGES * STAGE_BYTES;            // 192 KB, ARES: 192 / 224 KB
     static constexpr uint32_t SMEM_BYTES = OPERAND_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/ +
                                            (TOPK ? 32768u : 0u) /*histograms*/;
-    // symmetric variant: + 2 KB of column thresholds; the A-resident layout then leaves 768 bytes of alignment slack
-    static constexpr uint32_t SYM_THR_BYTES = 2 * 2 * 128 * 4;   // [2 parities][2 halves][128 columns]
+    // symmetric variant: + 1 KB of column thresholds (float16, rounded down); the A-resident layout then leaves 768
+    // bytes of alignment slack.  An SM has 228 KB of shared memory and every resident CTA reserves 1 KB of it: a
+    // window above 226 KB would own the SM outright, and the kernels that feed a gated launch from another stream
+    // (normalise, gate memset) could never become resident next to it - the launch would wait for itself.
+    static constexpr uint32_t SYM_THR_BYTES = 2 * 2 * 128 * 2;   // [2 parities][2 halves][128 columns] float16
     static constexpr uint32_t SYM_SMEM_BYTES = OPERAND_BYTES + 256 + SYM_THR_BYTES + (ARES ? 768u : 1024u);
-    static_assert(TOPK || SYM_SMEM_BYTES <= 232448, "symmetric variant exceeds the shared memory of a CTA");
+    static constexpr uint32_t CORESIDENT_MAX_BYTES = 233472 - 2 * 1024;
+    static_assert(TOPK || SYM_SMEM_BYTES <= CORESIDENT_MAX_BYTES,
+                  "symmetric variant leaves no shared memory for a co-resident CTA of the upload stream");
+    static_assert(TOPK || SMEM_BYTES <= CORESIDENT_MAX_BYTES,
+                  "top-1 variant (gated launches) leaves no shared memory for a co-resident CTA of the upload stream");
     static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
     static_assert(!ARES || NCTA == 2, "the A-resident variant exists for CTA pairs only");
 };
@@ -525,6 +533,19 @@ __device__ __forceinline__ void pend_flush(Pending& pd, RowStateK& st, float eps
     pd.n = 0;
 }
 
+// float16 threshold (low / high half of w) minus a float32 score in ONE instruction (FHADD, sm_100 mixed precision);
+// the difference of two nearby floats is exact, so (t - s <= 0) <=> (s >= t)
+__device__ __forceinline__ float thr_lo_minus(uint32_t w, float s) {
+    float d;
+    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tsub.rn.f32.f16 %0, lo, %2;\n\t}" : "=f"(d) : "r"(w), "f"(s));
+    return d;
+}
+__device__ __forceinline__ float thr_hi_minus(uint32_t w, float s) {
+    float d;
+    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tsub.rn.f32.f16 %0, hi, %2;\n\t}" : "=f"(d) : "r"(w), "f"(s));
+    return d;
+}
+
 // ---- per-thread epilogue context and the filter of one 32-column chunk ----------------------------
 template <bool TOPK>
 struct EpiCtx {
@@ -637,33 +658,36 @@ __device__ __forceinline__ void epi_chunk(EpiCtx<TOPK>& cx, uint32_t (&v)[32], i
         }
         if constexpr (SYM) {
             if (cdir) {
-                // column role.  thr[t] (shared memory, written once per tile) = threshold of column col_base + t.  Every
-                // thread takes the maximum of (score - column threshold) over its row's 32 columns - the exact test, so that
-                // the per-column spread of the thresholds cancels (block-level tests against the lowest threshold of a
+                // column role.  thr[t] (shared memory, float16, written once per tile) = threshold of column col_base + t.
+                // Every thread takes the minimum of (column threshold - score) over its row's 32 columns - the exact test, so
+                // that the per-column spread of the thresholds cancels (block-level tests against the lowest threshold of a
                 // group of columns were measured: they fire for 40-56 % of the blocks) - and only a row with a
-                // non-negative margin looks closer.
-                float mc = -CUDART_INF_F;
+                // non-positive margin looks closer.
+                float mc = CUDART_INF_F;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float4 t4;   // (explicit ld.shared: a generic load would go the slow way round)
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                 : "=f"(t4.x), "=f"(t4.y), "=f"(t4.z), "=f"(t4.w)
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t w0, w1, w2, w3;   // 8 thresholds (explicit ld.shared: a generic load would go the slow way round)
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
                                  : "r"(thr_s + 16u * j));
-                    mc = fmaxf(mc, fmaxf(__uint_as_float(v[4 * j]) - t4.x, __uint_as_float(v[4 * j + 1]) - t4.y));
-                    mc = fmaxf(mc, fmaxf(__uint_as_float(v[4 * j + 2]) - t4.z, __uint_as_float(v[4 * j + 3]) - t4.w));
+                    mc = fminf(mc, fminf(thr_lo_minus(w0, __uint_as_float(v[8 * j])), thr_hi_minus(w0, __uint_as_float(v[8 * j + 1]))));
+                    mc = fminf(mc, fminf(thr_lo_minus(w1, __uint_as_float(v[8 * j + 2])), thr_hi_minus(w1, __uint_as_float(v[8 * j + 3]))));
+                    mc = fminf(mc, fminf(thr_lo_minus(w2, __uint_as_float(v[8 * j + 4])), thr_hi_minus(w2, __uint_as_float(v[8 * j + 5]))));
+                    mc = fminf(mc, fminf(thr_lo_minus(w3, __uint_as_float(v[8 * j + 6])), thr_hi_minus(w3, __uint_as_float(v[8 * j + 7]))));
                 }
-                const bool hit = cx.row_ok && mc >= 0.f;
+                const bool hit = cx.row_ok && mc <= 0.f;
                 if (cx.tracing) {
                     ++cx.n_chunks;
                     cx.n_trig += __any_sync(0xffffffffu, hit) ? 1 : 0;
                 }
                 if (hit) {
 #pragma unroll
-                    for (int t = 0; t < 32; ++t) {
-                        const float s = __uint_as_float(v[t]);
-                        float th;
-                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(th) : "r"(thr_s + 4u * t));
-                        if (s >= th) log_append(cx.lg, p.best_enc, (int)(col_base + t), (int)cx.row, s);
+                    for (int t = 0; t < 32; t += 2) {
+                        uint32_t w;
+                        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(thr_s + 2u * t));
+                        const float s0 = __uint_as_float(v[t]), s1 = __uint_as_float(v[t + 1]);
+                        if (thr_lo_minus(w, s0) <= 0.f) log_append(cx.lg, p.best_enc, (int)(col_base + t), (int)cx.row, s0);
+                        if (thr_hi_minus(w, s1) <= 0.f) log_append(cx.lg, p.best_enc, (int)(col_base + t + 1), (int)cx.row, s1);
                     }
                 }
             }
@@ -882,7 +906,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
         cx.n_chunks = 0;
         if constexpr (TOPK) cx.hist = smem + Cfg::OPERAND_BYTES + 256 + half * TC_BM + row_in_tile;
         unsigned int* s_logcnt = reinterpret_cast<unsigned int*>(bars + 20) + (warp - 2);   // spare bytes of the barrier block
-        float* thr_buf = reinterpret_cast<float*>(smem + Cfg::OPERAND_BYTES + 256);         // SYM: [2 parities][2 halves][128]
+        uint16_t* thr_buf = reinterpret_cast<uint16_t*>(smem + Cfg::OPERAND_BYTES + 256);   // SYM: float16 [2 parities][2 halves][128]
         unsigned tile_seq = 0;
         unsigned nbc0 = 0u, nbc1 = 0u, nbc2 = 0u, nbc3 = 0u;   // SYM, first warp of a half: next tile's published column bests
         const int64_t log_region_id = (int64_t)blockIdx.x * TC_EPI_WARPS + (warp - 2);
@@ -940,7 +964,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
                     // (double-buffered by tile parity), then one named barrier of the half's four warps.  The writer fetched
                     // the published bests one tile ahead (nbc*), so that no L2 round trip sits in front of the barrier.
                     cdir = ui.coldir && ct != ui.row_unit;
-                    float* tb = thr_buf + (((tile_seq & 1) * 2 + half) * 128);
+                    uint16_t* tb = thr_buf + (((tile_seq & 1) * 2 + half) * 128);
                     if (quad == 0) {
                         constexpr unsigned ENC_POS_INF = 0xff800000u;
                         if (kt == 0 && cdir) {   // first tile of the unit: nothing was prefetched
@@ -951,14 +975,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
                             nbc3 = c + 96 < p.n ? __ldcg(p.best_enc + c + 96) : ENC_POS_INF;
                         }
                         if (cdir) {
-                            // finite lower bound: a masked (-inf) score minus the threshold stays -inf, never NaN
-                            float t0 = fmaxf(dec_score(nbc0) - p.eps, -3.0e38f), t1 = fmaxf(dec_score(nbc1) - p.eps, -3.0e38f);
-                            float t2 = fmaxf(dec_score(nbc2) - p.eps, -3.0e38f), t3 = fmaxf(dec_score(nbc3) - p.eps, -3.0e38f);
-                            const uint32_t ta = smem_u32(tb) + 4u * lane;
-                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(ta), "f"(t0) : "memory");
-                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(ta + 128u), "f"(t1) : "memory");
-                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(ta + 256u), "f"(t2) : "memory");
-                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(ta + 384u), "f"(t3) : "memory");
+                            // float16, rounded DOWN (a lower threshold only adds candidates; 2^-11 against eps = 2^-7), with a
+                            // finite lower bound: the threshold minus a masked (-inf) score is then +inf, never NaN
+                            const unsigned short t0 = __half_as_ushort(__float2half_rd(fmaxf(dec_score(nbc0) - p.eps, -60000.f)));
+                            const unsigned short t1 = __half_as_ushort(__float2half_rd(fmaxf(dec_score(nbc1) - p.eps, -60000.f)));
+                            const unsigned short t2 = __half_as_ushort(__float2half_rd(fmaxf(dec_score(nbc2) - p.eps, -60000.f)));
+                            const unsigned short t3 = __half_as_ushort(__float2half_rd(fmaxf(dec_score(nbc3) - p.eps, -60000.f)));
+                            const uint32_t ta = smem_u32(tb) + 2u * lane;
+                            asm volatile("st.shared.b16 [%0], %1;" ::"r"(ta), "h"(t0) : "memory");
+                            asm volatile("st.shared.b16 [%0], %1;" ::"r"(ta + 64u), "h"(t1) : "memory");
+                            asm volatile("st.shared.b16 [%0], %1;" ::"r"(ta + 128u), "h"(t2) : "memory");
+                            asm volatile("st.shared.b16 [%0], %1;" ::"r"(ta + 192u), "h"(t3) : "memory");
                         }
                         if (ui.coldir && kt + 1 < ui.count) {   // next tile of this unit (never the diagonal: ct grows)
                             const int64_t c = col0 + (int64_t)ui.stride * TC_BN + lane;
@@ -1031,7 +1058,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
                     for (int h = 0; h < 2; ++h) {
                         tmem_ld_wait(va);
                         tmem_ld_issue(tbase + (uint32_t)(64 * h + 32), vb);
-                        epi_chunk<false, SYM>(cx, va, col0 + 64 * h, plain, cdir, thr_tile + 256u * h);
+                        epi_chunk<false, SYM>(cx, va, col0 + 64 * h, plain, cdir, thr_tile + 128u * h);
                         tmem_ld_wait(vb);
                         if (h == 0) {
                             tmem_ld_issue(tbase + 64u, va);
@@ -1046,7 +1073,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_c
                             acc ^= 1;
                             if (acc == 0) acc_phase ^= 1;
                         }
-                        epi_chunk<false, SYM>(cx, vb, col0 + 64 * h + 32, plain, cdir, thr_tile + 256u * h + 128u);
+                        epi_chunk<false, SYM>(cx, vb, col0 + 64 * h + 32, plain, cdir, thr_tile + 128u * h + 64u);
                     }
                 }
                 if constexpr (TOPK) {
@@ -1967,7 +1994,7 @@ static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d,
         fprintf(stderr, "[slic] symmetric screen: n=%lld regions=%lld region=%lld records=%d fullest=%d\n", (long long)n,
                 (long long)regions, (long long)region, host_stats[3] * 16, host_stats[6]);
     const int n_over = host_stats[1];
-    if (n_over > 0) {
+    if (n_over > 0 && parts == 1) {   // (parts > 1: the caller merges the parts first and finishes what is left)
         Scratch oi, od;
         SLIC_CUDA_OK(oi.alloc((int64_t)n_over * sizeof(int), st));
         SLIC_CUDA_OK(od.alloc((int64_t)n_over * sizeof(T), st));
@@ -1979,6 +2006,30 @@ static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d,
     }
     if (stats_out) SLIC_CUDA_OK(cudaMemcpyAsync(stats_out, stats.ptr, 4 * sizeof(int), cudaMemcpyDeviceToDevice, st));
     return SLIC_OK;
+}
+
+// ---- multi-GPU symmetric self-search: every process screens every parts-th triangle unit ----------------
+// key = (float32 distance bits << 32) | neighbour: distances are >= 0, so their bit patterns order like the values and
+// an element-wise MIN over the processes' key arrays (one all-reduce) picks the smallest distance and, among equal
+// distances, the lowest neighbour index - np.argmin's rule.  A row without a record keeps the largest key.
+constexpr unsigned long long SYM_KEY_NONE = 0x7fffffff7fffffffull;
+
+__global__ void sym_pack_keys_kernel(const int* __restrict__ idx, const float* __restrict__ dist, int64_t n,
+                                     unsigned long long* __restrict__ keys) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int j = idx[i];
+    keys[i] = j == 0x7fffffff ? SYM_KEY_NONE : (((unsigned long long)__float_as_uint(dist[i]) << 32) | (unsigned int)j);
+}
+
+__global__ void sym_unpack_keys_kernel(const unsigned long long* __restrict__ keys, int64_t n, int* __restrict__ idx,
+                                       float* __restrict__ dist, int* __restrict__ unsettled) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = keys[i];
+    idx[i] = (int)(unsigned int)(k & 0xffffffffull);
+    dist[i] = __uint_as_float((unsigned int)(k >> 32));
+    if (k == SYM_KEY_NONE) atomicAdd(unsettled, 1);
 }
 
 int nn_top1_f32_gated(const float* q_unit, const uint16_t* q_bf16, int64_t nq, const float* x_unit,
@@ -2013,6 +2064,53 @@ int slic_nn_top1(const void* q_unit_dev, const uint16_t* q_bf16_dev, int64_t nq,
     return slic::nn_top1_impl<double>((const double*)q_unit_dev, q_bf16_dev, nq, (const double*)x_unit_dev, x_bf16_dev, n,
                                       d, d_pad, self_offset, eps, idx_out_dev, (double*)dist_out_dev, stats_out_dev,
                                       st);
+}
+
+int slic_nn_top1_sym_part(const float* unit_dev, const uint16_t* bf16_dev, int64_t n, int32_t d, int32_t d_pad,
+                          int32_t part, int32_t parts, float eps, uint64_t* keys_out_dev, int32_t* stats_out_dev,
+                          slic_stream_t stream) {
+    using namespace slic;
+    SLIC_REQUIRE(n > 1 && n < ((int64_t)1 << 31), "nn_top1_sym_part: bad shape");
+    SLIC_REQUIRE(d > 0 && d_pad >= d && d_pad % 64 == 0, "nn_top1_sym_part: d_pad must be a multiple of 64 >= d");
+    SLIC_REQUIRE(unit_dev && bf16_dev && keys_out_dev, "nn_top1_sym_part: null pointer");
+    SLIC_REQUIRE(parts >= 1 && part >= 0 && part < parts, "nn_top1_sym_part: part must be in [0, parts)");
+    SLIC_REQUIRE((reinterpret_cast<uintptr_t>(bf16_dev) & 15) == 0, "nn_top1_sym_part: bf16 matrix must be 16-byte aligned");
+    SLIC_PROPAGATE(slic_require_device());
+    if (!screen_self_search_is_symmetric(n)) {
+        set_error("nn_top1_sym_part: the symmetric screen needs n >= %lld rows (and SLIC_SCREEN_SYM != 0)",
+                  (long long)SYM_MIN_ROWS_FWD);
+        return SLIC_ERR_UNSUPPORTED;
+    }
+    if (eps <= 0.f) eps = TC_DEFAULT_EPS;
+    cudaStream_t st = as_stream(stream);
+    Scratch idx, dist;
+    SLIC_CUDA_OK(idx.alloc((size_t)n * sizeof(int), st));
+    SLIC_CUDA_OK(dist.alloc((size_t)n * sizeof(float), st));
+    bool overflowed = false;
+    SLIC_PROPAGATE(nn_top1_sym_impl<float>(unit_dev, bf16_dev, n, d, d_pad, eps, idx.as<int>(), dist.as<float>(),
+                                           stats_out_dev, st, part, parts, nullptr, nullptr, nullptr, &overflowed));
+    sym_pack_keys_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(idx.as<int>(), dist.as<float>(), n,
+                                                                     (unsigned long long*)keys_out_dev);
+    SLIC_LAUNCH_OK();
+    // keys[n] = 1, or 0 when this part's candidate log overflowed (records are missing): MIN over the parts tells
+    // every process whether the merged result is complete
+    const unsigned long long flag = overflowed ? 0ull : 1ull;
+    SLIC_CUDA_OK(cudaMemcpyAsync(keys_out_dev + n, &flag, sizeof(flag), cudaMemcpyHostToDevice, st));
+    SLIC_CUDA_OK(cudaStreamSynchronize(st));   // `flag` lives on this frame
+    return SLIC_OK;
+}
+
+int slic_unpack_neighbor_keys(const uint64_t* keys_dev, int64_t n, int32_t* idx_out_dev, float* dist_out_dev,
+                              int32_t* status_out_dev, slic_stream_t stream) {
+    using namespace slic;
+    SLIC_REQUIRE(n > 0 && keys_dev && idx_out_dev && dist_out_dev && status_out_dev, "unpack_neighbor_keys: bad argument");
+    SLIC_PROPAGATE(slic_require_device());
+    cudaStream_t st = as_stream(stream);
+    SLIC_CUDA_OK(cudaMemsetAsync(status_out_dev, 0, sizeof(int), st));
+    sym_unpack_keys_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>((const unsigned long long*)keys_dev, n, idx_out_dev,
+                                                                       dist_out_dev, status_out_dev);
+    SLIC_LAUNCH_OK();
+    return SLIC_OK;
 }
 
 int slic_topk_cosine_tc(const void* q_unit_dev, const uint16_t* q_bf16_dev, int64_t nq, const void* x_unit_dev,

@@ -1,8 +1,12 @@
-"""Multi-GPU level-0 first-neighbour search: query rows sharded across the ranks of one box, every
-rank holding the full embedding matrix; per-row neighbour ids (and distances, which the min_sim
-filter needs) are all-gathered over NCCL / NVLink.  Levels >= 1 (n_1 << N), the components and the
-means are serial work of a few milliseconds and run redundantly on every rank, so all ranks return
-the same partition without a broadcast.
+"""Multi-GPU level-0 first-neighbour search across the ranks of one box, every rank holding the full
+embedding matrix.  Two ways to share the O(N^2 D) stage:
+  * triangle parts (large float32 self-searches, the default): the symmetric screen computes only the tiles on
+    or right of the diagonal; rank r takes every world-th unit of that triangle and the per-row (distance,
+    neighbour) keys are merged by ONE all-reduce (MIN) over NCCL / NVLink - 8 (N + 1) bytes;
+  * row shards (small inputs, retrieval, fallback): rank r searches rows [r * ceil(N / G), ...) against all
+    columns; ids and distances (which the min_sim filter needs) are all-gathered.
+Levels >= 1 (n_1 << N), the components and the means are serial work of a few milliseconds and run
+redundantly on every rank, so all ranks return the same partition without a broadcast.
 
 One process per GPU (torch.distributed, backend nccl on GPUs; gloo works for the CPU tests with the
 stand-in backend).  The reference runs FINCH on rank 0 only while the other ranks wait at a barrier
@@ -21,13 +25,26 @@ def shard_range(n, rank, world):
     return r0, min(r0 + per, n), per
 
 
-def sharded_first_neighbors(be, group=None, timings=None):
-    """Returns a callable mat -> (nn, dist, unit) for FINCH(first_neighbors=...)."""
+def sharded_first_neighbors(be, group=None, timings=None, triangle=True):
+    """Returns a callable mat -> (nn, dist, unit) for FINCH(first_neighbors=...).
+    triangle=True (default): large float32 self-searches are shared as parts of the symmetric screen's triangle and
+    merged by one all-reduce; otherwise (and for small inputs) query rows are sharded and the ids all-gathered."""
 
     def search(mat):
         world = dist.get_world_size(group)
         rank = dist.get_rank(group)
         n = mat.shape[0]
+        if world > 1 and triangle and hasattr(be, "first_neighbors_part") and be.supports_triangle_parts(mat):
+            # The score matrix of a self-search is symmetric: the ranks share the tiles on or right of its diagonal
+            # (half the flops of the row-sharded full square) and every rank ends up with, for EVERY row, the best
+            # neighbour among the pairs it saw.  The exchange step is one all-reduce (MIN) of 8 (N + 1) bytes of
+            # (distance, neighbour) keys; every rank sees the same merged array, hence takes the same branch below.
+            keys, unit = be.first_neighbors_part(mat, rank, world)
+            dist.all_reduce(keys, op=dist.ReduceOp.MIN, group=group)
+            nn, d, complete = be.unpack_neighbor_keys(keys)
+            if complete:
+                return nn, d, unit
+            # (a candidate log overflowed on some rank - degenerate input: repeat on the row-sharded full square)
         r0, r1, per = shard_range(n, rank, world)
         nn_loc, d_loc, unit = be.first_neighbors(mat, row_range=(r0, r1))
         if world == 1:
