@@ -18,6 +18,9 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_error, sizeof(g_error), fmt, ap);
     va_end(ap);
+    // a wait inside a gated screen launch timed out (the kernel trapped): say which one
+    const char* rec = timeout_record_text();
+    if (rec[0]) strncat(g_error, rec, sizeof(g_error) - strlen(g_error) - 1);
 }
 
 int num_sms() {

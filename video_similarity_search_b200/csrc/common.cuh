@@ -9,6 +9,8 @@
 namespace slic {
 
 void set_error(const char* fmt, ...);
+// nn_screen_tc.cu: post-mortem text of a timed-out wait in a gated screen launch ("" when there is none)
+const char* timeout_record_text();
 
 #define SLIC_CUDA_OK(expr)                                                                     \
     do {                                                                                       \
@@ -78,6 +80,10 @@ struct GateSpec {
     int64_t chunk_rows;   // multiple of 256
 };
 typedef int (*AfterScreenFn)(void* ctx);
+// can CTAs of the given shape co-reside with the persistent screen kernel of a gated self-search (see nn_screen_tc.cu)
+bool screen_can_overlap_upload(int64_t n, int d_pad, int guest_threads, int guest_regs);
+// prep.cu: CTA shape of the float32 normalise kernel (the guest of a gated launch)
+int normalize_kernel_shape(int* threads, int* regs);
 // true: a self-search of n rows runs the symmetric screen (upper-triangular tiles, row + column filters)
 bool screen_self_search_is_symmetric(int64_t n);
 int nn_top1_f32_gated(const float* q_unit, const uint16_t* q_bf16, int64_t nq, const float* x_unit,

@@ -77,6 +77,15 @@ __global__ void stack_columns_kernel(ColumnPtrs cols, int levels, int64_t n, int
     out[t] = cols.col[l][i];
 }
 
+// opens upload gate `g` (own kernel, one warp: a cudaMemsetAsync may be a driver kernel of unknown shape, and whatever
+// runs on the copy stream must fit next to the persistent screen kernel)
+__global__ void open_gate_kernel(int* gate) {
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicExch(gate, 1);
+    }
+}
+
 __global__ void convert_rank_kernel(const int64_t* __restrict__ in, int64_t n, int* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (int)in[i];
@@ -215,7 +224,10 @@ static int run_upload(void* ctx) {
                                      cudaMemcpyHostToDevice, up->copy_stream));
         SLIC_PROPAGATE(slic_normalize_rows(up->data + r0 * up->d, rows, up->d, SLIC_F32, up->unit + r0 * up->d, nullptr,
                                            up->ub + r0 * up->d_pad, up->d_pad, up->copy_stream));
-        if (up->gates) SLIC_CUDA_OK(cudaMemsetAsync(up->gates + c, 1, sizeof(int), up->copy_stream));
+        if (up->gates) {
+            open_gate_kernel<<<1, 32, 0, up->copy_stream>>>(up->gates + c);
+            SLIC_LAUNCH_OK();
+        }
     }
     if (g_host_trace) SLIC_CUDA_OK(cudaEventRecord(g_up1, up->copy_stream));
     SLIC_CUDA_OK(cudaEventRecord(up->done, up->copy_stream));
@@ -273,14 +285,22 @@ static int finch_host_impl(const float* x_host, int64_t n, int d, const int64_t*
         Upload up = {x_host, n, d, dp, data.as<float>(), unit.as<float>(), ub.as<uint16_t>(), nullptr, 1, n, hs.copy, st,
                      hs.done};
         if (g_host_trace) SLIC_CUDA_OK(cudaEventRecord(g_t0, st));
-        if (screen && n >= GATED_MIN_ROWS && gated_chunks() > 1) {
+        int guest_threads = 0, guest_regs = 0;
+        SLIC_PROPAGATE(normalize_kernel_shape(&guest_threads, &guest_regs));
+        if (screen && n >= GATED_MIN_ROWS && gated_chunks() > 1 &&
+            screen_can_overlap_upload(n, dp, guest_threads, guest_regs)) {
             // pipelined: screen first, upload behind it
             up.num_chunks = gated_chunks();
             up.chunk_rows = ceil_div(ceil_div(n, up.num_chunks), 256) * 256;
             up.num_chunks = (int)ceil_div(n, up.chunk_rows);
-            SLIC_CUDA_OK(gates.alloc(up.num_chunks * sizeof(int), st));
-            SLIC_CUDA_OK(cudaMemsetAsync(gates.ptr, 0, up.num_chunks * sizeof(int), st));
+            SLIC_CUDA_OK(gates.alloc((up.num_chunks + 1) * sizeof(int), st));
+            SLIC_CUDA_OK(cudaMemsetAsync(gates.ptr, 0, (up.num_chunks + 1) * sizeof(int), st));
             up.gates = gates.as<int>();
+            // Every kernel the copy stream will run must be LOADED before the screen kernel starts to wait for it: with
+            // lazy module loading the first launch of a function may synchronise the context - behind the very kernel
+            // that is waiting.  normalize_kernel_shape() above loaded the normalise kernel; open a spare gate here.
+            open_gate_kernel<<<1, 32, 0, st>>>(up.gates + up.num_chunks);
+            SLIC_LAUNCH_OK();
             // the copy stream may touch the buffers (allocated in stream order on `st`) and the zeroed gates only
             // after this point
             SLIC_CUDA_OK(cudaEventRecord(hs.ready, st));

@@ -183,6 +183,24 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// Post-mortem of a timed-out wait: a trap kills the context, so the record goes to MAPPED HOST memory (readable after
+// the failure): {site, block, thread, a, b}.  site 1 = mbarrier (a = smem address, b = parity), 2 = upload gate
+// (a = gate address low bits), 3 = pre-pass counter (a = value seen, b = target).  First writer wins.
+__device__ int* g_timeout_record = nullptr;
+__device__ int g_timeout_lock = 0;
+__device__ __noinline__ void record_timeout(int site, int a, int b) {
+    int* r = g_timeout_record;
+    if (r && atomicCAS(&g_timeout_lock, 0, 1) == 0) {
+        volatile int* v = r;
+        v[1] = (int)blockIdx.x;
+        v[2] = (int)threadIdx.x;
+        v[3] = a;
+        v[4] = b;
+        v[0] = site;
+        __threadfence_system();
+    }
+}
+
 // Bounded wait: a protocol bug must not hang the GPU - after ~4 s the kernel flags the error and traps.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* error_flag) {
     uint32_t done = 0;
@@ -202,6 +220,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
             if (t0 == 0) t0 = now;
             else if (now - t0 > 8000000000ll) {
                 if (error_flag) atomicExch(error_flag, 1);
+                record_timeout(1, (int)bar, (int)parity);
                 __trap();
             }
         }
@@ -234,6 +253,7 @@ __device__ __forceinline__ void gate_wait(const int* gate, int* error_flag) {
             if (t0 == 0) t0 = now;
             else if (now - t0 > 20000000000ll) {   // ~10 s: the upload died
                 if (error_flag) atomicExch(error_flag, 1);
+                record_timeout(2, (int)(reinterpret_cast<uintptr_t>(gate) & 0xffff), v);
                 __trap();
             }
         }
@@ -253,6 +273,7 @@ __device__ __forceinline__ void counter_wait(const int* counter, int target, int
             if (t0 == 0) t0 = now;
             else if (now - t0 > 20000000000ll) {
                 if (error_flag) atomicExch(error_flag, 1);
+                record_timeout(3, v, target);
                 __trap();
             }
         }
@@ -696,8 +717,14 @@ __device__ __forceinline__ void epi_chunk(EpiCtx<TOPK>& cx, uint32_t (&v)[32], i
 }
 
 // ---- the kernel ------------------------------------------------------------------------------
+// Register cap of the top-1 kernels.  A gated launch runs while another stream normalises the arriving chunks: those
+// CTAs must become resident NEXT TO this persistent kernel or the launch waits for itself.  Registers are allocated
+// per SM sub-partition (16 384 each); the 10 warps of a screen CTA put 3 on two of the four, so
+// 3 * 32 * 152 = 14 592 leaves 1 792 registers there - one warp of a 128-thread guest CTA (<= 56 registers/thread).
+// (slic_screen_can_overlap_upload checks the built kernels against this arithmetic before a gated launch.)
+constexpr int TC_TOP1_MAX_REGS = 152;
 template <bool TOPK, int NCTA, bool ARES, bool SYM = false>
-__global__ void __launch_bounds__(TC_THREADS, 1) nn_screen_kernel(const __grid_constant__ CUtensorMap tmap_q,
+__global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(const __grid_constant__ CUtensorMap tmap_q,
                                                                   const __grid_constant__ CUtensorMap tmap_x,
                                                                   const ScreenParams p) {
     typedef TcCfg<NCTA, ARES, TOPK> Cfg;
@@ -1459,6 +1486,44 @@ static int topk_cap(int k, int64_t cols_per_split) {
     return cap;
 }
 
+typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const ScreenParams);
+static void pick_screen_kernel(bool sym, bool ares, int ncta, bool is_topk, KernelFn* fn, size_t* smem_bytes) {
+    if (sym) {
+        *fn = ares ? (KernelFn)nn_screen_kernel<false, 2, true, true> : (KernelFn)nn_screen_kernel<false, 2, false, true>;
+        *smem_bytes = ares ? TcCfg<2, true, false>::SYM_SMEM_BYTES : TcCfg<2, false, false>::SYM_SMEM_BYTES;
+    } else if (ares) {
+        *fn = is_topk ? (KernelFn)nn_screen_kernel<true, 2, true> : (KernelFn)nn_screen_kernel<false, 2, true>;
+        *smem_bytes = is_topk ? TcCfg<2, true, true>::SMEM_BYTES : TcCfg<2, true, false>::SMEM_BYTES;
+    } else if (ncta == 2) {
+        *fn = is_topk ? (KernelFn)nn_screen_kernel<true, 2, false> : (KernelFn)nn_screen_kernel<false, 2, false>;
+        *smem_bytes = is_topk ? TcCfg<2, false, true>::SMEM_BYTES : TcCfg<2, false, false>::SMEM_BYTES;
+    } else {
+        *fn = is_topk ? (KernelFn)nn_screen_kernel<true, 1, false> : (KernelFn)nn_screen_kernel<false, 1, false>;
+        *smem_bytes = is_topk ? TcCfg<1, false, true>::SMEM_BYTES : TcCfg<1, false, false>::SMEM_BYTES;
+    }
+}
+
+static int* g_timeout_record_host = nullptr;   // mapped pinned memory, [8]
+static int arm_timeout_record() {
+    if (!g_timeout_record_host) {
+        SLIC_CUDA_OK(cudaHostAlloc(&g_timeout_record_host, 8 * sizeof(int), cudaHostAllocMapped));
+        int* dev_view = nullptr;
+        SLIC_CUDA_OK(cudaHostGetDevicePointer(&dev_view, g_timeout_record_host, 0));
+        SLIC_CUDA_OK(cudaMemcpyToSymbol(g_timeout_record, &dev_view, sizeof(dev_view)));
+    }
+    for (int i = 0; i < 8; ++i) g_timeout_record_host[i] = 0;
+    return SLIC_OK;
+}
+// appended to the error text of a failed screen launch
+const char* timeout_record_text() {
+    static thread_local char buf[160];
+    const int* r = g_timeout_record_host;
+    if (!r || r[0] == 0) return "";
+    snprintf(buf, sizeof(buf), " [timed-out wait: site %d (1 mbarrier, 2 upload gate, 3 pre-pass counter) block %d thread %d a=%d b=%d]",
+             r[0], r[1], r[2], r[3], r[4]);
+    return buf;
+}
+
 static int launch_screen(const uint16_t* q_bf16, int64_t nq, const uint16_t* x_bf16, int64_t n, int d_pad,
                          int64_t self_offset, float eps, int cap, const ScreenPlan& pl, int* cand_idx, float* cand_score,
                          int* cand_cnt, int* cand_flags, float* dump, int* error_flag, cudaStream_t st, int topk = 0,
@@ -1466,6 +1531,7 @@ static int launch_screen(const uint16_t* q_bf16, int64_t nq, const uint16_t* x_b
                          unsigned int* best_enc = nullptr, int64_t exec_tiles = 0, int* log_q = nullptr,
                          int log_region = 0, int* sync_counter = nullptr, const int* sync_targets = nullptr) {
     const int ncta = screen_ncta();
+    if (gates) SLIC_PROPAGATE(arm_timeout_record());
     CUtensorMap tq, tx;
     SLIC_PROPAGATE(make_tmap(&tq, q_bf16, nq, d_pad, TC_BM));
     SLIC_PROPAGATE(make_tmap(&tx, x_bf16, n, d_pad, TC_BN / ncta));
@@ -1496,28 +1562,15 @@ static int launch_screen(const uint16_t* q_bf16, int64_t nq, const uint16_t* x_b
     p.sync_counter = sync_counter;
     p.sync_targets = sync_targets;
     const bool sym = best_enc != nullptr;
-    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const ScreenParams);
     const bool is_topk = topk > 0;
     const bool ares = ncta == 2 && p.num_k_slabs <= TC_ARES_MAX_SLABS && screen_ares_allowed();
+    if (sym && (ncta != 2 || is_topk || !unit_table)) {
+        set_error("symmetric screen: needs the CTA-pair top-1 kernel and a unit list");
+        return SLIC_ERR_UNSUPPORTED;
+    }
     KernelFn fn;
     size_t smem_bytes;
-    if (sym) {
-        if (ncta != 2 || is_topk || !unit_table) {
-            set_error("symmetric screen: needs the CTA-pair top-1 kernel and a unit list");
-            return SLIC_ERR_UNSUPPORTED;
-        }
-        fn = ares ? (KernelFn)nn_screen_kernel<false, 2, true, true> : (KernelFn)nn_screen_kernel<false, 2, false, true>;
-        smem_bytes = ares ? TcCfg<2, true, false>::SYM_SMEM_BYTES : TcCfg<2, false, false>::SYM_SMEM_BYTES;
-    } else if (ares) {
-        fn = is_topk ? (KernelFn)nn_screen_kernel<true, 2, true> : (KernelFn)nn_screen_kernel<false, 2, true>;
-        smem_bytes = is_topk ? TcCfg<2, true, true>::SMEM_BYTES : TcCfg<2, true, false>::SMEM_BYTES;
-    } else if (ncta == 2) {
-        fn = is_topk ? (KernelFn)nn_screen_kernel<true, 2, false> : (KernelFn)nn_screen_kernel<false, 2, false>;
-        smem_bytes = is_topk ? TcCfg<2, false, true>::SMEM_BYTES : TcCfg<2, false, false>::SMEM_BYTES;
-    } else {
-        fn = is_topk ? (KernelFn)nn_screen_kernel<true, 1, false> : (KernelFn)nn_screen_kernel<false, 1, false>;
-        smem_bytes = is_topk ? TcCfg<1, false, true>::SMEM_BYTES : TcCfg<1, false, false>::SMEM_BYTES;
-    }
+    pick_screen_kernel(sym, ares, ncta, is_topk, &fn, &smem_bytes);
     static bool attr_done[64][16] = {{false}};
     int dev = 0;
     SLIC_CUDA_OK(cudaGetDevice(&dev));
@@ -1941,6 +1994,7 @@ static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d,
                                  flag.as<int>(), nullptr, stats.as<int>() + 4, st, 0, nullptr, table_dev.as<int4>(),
                                  gate ? gate->gates : nullptr, best.as<unsigned int>(), exec_tiles, lq.as<int>(),
                                  (int)region, sync.as<int>(), sync.as<int>() + 1));
+    if (g_profile && parts > 1) g_last_flop /= (double)parts;   // this process's share of the algorithmic 2 n^2 d
     if (after) SLIC_PROPAGATE(after(after_ctx));
     sym_rerank_dist_kernel<T><<<(unsigned)regions, 256, 0, st>>>(unit, d, eps, (int)region, lq.as<int>(), lnb.as<int>(),
                                                                  ls.as<float>(), lcnt.as<int>(), best.as<unsigned int>(),
@@ -2030,6 +2084,33 @@ __global__ void sym_unpack_keys_kernel(const unsigned long long* __restrict__ ke
     idx[i] = (int)(unsigned int)(k & 0xffffffffull);
     dist[i] = __uint_as_float((unsigned int)(k >> 32));
     if (k == SYM_KEY_NONE) atomicAdd(unsettled, 1);
+}
+
+// Can CTAs of `guest_threads` threads x `guest_regs` registers (no shared memory of their own) become resident next to
+// the persistent top-1 screen kernel that a gated self-search of n rows x d_pad would launch?  Resources per SM:
+// 228 KB of shared memory with 1 KB reserved per resident CTA; 4 sub-partitions of 16 384 registers, warps dealt
+// round-robin, registers allocated per warp in units of 8 per thread.  false -> the caller uploads first, then searches.
+bool screen_can_overlap_upload(int64_t n, int d_pad, int guest_threads, int guest_regs) {
+    const int ncta = screen_ncta();
+    const bool sym = screen_self_search_is_symmetric(n);
+    const bool ares = ncta == 2 && d_pad / TC_BK <= TC_ARES_MAX_SLABS && screen_ares_allowed();
+    KernelFn fn;
+    size_t smem_bytes;
+    pick_screen_kernel(sym, ares, ncta, false, &fn, &smem_bytes);
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, fn) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    const int host_regs = (fa.numRegs + 7) / 8 * 8, gr = (guest_regs + 7) / 8 * 8;
+    const int host_warps = (TC_THREADS / 32 + 3) / 4, guest_warps = (guest_threads / 32 + 3) / 4;   // on the fullest sub-partition
+    const bool regs_ok = 32 * (host_warps * host_regs + guest_warps * gr) <= 16384;
+    const bool smem_ok = smem_bytes + 2 * 1024 <= 233472;
+    const bool threads_ok = TC_THREADS + guest_threads <= 2048;
+    if (getenv("SLIC_SYM_DEBUG"))
+        fprintf(stderr, "[slic] overlap check: screen %d regs, %zu B smem; guest %d threads x %d regs -> regs %d smem %d\n",
+                fa.numRegs, smem_bytes, guest_threads, guest_regs, (int)regs_ok, (int)smem_ok);
+    return regs_ok && smem_ok && threads_ok;
 }
 
 int nn_top1_f32_gated(const float* q_unit, const uint16_t* q_bf16, int64_t nq, const float* x_unit,

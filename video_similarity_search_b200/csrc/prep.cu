@@ -9,8 +9,11 @@
 
 namespace slic {
 
+// 128-thread CTAs (4 rows): one warp per SM sub-partition, so that these CTAs fit next to the persistent screen kernel
+// while it waits for the chunk they are normalising (gated launches, finch_driver.cu)
+constexpr int NORM_THREADS = 128;
 template <typename T>
-__global__ void __launch_bounds__(256) normalize_rows_kernel(const T* __restrict__ x, int64_t n, int d,
+__global__ void __launch_bounds__(NORM_THREADS) normalize_rows_kernel(const T* __restrict__ x, int64_t n, int d,
                                                              T* __restrict__ unit, T* __restrict__ norms,
                                                              __nv_bfloat16* __restrict__ ub, int d_pad) {
     const int lane = threadIdx.x & 31;
@@ -37,6 +40,14 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const T* __restrict
     }
 }
 
+int normalize_kernel_shape(int* threads, int* regs) {
+    cudaFuncAttributes fa;
+    SLIC_CUDA_OK(cudaFuncGetAttributes(&fa, normalize_rows_kernel<float>));
+    *threads = NORM_THREADS;
+    *regs = fa.numRegs;
+    return SLIC_OK;
+}
+
 }  // namespace slic
 
 extern "C" int slic_normalize_rows(const void* x_dev, int64_t n, int32_t d, int32_t dtype, void* unit_dev,
@@ -46,13 +57,13 @@ extern "C" int slic_normalize_rows(const void* x_dev, int64_t n, int32_t d, int3
     if (unit_bf16_dev) SLIC_REQUIRE(d_pad >= d && d_pad % 64 == 0, "normalize_rows: d_pad must be a multiple of 64 >= d");
     if (n == 0) return SLIC_OK;
     const int dp = unit_bf16_dev ? d_pad : d;
-    const unsigned blocks = (unsigned)slic::ceil_div(n, 8);
+    const unsigned blocks = (unsigned)slic::ceil_div(n, slic::NORM_THREADS / 32);
     cudaStream_t st = slic::as_stream(stream);
     if (dtype == SLIC_F32)
-        slic::normalize_rows_kernel<float><<<blocks, 256, 0, st>>>((const float*)x_dev, n, d, (float*)unit_dev,
+        slic::normalize_rows_kernel<float><<<blocks, slic::NORM_THREADS, 0, st>>>((const float*)x_dev, n, d, (float*)unit_dev,
                                                                    (float*)norms_dev, (__nv_bfloat16*)unit_bf16_dev, dp);
     else
-        slic::normalize_rows_kernel<double><<<blocks, 256, 0, st>>>((const double*)x_dev, n, d, (double*)unit_dev,
+        slic::normalize_rows_kernel<double><<<blocks, slic::NORM_THREADS, 0, st>>>((const double*)x_dev, n, d, (double*)unit_dev,
                                                                     (double*)norms_dev, (__nv_bfloat16*)unit_bf16_dev, dp);
     SLIC_LAUNCH_OK();
     return SLIC_OK;
