@@ -52,9 +52,9 @@ def parse_args():
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed
-# `ncu --set full` capture (profiles/r1_screen_kernel_ncu_full.txt); keyed by (workload, ranks).  Not measured live:
+# `ncu --set full` capture (profiles/r1_sym_screen_kernel_ncu_full.txt); keyed by (workload, ranks).  Not measured live:
 # a number taken under the profiler's replay is evidence of traffic, never of time.
-NCU_TRAFFIC_BYTES = {("C3", 1): 4.493117e9 + 159.316224e6}
+NCU_TRAFFIC_BYTES = {("C3", 1): 2.101503e9 + 102.8736e6}
 
 
 def load_peaks():
@@ -334,6 +334,15 @@ def run_b200(args):
         step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)
 
+    sharded_equal = None
+    if world > 1:
+        # parity of the exchange step, outside the timed region: the merged multi-GPU first neighbours must equal the
+        # single-GPU search of the same matrix on this rank, bit for bit (indices and float32 distances)
+        nn_s, d_s, _ = search(x_dev)
+        nn_1, d_1, _ = be.first_neighbors(x_dev)
+        ok = torch.tensor([int(torch.equal(nn_s, nn_1) and torch.equal(d_s, d_1))], device=be.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        sharded_equal = bool(ok.item())
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -350,14 +359,18 @@ def run_b200(args):
         "config": {"workload": "FINCH full hierarchy, N=%d x D=%d Gaussian mixture (K=%d, seed %d), cosine" % (n, d, k, seed),
                    "l2": "inputs exceed L2 (%.0f MB fp32 + %.0f MB bf16 per step)" % (n * d * 4 / 1e6, n * d_pad * 2 / 1e6),
                    "partitions": [int(v) for v in num_clust],
-                   "parallelism": "level-0 NN rows sharded over %d GPU(s), ids all-gathered (NCCL)" % world},
+                   "parallelism": ("1 GPU" if world == 1 else
+                                   "level-0 NN: the %d ranks share the tiles of the symmetric screen's triangle, (distance, "
+                                   "neighbour) keys merged by one NCCL all-reduce MIN of 8(N+1) bytes; levels >= 1 replicated"
+                                   % world)},
         "finch_seconds": ms_step * 1e-3,
         "nn_stage": {"ms": ms_nn, "queries_per_s": n / (ms_nn * 1e-3)},
         "e2e": {"value": n / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(n * d * 4), "d2h_bytes_per_step": int(c.size * 4)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "nn_screen_kernel (level 0, per rank: %d x %d x %d)" % ((n + world - 1) // world, n, d_pad),
+        "roofline": {"kernel": "nn_screen_kernel (level 0, %d x %d x %d%s)" % (n, n, d_pad, "" if world == 1 else
+                                                                               ", this rank's 1/%d of the tiles" % world),
                      "bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                      "frac": achieved_tf / peaks["bf16_tflops"], "peak_source": peaks["source"] + " burst bf16",
                      "frac_of_sustained": (achieved_tf / peaks["bf16_tflops_sustained"]) if peaks.get("bf16_tflops_sustained") else None,
@@ -395,6 +408,8 @@ def run_b200(args):
             "finch_seconds_est": est}
         line["parity"] = {"first_neighbors_equal_on_sample": parity_nn, "tie_rows_in_sample": int((~clear).sum()),
                           "partition_equals_oracle": parity_partition}
+    if sharded_equal is not None:
+        line["parity"] = {"sharded_first_neighbors_equal_single_gpu_on_every_rank": sharded_equal}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
