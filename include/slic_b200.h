@@ -229,6 +229,25 @@ int slic_label_mask_u8(const int64_t* a_dev, int64_t na, const int64_t* b_dev, i
 int slic_label_mask_bits(const int64_t* a_dev, int64_t na, const int64_t* b_dev, int64_t nb,
                          int32_t negate, uint32_t* out_dev, slic_stream_t stream);
 
+/* online_train.py:648-652: cluster assignments back in the unshuffled order of the dataset,
+ *   out[positions[i]] = values[i]  for i = 0..n-1 IN ORDER (a dataset index the sampler repeated keeps the LAST value),
+ * slots nobody wrote = fill (the reference leaves None there).  out_of_range_dev[0] = positions outside [0, n_out). */
+int slic_scatter_last_wins(const int32_t* values_dev, const int64_t* positions_dev, int64_t n,
+                           int64_t n_out, int32_t fill, int32_t* out_dev, int32_t* out_of_range_dev,
+                           slic_stream_t stream);
+
+/* ---- cluster-quality scores ----------------------------------------- */
+/* online_train.py:633-642 calls sklearn's normalized_mutual_info_score and adjusted_mutual_info_score on the true
+ * labels and the FINCH labels.  This entry computes their ingredients on the device, following sklearn's arithmetic
+ * (metrics/cluster/_supervised.py mutual_info_score + entropy, _expected_mutual_info_fast.pyx):
+ *   out_dev[0] mutual information (nats)   [1] entropy of labels_true   [2] entropy of labels_pred
+ *   out_dev[3] expected mutual information (0 unless want_emi)   [4], [5] number of non-empty classes / clusters
+ * Labels must lie in [0, num_true) / [0, num_pred) (empty classes are allowed); num_true * num_pred <= 2^28 cells
+ * (SLIC_ERR_UNSUPPORTED above).  The final ratios (and sklearn's special cases) are host arithmetic on these six numbers. */
+int slic_cluster_metrics(const int32_t* labels_true_dev, const int32_t* labels_pred_dev, int64_t n,
+                         int32_t num_true, int32_t num_pred, int32_t want_emi, double* out_dev,
+                         slic_stream_t stream);
+
 /* datasets/triplets_dataset.py:99-104 (label_to_indices) as CSR: order[] lists the rows of label
  * 0, then label 1, ... (ascending row index inside a label, what np.where yields);
  * offsets[c]..offsets[c+1] delimit label c.  Labels must lie in [0, num_labels). */

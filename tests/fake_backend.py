@@ -106,6 +106,35 @@ class FakeBackend:
         complete = bool(k[n] == 1 and not (k[:n] == self.KEY_NONE).any())
         return torch.from_numpy(nn), torch.from_numpy(d.copy()), complete
 
+    # label hand-over / cluster-quality scores (slic_scatter_last_wins, slic_cluster_metrics)
+    def scatter_last_wins(self, values, positions, n_out, fill=-1):
+        v, p = _np(values), _np(positions)
+        out = np.full(n_out, fill, dtype=np.int32)
+        ok = (p >= 0) & (p < n_out)
+        for i in np.flatnonzero(ok):
+            out[p[i]] = v[i]
+        return torch.from_numpy(out), int((~ok).sum())
+
+    def cluster_metrics(self, labels_true, labels_pred, num_true, num_pred, want_emi=True):
+        from sklearn.metrics.cluster._expected_mutual_info_fast import expected_mutual_information
+        import scipy.sparse as sp
+        lt, lp = _np(labels_true).astype(np.int64), _np(labels_pred).astype(np.int64)
+        n = len(lt)
+        cont = np.zeros((num_true, num_pred), dtype=np.int64)
+        np.add.at(cont, (lt, lp), 1)
+        a, b = cont.sum(1), cont.sum(0)
+
+        def ent(c):
+            c = c[c > 0].astype(np.float64)
+            return 0.0 if c.size <= 1 else float(-np.sum((c / n) * (np.log(c) - np.log(n))))
+        i, j = np.nonzero(cont)
+        nij = cont[i, j].astype(np.float64)
+        t = (nij / n) * (np.log(nij) - np.log(n)) + (nij / n) * (-np.log((a[i] * b[j]).astype(np.float64)) + 2 * np.log(n))
+        t[np.abs(t) < np.finfo(np.float64).eps] = 0.0
+        mi = max(float(t.sum()), 0.0)
+        emi = float(expected_mutual_information(sp.csr_matrix(cont), n)) if want_emi else 0.0
+        return [mi, ent(a), ent(b), emi, float((a > 0).sum()), float((b > 0).sum())]
+
     def distance_matrix(self, q, x, metric="cosine", same=False):
         dt = _np(x).dtype
         if metric == "cosine":

@@ -312,6 +312,21 @@ class CudaBackend:
         _lib.call("slic_label_mask_bits", _p(a), na, _p(b), nb, int(negate), _p(out), self._stream())
         return out
 
+    def scatter_last_wins(self, values, positions, n_out, fill=-1):
+        """out[positions[i]] = values[i] in order of i (slic_scatter_last_wins).  -> (out int32 [n_out], out_of_range int)."""
+        out = torch.empty(n_out, dtype=torch.int32, device=values.device)
+        bad = torch.empty(1, dtype=torch.int32, device=values.device)
+        _lib.call("slic_scatter_last_wins", _p(values), _p(positions), values.shape[0], n_out, int(fill), _p(out), _p(bad),
+                  self._stream())
+        return out, int(bad.item())
+
+    def cluster_metrics(self, labels_true, labels_pred, num_true, num_pred, want_emi=True):
+        """-> [mi, h_true, h_pred, emi, classes, clusters] as Python floats (slic_cluster_metrics; one read-back)."""
+        out = torch.empty(6, dtype=torch.float64, device=labels_true.device)
+        _lib.call("slic_cluster_metrics", _p(labels_true), _p(labels_pred), labels_true.shape[0], int(num_true),
+                  int(num_pred), int(bool(want_emi)), _p(out), self._stream())
+        return out.tolist()
+
     def group_by_label(self, labels, num_labels):
         n = labels.shape[0]
         order = torch.empty(n, dtype=torch.int32, device=labels.device)

@@ -109,9 +109,53 @@ __global__ void __launch_bounds__(256) hit_at_k_kernel(const int* __restrict__ t
     if (lane < num_ks && first < ks[lane]) atomicAdd(&hits[lane], 1);
 }
 
+// online_train.py:648-652 - `out[idxs[i]] = labels[i]` for i = 0..n-1 in order: where the distributed sampler padded
+// the epoch with repeated dataset indices the LAST occurrence wins.  Pass 1 elects, per output slot, the largest source
+// position (integer atomic max: exact, order-free); pass 2 copies that source's value.
+__global__ void scatter_elect_kernel(const int64_t* __restrict__ pos, int64_t n, int64_t n_out, int* __restrict__ winner,
+                                     int* __restrict__ bad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t p = pos[i];
+    if (p < 0 || p >= n_out) {
+        atomicAdd(bad, 1);
+        return;
+    }
+    atomicMax(winner + p, (int)i);
+}
+__global__ void scatter_copy_kernel(const int* __restrict__ values, const int* __restrict__ winner, int64_t n_out, int fill,
+                                    int* __restrict__ out) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_out) return;
+    const int w = winner[p];
+    out[p] = w >= 0 ? values[w] : fill;
+}
+
 }  // namespace slic
 
 extern "C" {
+
+int slic_scatter_last_wins(const int32_t* values_dev, const int64_t* positions_dev, int64_t n, int64_t n_out,
+                           int32_t fill, int32_t* out_dev, int32_t* out_of_range_dev, slic_stream_t stream) {
+    using namespace slic;
+    SLIC_REQUIRE(n >= 0 && n < ((int64_t)1 << 31) && n_out >= 0, "scatter_last_wins: bad shape");
+    SLIC_REQUIRE((n == 0 || (values_dev && positions_dev)) && (n_out == 0 || out_dev) && out_of_range_dev,
+                 "scatter_last_wins: null pointer");
+    cudaStream_t st = as_stream(stream);
+    SLIC_CUDA_OK(cudaMemsetAsync(out_of_range_dev, 0, sizeof(int), st));
+    if (n_out == 0) return SLIC_OK;
+    Scratch winner;
+    SLIC_CUDA_OK(winner.alloc((size_t)n_out * sizeof(int), st));
+    SLIC_CUDA_OK(cudaMemsetAsync(winner.ptr, 0xff, (size_t)n_out * sizeof(int), st));   // -1: nobody wrote this slot
+    if (n > 0) {
+        scatter_elect_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(positions_dev, n, n_out, winner.as<int>(),
+                                                                         out_of_range_dev);
+        SLIC_LAUNCH_OK();
+    }
+    scatter_copy_kernel<<<(unsigned)ceil_div(n_out, 256), 256, 0, st>>>(values_dev, winner.as<int>(), n_out, fill, out_dev);
+    SLIC_LAUNCH_OK();
+    return SLIC_OK;
+}
 
 int slic_label_mask_u8(const int64_t* a_dev, int64_t na, const int64_t* b_dev, int64_t nb, int32_t prepend_ones,
                        int32_t negate, uint8_t* out_dev, slic_stream_t stream) {
