@@ -83,6 +83,12 @@ int slic_normalize_rows(const void* x_dev, int64_t n, int32_t d, int32_t dtype,
                         void* unit_dev, void* norms_dev,
                         uint16_t* unit_bf16_dev, int32_t d_pad, slic_stream_t stream);
 
+/* coclr_classify.py:788-789: out = x - x.mean(dim=0, keepdim=True) for a float32 [n, d] matrix.
+ * Column sums in float64 (deterministic), mean rounded to float32 before the subtraction as torch holds it.
+ * out_dev may alias x_dev; means_out_dev [d] is optional. */
+int slic_center_columns(const float* x_dev, int64_t n, int32_t d, float* out_dev, float* means_out_dev,
+                        slic_stream_t stream);
+
 /* ---- K1 exact: brute-force first neighbour in the reference dtype ------------------------ */
 /* clustering/finch.py:27-29 (pairwise_distances + fill_diagonal + argmin) without the n x n
  * matrix: for query row r (database row r + self_offset when self_offset >= 0, which is then

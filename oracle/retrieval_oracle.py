@@ -67,3 +67,37 @@ def topk_retrieval_counts(x_train, y_train, x_test, y_test, ks=(1, 5, 10, 20, 50
 def boundary_gaps(d_sorted_vals, ks):
     """gap between the k-th and (k+1)-th smallest distance per row, for the tie-margin filter."""
     return {k: d_sorted_vals[:, k] - d_sorted_vals[:, k - 1] for k in ks}
+
+
+def coclr_nn_accuracy(test_feature, test_label, train_feature, train_label, ks=(1, 5, 10, 20, 50)):
+    """coclr_classify.py:784-810 restated with the same torch (CPU) calls: centring, F.normalize, matmul, torch.topk per
+    k, kNN accuracy.  Returns (accs, sim) - sim for tie-margin bookkeeping in the tests."""
+    import torch
+    import torch.nn.functional as F
+    test_feature = torch.as_tensor(test_feature, dtype=torch.float32)
+    train_feature = torch.as_tensor(train_feature, dtype=torch.float32)
+    test_label, train_label = torch.as_tensor(test_label), torch.as_tensor(train_label)
+    test_feature = test_feature - test_feature.mean(dim=0, keepdim=True)
+    train_feature = train_feature - train_feature.mean(dim=0, keepdim=True)
+    test_feature = F.normalize(test_feature, p=2, dim=1)
+    train_feature = F.normalize(train_feature, p=2, dim=1)
+    sim = test_feature.matmul(train_feature.t())
+    accs = []
+    for k in ks:
+        _, topkidx = torch.topk(sim, k, dim=1)
+        accs.append(torch.any(train_label[topkidx] == test_label.unsqueeze(1), dim=1).float().mean().item())
+    return accs, sim.numpy()
+
+
+def pdist_v2(vector1, vector2, eps, dist_metric):
+    """loss/triplet_loss.py:438-447, same torch calls."""
+    import torch
+    import torch.nn.functional as F
+    vector1, vector2 = torch.as_tensor(vector1), torch.as_tensor(vector2)
+    rows = []
+    for i in range(len(vector1)):
+        if dist_metric == 'euclidean':
+            rows.append(F.pairwise_distance(vector1[i], vector2, eps=eps).unsqueeze(0))
+        else:
+            rows.append(1 - F.cosine_similarity(vector1[i].unsqueeze(0), vector2, dim=1).unsqueeze(0))
+    return torch.cat(rows, dim=0).numpy()

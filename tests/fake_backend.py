@@ -40,6 +40,10 @@ class FakeBackend:
         unit = torch.from_numpy(a / nrm[:, None])
         return unit, (unit.to(torch.bfloat16) if want_bf16 else None)
 
+    def center_columns(self, x):
+        a = _np(x)
+        return torch.from_numpy(a - a.astype(np.float64).mean(0).astype(np.float32)[None, :])
+
     def _sims(self, q, x):
         return _np(q).astype(np.float64) @ _np(x).astype(np.float64).T
 

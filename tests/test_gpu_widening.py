@@ -82,3 +82,40 @@ def test_device_resident_handoff_feeds_finch(be):
     assert np.array_equal(got, co[:, 0])
     full = cluster_io.unshuffled_assignments(got, idxs, 3000, backend=be)
     assert np.array_equal(full, co[:, 0])
+
+
+@pytest.mark.parametrize("n_train,n_test,d", [(3000, 500, 128), (9537, 3783, 512)])
+def test_coclr_retrieval_matches_torch_restatement(be, n_train, n_test, d):
+    """coclr_classify.py:784-810: kNN accuracies at k = 1, 5, 10, 20, 50 equal the torch restatement's; the top-50 SETS
+    agree on every row whose 50th / 51st similarity gap exceeds 1e-6 (float32 summation order decides closer ties)."""
+    from oracle import retrieval_oracle as ro
+    from tests.test_widening_host import _hard_retrieval_case
+    from video_similarity_search_b200 import coclr_retrieval as cr
+    tr, ytr, te, yte = _hard_retrieval_case(n_train, n_test, d, 40, 1)
+    accs = cr.nn_retrieval_accuracy(te, yte, tr, ytr, backend=be)
+    want, sim = ro.coclr_nn_accuracy(te, yte, tr, ytr)
+    assert 0.05 < want[0] < 0.9
+    assert accs == want
+    idx, s = cr.retrieval_topk(te, tr, 50, backend=be)
+    idx, s = idx.cpu().numpy(), s.cpu().numpy()
+    order = np.argsort(-sim, axis=1)[:, :51]
+    top = np.take_along_axis(sim, order, 1)
+    clear = (top[:, 49] - top[:, 50]) > 1e-6
+    assert clear.mean() > 0.95
+    assert all(set(idx[i]) == set(order[i, :50]) for i in np.flatnonzero(clear))
+    np.testing.assert_allclose(s, top[:, :50], rtol=0, atol=2e-6)          # similarity scores, float32
+    # centring alone: column means are zero to float32 rounding
+    c = be.center_columns(torch.from_numpy(tr).cuda()).cpu().numpy()
+    np.testing.assert_allclose(c, tr - tr.astype(np.float64).mean(0).astype(np.float32), rtol=0, atol=0)
+
+
+def test_pdist_matches_torch_restatement(be):
+    from oracle import retrieval_oracle as ro
+    from video_similarity_search_b200 import coclr_retrieval as cr
+    rng = np.random.default_rng(3)
+    a, b = rng.standard_normal((208, 512)).astype(np.float32), rng.standard_normal((77, 512)).astype(np.float32)
+    for metric, tol in (("cosine", 1e-6), ("euclidean", 1e-4)):
+        np.testing.assert_allclose(cr.pdist_v2(a, b, 1e-6, metric, backend=be).cpu().numpy(), ro.pdist_v2(a, b, 1e-6, metric),
+                                   rtol=0, atol=tol)
+        np.testing.assert_allclose(cr.pdist(a, 1e-6, metric, backend=be).cpu().numpy(), ro.pdist_v2(a, a, 1e-6, metric),
+                                   rtol=0, atol=tol if metric == "cosine" else 4e-3)   # euclidean self-distances: eps * sqrt(d) in the reference

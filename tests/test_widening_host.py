@@ -100,3 +100,27 @@ def _collector_worker(rank, world, port, out_dir):
 def test_embedding_collector_gathers_batches_rank_major_under_gloo(tmp_path):
     mp.spawn(_collector_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     assert torch.equal(torch.load(tmp_path / "emb0.pt"), torch.load(tmp_path / "emb1.pt"))
+
+
+def _hard_retrieval_case(n_train=3000, n_test=500, d=128, k=40, seed=0):
+    """Overlapping mixture: kNN accuracy well below 1, so the hit counts say something."""
+    rng = np.random.default_rng(seed)
+    centres = 0.22 * rng.standard_normal((k, d))
+    ytr, yte = rng.integers(0, k, n_train), rng.integers(0, k, n_test)
+    tr = (centres[ytr] + rng.standard_normal((n_train, d)) + 0.5).astype(np.float32)     # + 0.5: centring matters
+    te = (centres[yte] + rng.standard_normal((n_test, d)) + 0.5).astype(np.float32)
+    return tr, ytr, te, yte
+
+
+def test_coclr_retrieval_wrapper_matches_torch_restatement(capsys):
+    from oracle import retrieval_oracle as ro
+    from video_similarity_search_b200 import coclr_retrieval as cr
+    tr, ytr, te, yte = _hard_retrieval_case()
+    accs = cr.nn_retrieval_accuracy(torch.from_numpy(te), torch.from_numpy(yte), torch.from_numpy(tr), torch.from_numpy(ytr),
+                                    backend=FakeBackend())
+    want, _ = ro.coclr_nn_accuracy(te, yte, tr, ytr)
+    assert 0.05 < want[0] < 0.9 and accs == want
+    assert capsys.readouterr().out.splitlines()[0] == '1NN acc = %.4f' % want[0]
+    for metric, tol in (("cosine", 1e-6), ("euclidean", 1e-4)):
+        got = cr.pdist_v2(te[:40], tr[:60], 1e-6, metric, backend=FakeBackend()).numpy()
+        np.testing.assert_allclose(got, ro.pdist_v2(te[:40], tr[:60], 1e-6, metric), rtol=0, atol=tol)

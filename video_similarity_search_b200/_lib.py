@@ -23,6 +23,7 @@ SIGNATURES = {
     "slic_last_screen_exec_flop": [_ptr],
     "slic_screen_trace": [_i32, _ptr],
     "slic_normalize_rows": [_ptr, _i64, _i32, _i32, _ptr, _ptr, _ptr, _i32, _ptr],
+    "slic_center_columns": [_ptr, _i64, _i32, _ptr, _ptr, _ptr],
     "slic_nn_exact_top1": [_ptr, _ptr, _i64, _ptr, _i64, _i32, _i32, _i64, _ptr, _ptr, _ptr],
     "slic_nn_top1": [_ptr, _ptr, _i64, _ptr, _ptr, _i64, _i32, _i32, _i32, _i64, _f32, _ptr, _ptr, _ptr, _ptr],
     "slic_nn_top1_sym_part": [_ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _f32, _ptr, _ptr, _ptr],

@@ -79,6 +79,12 @@ class CudaBackend:
         _lib.call("slic_normalize_rows", _p(x), n, d, _DT[x.dtype], _p(unit), None, _p(ub), dp, self._stream())
         return unit, ub
 
+    def center_columns(self, x):
+        """x - x.mean(dim=0, keepdim=True) for a float32 matrix (slic_center_columns)."""
+        out = torch.empty_like(x)
+        _lib.call("slic_center_columns", _p(x), x.shape[0], x.shape[1], _p(out), None, self._stream())
+        return out
+
     def nn_exact_top1(self, q_unit, x_unit, self_offset=-1, q_rows=None):
         nq = q_unit.shape[0] if q_rows is None else q_rows.shape[0]
         n, d = x_unit.shape

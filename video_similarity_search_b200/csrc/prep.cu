@@ -40,6 +40,34 @@ __global__ void __launch_bounds__(NORM_THREADS) normalize_rows_kernel(const T* _
     }
 }
 
+// ---- column centring (coclr_classify.py:788-789: feature - feature.mean(dim=0, keepdim=True)) ----------------
+// HBM-bound: x is read twice (sums, subtract) and written once.  Column sums are taken in float64 over fixed row slabs
+// and the slab partials added in slab order: deterministic.
+constexpr int CENTER_SLAB = 1024;
+__global__ void __launch_bounds__(256) column_partial_sums_kernel(const float* __restrict__ x, int64_t n, int d,
+                                                                 double* __restrict__ partial) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= d) return;
+    const int64_t r0 = (int64_t)blockIdx.y * CENTER_SLAB;
+    const int64_t r1 = r0 + CENTER_SLAB < n ? r0 + CENTER_SLAB : n;
+    double acc = 0.0;
+    for (int64_t r = r0; r < r1; ++r) acc += (double)x[r * d + col];   // consecutive threads: consecutive columns
+    partial[(int64_t)blockIdx.y * d + col] = acc;
+}
+__global__ void __launch_bounds__(256) column_means_kernel(const double* __restrict__ partial, int64_t slabs, int d, int64_t n,
+                                                          float* __restrict__ means) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= d) return;
+    double acc = 0.0;
+    for (int64_t s = 0; s < slabs; ++s) acc += partial[s * d + col];
+    means[col] = (float)(acc / (double)n);
+}
+__global__ void __launch_bounds__(256) subtract_columns_kernel(const float* __restrict__ x, int64_t total, int d,
+                                                              const float* __restrict__ means, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total) out[i] = x[i] - means[i % d];
+}
+
 int normalize_kernel_shape(int* threads, int* regs) {
     cudaFuncAttributes fa;
     SLIC_CUDA_OK(cudaFuncGetAttributes(&fa, normalize_rows_kernel<float>));
@@ -66,5 +94,26 @@ extern "C" int slic_normalize_rows(const void* x_dev, int64_t n, int32_t d, int3
         slic::normalize_rows_kernel<double><<<blocks, slic::NORM_THREADS, 0, st>>>((const double*)x_dev, n, d, (double*)unit_dev,
                                                                     (double*)norms_dev, (__nv_bfloat16*)unit_bf16_dev, dp);
     SLIC_LAUNCH_OK();
+    return SLIC_OK;
+}
+
+extern "C" int slic_center_columns(const float* x_dev, int64_t n, int32_t d, float* out_dev, float* means_out_dev,
+                                   slic_stream_t stream) {
+    using namespace slic;
+    SLIC_REQUIRE(n >= 1 && d >= 1 && x_dev && out_dev, "center_columns: bad arguments");
+    cudaStream_t st = as_stream(stream);
+    const int64_t slabs = ceil_div(n, CENTER_SLAB);
+    SLIC_REQUIRE(slabs <= 65535, "center_columns: more than 67 M rows");
+    Scratch partial, means;
+    SLIC_CUDA_OK(partial.alloc((size_t)slabs * d * sizeof(double), st));
+    SLIC_CUDA_OK(means.alloc((size_t)d * sizeof(float), st));
+    dim3 grid((unsigned)ceil_div(d, 256), (unsigned)slabs);
+    column_partial_sums_kernel<<<grid, 256, 0, st>>>(x_dev, n, d, partial.as<double>());
+    SLIC_LAUNCH_OK();
+    column_means_kernel<<<(unsigned)ceil_div(d, 256), 256, 0, st>>>(partial.as<double>(), slabs, d, n, means.as<float>());
+    SLIC_LAUNCH_OK();
+    subtract_columns_kernel<<<(unsigned)ceil_div(n * d, 256), 256, 0, st>>>(x_dev, n * d, d, means.as<float>(), out_dev);
+    SLIC_LAUNCH_OK();
+    if (means_out_dev) SLIC_CUDA_OK(cudaMemcpyAsync(means_out_dev, means.ptr, (size_t)d * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return SLIC_OK;
 }
