@@ -37,14 +37,22 @@ def test_nmi_ami_match_sklearn(be, n, r, c, seed):
     rng = np.random.default_rng(seed)
     lt = rng.integers(0, r, n) * 3 + 5
     lp = (lt // 3 * max(1, c // r) + rng.integers(0, max(1, c // max(r, 1)), n)) % c
-    if seed == 4:
-        lt, lp = np.arange(n), np.arange(n)[::-1].copy()
+    if seed == 4:       # a perfect match under a relabelling: NMI = AMI = 1
+        lt = rng.integers(0, 20, n)
+        lp = (lt * 7 + 3) % 20
     # float64 sums reduced in a different (fixed) order than numpy's, lgamma from CUDA's libm: 1e-12 / 1e-10 absolute
     assert metrics.mutual_info_score(lt, lp, backend=be) == pytest.approx(mo.mutual_info_score(lt, lp), abs=1e-12)
     assert metrics.normalized_mutual_info_score(lt, lp, backend=be) == pytest.approx(mo.normalized_mutual_info_score(lt, lp), abs=1e-12)
     assert metrics.adjusted_mutual_info_score(lt, lp, backend=be) == pytest.approx(mo.adjusted_mutual_info_score(lt, lp), abs=1e-10)
     # run-to-run reproducible (fixed reduction order)
     assert metrics.cluster_scores(lt, lp, backend=be) == metrics.cluster_scores(torch.from_numpy(lt).cuda(), torch.from_numpy(lp).cuda(), backend=be)
+
+
+def test_nmi_of_all_singletons_is_one(be):
+    """Every row its own class on both sides: NMI = 1.  (AMI is 0 / 0 there - mi, emi and the entropies all equal
+    log n - and sklearn's own value is rounding noise over eps; not pinned.)"""
+    lt = np.arange(300)
+    assert metrics.normalized_mutual_info_score(lt, lt[::-1].copy(), backend=be) == pytest.approx(1.0, abs=1e-12)
 
 
 def test_nmi_ami_kinetics_size_on_finch_labels(be):
