@@ -80,6 +80,12 @@ template <int NCTA, bool ARES, bool TOPK> struct TcCfg {
 constexpr int TC_MAX_STAGES = 6;
 constexpr int TC_EPI_WARPS = 8;   // two per TMEM lane quadrant: each takes one 128-column half of every tile
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+// Symmetric kernels: an eleventh warp does nothing but publish the column thresholds of the coming tiles (two tiles
+// ahead, double-buffered, mbarrier hand-shake), so that no epilogue warp ever waits for another one at a tile boundary.
+// (false: the first epilogue warp of each 128-column half writes them and the half meets at a named barrier per tile -
+// measured: 22 % of the epilogue's stall samples.)
+constexpr bool TC_SYM_THR_WARP = true;
+constexpr int TC_THREADS_SYM = TC_THREADS + (TC_SYM_THR_WARP ? 32 : 0);
 constexpr int TC_TMEM_COLS = 512;
 // Screen error allowance: a bf16-rounded operand carries relative error <= 2^-9, a product of two <= 2^-8 (+2^-18),
 // so for unit rows |screened - exact| <= 2^-8 * sum|a_k b_k| <= 2^-8, plus fp32 accumulation (<= d * 2^-24 relative to
@@ -748,6 +754,8 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
     const uint32_t bar_a_full = smem_u32(bars + 2 * TC_MAX_STAGES + 4);    // ARES: resident A landed (leader's used)
     const uint32_t bar_a_empty = smem_u32(bars + 2 * TC_MAX_STAGES + 5);   // ARES: the unit's MMAs retired
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 6);
+    const uint32_t bar_thr_full = smem_u32(bars + 24);    // SYM [2]: thresholds of a tile are in place (threshold warp)
+    const uint32_t bar_thr_empty = smem_u32(bars + 26);   // SYM [2]: the CTA's epilogue warps are done with them
     const uint32_t smem_base = smem_u32(smem);                 // ARES: resident A, slab ks at + ks * 16 KB
     const uint32_t ring_base = smem_base + Cfg::A_RES_BYTES;   // operand ring
 
@@ -769,6 +777,12 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
         }
         mbar_init(bar_a_full, 1);
         mbar_init(bar_a_empty, 1);
+        if constexpr (SYM) {
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(bar_thr_full + 8 * b, 1);
+                mbar_init(bar_thr_empty + 8 * b, TC_EPI_WARPS);
+            }
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -915,6 +929,43 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
                 atomicAdd(p.trace + 3, (unsigned long long)(clock64() - t_begin));   // MMA issuer total
             }
         }
+    } else if (SYM && TC_SYM_THR_WARP && warp == 2 + TC_EPI_WARPS) {
+        // ===================== SYM: column-threshold publisher =====================
+        // For every tile strictly right of the diagonal (the epilogue's "column role"): threshold of column c =
+        // best score published for row c so far - eps, as float16 rounded DOWN (a lower threshold only adds candidates;
+        // 2^-11 against eps = 2^-7), with a finite lower bound (threshold - masked score = +inf, never NaN).
+        uint16_t* thr_buf = reinterpret_cast<uint16_t*>(smem + Cfg::OPERAND_BYTES + 256);   // [2 buffers][2 halves][128]
+        constexpr unsigned ENC_POS_INF = 0xff800000u;
+        unsigned seq = 0;
+        for (int64_t u = group; u < p.num_units; u += num_groups) {
+            const UnitInfo ui = unit_info(p, u, n_col_tiles);
+            if (!ui.coldir) continue;
+            if (p.sync_counter) {   // published bests of the pre-pass are in place (speed only, as for the epilogue)
+                if (lane == 0) counter_wait(p.sync_counter, __ldg(p.sync_targets + ui.gate + 1), p.error_flag);
+                __syncwarp();
+            }
+            for (int kt = 0; kt < ui.count; ++kt) {
+                const int64_t ct = ui.ct0 + (int64_t)kt * ui.stride;
+                if (ct == ui.row_unit) continue;
+                const uint32_t buf = seq & 1u, ph = (seq >> 1) & 1u;
+                unsigned e[8];   // fetched first: the L2 round trip overlaps the wait for the buffer
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int64_t c = ct * TC_BN + lane + 32 * j;
+                    e[j] = c < p.n ? __ldcg(p.best_enc + c) : ENC_POS_INF;
+                }
+                mbar_wait(bar_thr_empty + 8 * buf, ph ^ 1u, p.error_flag);
+                const uint32_t ta = smem_u32(thr_buf + buf * 256) + 2u * lane;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const unsigned short t = __half_as_ushort(__float2half_rd(fmaxf(dec_score(e[j]) - p.eps, -60000.f)));
+                    asm volatile("st.shared.b16 [%0], %1;" ::"r"(ta + 64u * j), "h"(t) : "memory");
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_thr_full + 8 * buf);
+                ++seq;
+            }
+        }
     } else {
         // ===================== epilogue: fused candidate filter =====================
         // Warp w reads TMEM lanes [32 * (w % 4), +32) (the hardware's lane window of that warp) and the 128-column
@@ -986,7 +1037,17 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
                 // published bests now, the accumulator wait below hides the latency
                 bool cdir = false;
                 uint32_t thr_tile = 0u;   // shared-memory address of this tile's 128 column thresholds
-                if constexpr (SYM) {
+                uint32_t thr_done_bar = 0u;
+                if constexpr (SYM && TC_SYM_THR_WARP) {
+                    cdir = ui.coldir && ct != ui.row_unit;
+                    if (cdir) {   // the threshold warp runs two tiles ahead: this wait is normally a single poll
+                        const uint32_t buf = tile_seq & 1u, ph = (tile_seq >> 1) & 1u;
+                        thr_tile = smem_u32(thr_buf + (buf * 2 + half) * 128);
+                        thr_done_bar = bar_thr_empty + 8 * buf;
+                        mbar_wait(bar_thr_full + 8 * buf, ph, p.error_flag);
+                        ++tile_seq;
+                    }
+                } else if constexpr (SYM) {
                     // column thresholds of this tile's 128-column half: written to shared memory by the half's first warp
                     // (double-buffered by tile parity), then one named barrier of the half's four warps.  The writer fetched
                     // the published bests one tile ahead (nbc*), so that no L2 round trip sits in front of the barrier.
@@ -1101,6 +1162,12 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
                             if (acc == 0) acc_phase ^= 1;
                         }
                         epi_chunk<false, SYM>(cx, vb, col0 + 64 * h + 32, plain, cdir, thr_tile + 128u * h + 64u);
+                    }
+                    if constexpr (SYM && TC_SYM_THR_WARP) {
+                        if (cdir) {   // this warp no longer reads the tile's thresholds
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(thr_done_bar);
+                        }
                     }
                 }
                 if constexpr (TOPK) {
@@ -1590,7 +1657,7 @@ static int launch_screen(const uint16_t* q_bf16, int64_t nq, const uint16_t* x_b
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(TC_THREADS);
+    cfg.blockDim = dim3(sym ? TC_THREADS_SYM : TC_THREADS);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -2103,10 +2170,11 @@ bool screen_can_overlap_upload(int64_t n, int d_pad, int guest_threads, int gues
         return false;
     }
     const int host_regs = (fa.numRegs + 7) / 8 * 8, gr = (guest_regs + 7) / 8 * 8;
-    const int host_warps = (TC_THREADS / 32 + 3) / 4, guest_warps = (guest_threads / 32 + 3) / 4;   // on the fullest sub-partition
+    const int host_threads = sym ? TC_THREADS_SYM : TC_THREADS;
+    const int host_warps = (host_threads / 32 + 3) / 4, guest_warps = (guest_threads / 32 + 3) / 4;   // on the fullest sub-partition
     const bool regs_ok = 32 * (host_warps * host_regs + guest_warps * gr) <= 16384;
     const bool smem_ok = smem_bytes + 2 * 1024 <= 233472;
-    const bool threads_ok = TC_THREADS + guest_threads <= 2048;
+    const bool threads_ok = host_threads + guest_threads <= 2048;
     if (getenv("SLIC_SYM_DEBUG"))
         fprintf(stderr, "[slic] overlap check: screen %d regs, %zu B smem; guest %d threads x %d regs -> regs %d smem %d\n",
                 fa.numRegs, smem_bytes, guest_threads, guest_regs, (int)regs_ok, (int)smem_ok);
