@@ -116,17 +116,28 @@ int slic_nn_top1(const void* q_unit_dev, const uint16_t* q_bf16_dev, int64_t nq,
 
 /* Multi-GPU share of the level-0 self-search (clustering/finch.py:27-29 on N rows, spread over the GPUs of one box).
  * The score matrix of a self-search is symmetric: only the 256 x 256 tiles on or right of its diagonal are computed
- * and each is filtered along its rows and along its columns.  Process `part` of `parts` screens every parts-th unit of
- * that triangle (plus a small pre-pass over all rows) and re-ranks its candidates exactly, so it holds, for EVERY row,
+ * and each is filtered along its rows and along its columns.  Process `part` of `parts` screens a contiguous
+ * 1 / parts share (by tile count) of that triangle (plus a small pre-pass over all rows) and re-ranks its candidates exactly, so it holds, for EVERY row,
  * the best neighbour among the pairs it saw.  keys_out_dev [n + 1] (uint64):
  *   keys[i] = (float32 distance bits << 32) | neighbour index   (0x7fffffff7fffffff: no candidate seen for row i)
  *   keys[n] = 1, or 0 if this part's candidate log overflowed (its keys are then incomplete)
  * An element-wise MIN over the parts' arrays - one all-reduce over NCCL / NVLink - yields every row's first
  * neighbour with np.argmin's tie rule (smallest distance, then lowest index) and tells every process whether the
- * result is complete; slic_unpack_neighbor_keys splits it.  Needs n >= 16384 (SLIC_ERR_UNSUPPORTED below). */
+ * result is complete; slic_unpack_neighbor_keys splits it.  Needs n >= 16384 (SLIC_ERR_UNSUPPORTED below).
+ *
+ * The candidate filter of a row keeps what lies within eps of the best score seen for that row SO FAR; a part that sees
+ * 1 / parts of the tiles alone learns those bests slowly and logs (and re-ranks) far too much.  Two-phase use:
+ *   slic_sym_row_bests      part p screens its 1 / parts of the ROWS against 16 sampled column tiles and returns, for
+ *                           those rows, the best screened score in a signed-comparable int32 form (INT32-lowest elsewhere);
+ *   all-reduce MAX          of that [n] int32 array over the parts (4 n bytes);
+ *   slic_nn_top1_sym_part   with row_bests_dev = the merged array: thresholds for ALL rows from the first tile on, no
+ *                           pre-pass of its own.  row_bests_dev = NULL: single-phase (own pre-pass over all rows). */
+int slic_sym_row_bests(const float* unit_dev, const uint16_t* unit_bf16_dev, int64_t n, int32_t d, int32_t d_pad,
+                       int32_t part, int32_t parts, int32_t* bests_out_dev, slic_stream_t stream);
 int slic_nn_top1_sym_part(const float* unit_dev, const uint16_t* unit_bf16_dev, int64_t n, int32_t d,
-                          int32_t d_pad, int32_t part, int32_t parts, float eps, uint64_t* keys_out_dev,
-                          int32_t* stats_out_dev /* [4] or NULL, as slic_nn_top1 */, slic_stream_t stream);
+                          int32_t d_pad, int32_t part, int32_t parts, const int32_t* row_bests_dev, float eps,
+                          uint64_t* keys_out_dev, int32_t* stats_out_dev /* [4] or NULL, as slic_nn_top1 */,
+                          slic_stream_t stream);
 /* keys [n] (merged) -> idx_out [n] int32, dist_out [n] float32; status_out_dev[0] = rows without a neighbour. */
 int slic_unpack_neighbor_keys(const uint64_t* keys_dev, int64_t n, int32_t* idx_out_dev,
                               float* dist_out_dev, int32_t* status_out_dev, slic_stream_t stream);

@@ -77,13 +77,27 @@ class FakeBackend:
     def supports_triangle_parts(self, x):
         return x.dtype == torch.float32 and x.shape[0] >= self.SYM_MIN_ROWS
 
-    def first_neighbors_part(self, x, part, parts):
+    def first_neighbors_part(self, x, part, parts, reduce_max=None):
         """Block pairs (bi <= bj) of the distance matrix are dealt round-robin to the parts; a part evaluates its pairs
-        in both directions and keeps, per row, the smallest (distance bits, neighbour) key."""
+        in both directions and keeps, per row, the smallest (distance bits, neighbour) key.  reduce_max: the row-best
+        exchange of the two-phase search - exercised with this part's rows' best similarity to a column sample."""
         self.calls.append(("first_neighbors_part", tuple(x.shape), part, parts))
         unit, _ = self.normalize_rows(x, want_bf16=False)
         u = _np(unit)
         n, b = len(u), self.PART_BLOCK
+        if reduce_max is not None and parts > 1:
+            lo = np.iinfo(np.int32).min
+            bests = np.full(n, lo, dtype=np.int32)
+            r0, r1 = n * part // parts, n * (part + 1) // parts
+            s = (u[r0:r1].astype(np.float64) @ u[::7].astype(np.float64).T).astype(np.float32)
+            s[s > 0.99999] = -1.0                                       # (the row itself, if sampled)
+            enc = s.max(axis=1).view(np.uint32).astype(np.int64)
+            enc = np.where(enc & 0x80000000, ~enc & 0xffffffff, enc | 0x80000000) ^ 0x80000000
+            bests[r0:r1] = enc.astype(np.uint32).view(np.int32)
+            t = torch.from_numpy(bests)
+            reduce_max(t)
+            self.exchanged_bests = t
+            assert int((t == lo).sum()) == 0, "row bests of some rows were not delivered by the exchange"
         keys = np.full(n + 1, self.KEY_NONE, dtype=np.int64)
         keys[n] = 1
         nb = (n + b - 1) // b

@@ -397,6 +397,24 @@ def test_symmetric_screen_parts_merge_to_the_full_search(be, n, d, k, seed, part
     if parts > 1:
         nn0, _, _ = be.unpack_neighbor_keys(keys)
         assert not torch.equal(nn0, idx_ex)
+    # two-phase form (what sharded.py runs): every part first screens ITS rows against a column sample, the row bests
+    # are merged by MAX (the all-reduce), and every part starts its share of the triangle with thresholds for all rows
+    from video_similarity_search_b200 import _lib
+    unit2, ub = be.normalize_rows(xd)
+    bests = None
+    for part in range(parts):
+        b = torch.empty(n, dtype=torch.int32, device=xd.device)
+        _lib.call("slic_sym_row_bests", unit2.data_ptr(), ub.data_ptr(), n, d, ub.shape[1], part, parts, b.data_ptr(), None)
+        bests = b if bests is None else torch.maximum(bests, b)
+    assert int((bests == torch.iinfo(torch.int32).min).sum()) == 0 and int(bests.min()) > -2139095041   # every row has a finite best
+    merged2, logged = None, 0
+    for part in range(parts):
+        keys, _ = be.first_neighbors_part(xd, part, parts, reduce_max=lambda t: t.copy_(bests))
+        assert int(keys[n]) == 1
+        logged += int(be.last_stats[0])
+        merged2 = keys if merged2 is None else torch.minimum(merged2, keys)
+    nn2, dist2, complete2 = be.unpack_neighbor_keys(merged2)
+    assert complete2 and torch.equal(nn2, idx_ex) and torch.equal(dist2, dist)
     # parts = 1 is the whole triangle
     keys1, _ = be.first_neighbors_part(xd, 0, 1)
     nn1, _, complete1 = be.unpack_neighbor_keys(keys1)

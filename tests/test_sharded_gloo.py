@@ -43,12 +43,14 @@ def _worker(rank, world, port, name, golden_dir, out_dir):
         assert torch.equal(nn2, full_nn) and torch.equal(d2, full_d)
         assert [c[2:] for c in be2.calls if c[0] == "first_neighbors_part"] == [(rank, world)]
         assert not [c for c in be2.calls if c[0] == "first_neighbors"]
+        # phase 1 of the two-phase search: every rank received every row's best through the all-reduce MAX
+        assert be2.exchanged_bests.shape[0] == n
         # an incomplete part (candidate log overflow on one rank) sends every rank to the row-sharded search
         be3 = FakeBackend()
         part = be3.first_neighbors_part
 
-        def overflowing(mat, p, ps):
-            keys, unit = part(mat, p, ps)
+        def overflowing(mat, p, ps, reduce_max=None):
+            keys, unit = part(mat, p, ps, reduce_max=reduce_max)
             if p == ps - 1:
                 keys[-1] = 0
             return keys, unit

@@ -129,16 +129,26 @@ class CudaBackend:
         """True when the multi-process share of the symmetric self-search applies (level 0: float32, large n)."""
         return x.dtype == torch.float32 and x.shape[0] >= self.SYM_MIN_ROWS
 
-    def first_neighbors_part(self, x, part, parts):
-        """This process's share of the symmetric first-neighbour search of all rows of x (slic_nn_top1_sym_part).
+    def first_neighbors_part(self, x, part, parts, reduce_max=None):
+        """This process's share of the symmetric first-neighbour search of all rows of x.
+        reduce_max: callable applying an element-wise MAX over the parts to an int32 device tensor in place (the
+        all-reduce).  Given it, the search runs in two phases - slic_sym_row_bests on this part's rows, the exchange,
+        then slic_nn_top1_sym_part seeded with every row's best - so that the candidate filter starts tight on every
+        part; without it each part runs its own pre-pass over all rows (single-process use / tests).
         -> (keys int64 [n + 1], unit): keys[i] = (distance bits << 32) | neighbour for the best pair this part saw,
         keys[n] = completeness flag; an element-wise MIN over the parts merges them."""
         n, d = x.shape
         unit, ub = self.normalize_rows(x, want_bf16=True)
+        bests = None
+        if reduce_max is not None and parts > 1:
+            bests = torch.empty(n, dtype=torch.int32, device=x.device)
+            _lib.call("slic_sym_row_bests", _p(unit), _p(ub), n, d, ub.shape[1], int(part), int(parts), _p(bests),
+                      self._stream())
+            reduce_max(bests)
         keys = torch.empty(n + 1, dtype=torch.int64, device=x.device)
         stats = torch.zeros(4, dtype=torch.int32, device=x.device)
-        _lib.call("slic_nn_top1_sym_part", _p(unit), _p(ub), n, d, ub.shape[1], int(part), int(parts), 0.0, _p(keys),
-                  _p(stats), self._stream())
+        _lib.call("slic_nn_top1_sym_part", _p(unit), _p(ub), n, d, ub.shape[1], int(part), int(parts), _p(bests), 0.0,
+                  _p(keys), _p(stats), self._stream())
         self.last_stats = stats
         return keys, unit
 

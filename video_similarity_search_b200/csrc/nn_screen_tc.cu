@@ -1703,10 +1703,16 @@ static int4 unit_entry(int64_t row_unit, int64_t ct0, int count, int stride, int
 //             so the ~74 concurrently running CTA pairs stream the same 16 MB of B tiles and share them through L2
 //             (row-major orders were measured: each pair then streams its own column range from HBM and the kernel
 //             becomes DRAM-bound).
-// part / parts: this process takes every parts-th triangle unit (multi-GPU); the pre-pass is done by everyone.
+// part / parts: this process takes one contiguous 1 / parts share of the triangle (multi-GPU); the pre-pass is done by everyone.
 constexpr int SYM_CHUNK_TILES = 64;
 constexpr int SYM_SAMPLE_TILES = 16;
-static int plan_screen_sym(int64_t n, int part, int parts, const GateSpec* g, ScreenPlan* pl, std::vector<int4>* table) {
+// mode: SYM_FULL      pre-pass over all row units + this part's share of the triangle
+//       SYM_BESTS     ONLY a pre-pass, over this part's 1 / parts of the row units (multi-GPU phase 1: the parts then
+//                     exchange the row bests, so that every part starts the triangle with thresholds for ALL rows)
+//       SYM_TRIANGLE  ONLY this part's share of the triangle (row bests were seeded by the caller)
+enum SymMode { SYM_FULL = 0, SYM_BESTS = 1, SYM_TRIANGLE = 2 };
+static int plan_screen_sym(int64_t n, int part, int parts, const GateSpec* g, ScreenPlan* pl, std::vector<int4>* table,
+                           SymMode mode = SYM_FULL) {
     const int64_t T = ceil_div(n, TC_BN);
     SLIC_REQUIRE(T < 65536, "symmetric screen: more than 16.7 M rows");
     SLIC_REQUIRE(parts >= 1 && part >= 0 && part < parts, "symmetric screen: bad partition");
@@ -1725,20 +1731,38 @@ static int plan_screen_sym(int64_t n, int part, int parts, const GateSpec* g, Sc
     table->clear();
     // pre-pass sample: tiles spread over the whole matrix, or over the first upload chunk when the rest is in flight
     const int64_t span = g ? (chunk_tiles_gate < T ? chunk_tiles_gate : T) : T;
-    int samples = SYM_SAMPLE_TILES / parts;
+    // SYM_BESTS: every part pays a warm-up of loose thresholds at the start of its (short) share of the triangle, so a
+    // stronger sample pays off from 4 parts on (measured at 8 parts, C3: 16 / 32 / 64 tiles -> 3.96 / 3.64 / 3.30 ms for
+    // the triangle share against +0.1 ms per 16 tiles here)
+    int samples = mode == SYM_BESTS ? (parts >= 4 ? 4 * SYM_SAMPLE_TILES : SYM_SAMPLE_TILES) : SYM_SAMPLE_TILES / parts;
     if (samples < 4) samples = 4;
+    if (const char* e = getenv("SLIC_SYM_SAMPLES")) {   // experiments only
+        const int v = atoi(e);
+        if (v >= 1 && v <= 64) samples = v;
+    }
     if (samples > span) samples = (int)span;
     const int stride = (int)(span / samples);
-    for (int64_t r = 0; r < T; ++r) {
+    const int64_t pre0 = mode == SYM_BESTS ? T * part / parts : 0, pre1 = mode == SYM_BESTS ? T * (part + 1) / parts : T;
+    for (int64_t r = pre0; r < pre1 && mode != SYM_TRIANGLE; ++r) {
         const int gate = g ? (int)(r / chunk_tiles_gate) : -1;
         table->push_back(unit_entry(r, 0, samples, stride, gate, 0, false));
     }
-    int64_t tri = 0;
+    // part / parts: a CONTIGUOUS range of the chunk-major unit list holding 1 / parts of the triangle's tiles.  (Dealing
+    // the units round-robin was measured at 8 ranks: a rank's 74 concurrent CTA pairs then span ~9 column chunks, the B
+    // tiles are no longer shared through L2 and the kernel runs at half speed.)
+    int64_t total_tiles = 0;
     for (int64_t c0 = 0; c0 < T; c0 += SYM_CHUNK_TILES) {
+        const int64_t c1 = c0 + SYM_CHUNK_TILES < T ? c0 + SYM_CHUNK_TILES : T;
+        for (int64_t r = 0; r < c1; ++r) total_tiles += c1 - (r > c0 ? r : c0);
+    }
+    int64_t seen_tiles = 0;
+    for (int64_t c0 = 0; c0 < T && mode != SYM_BESTS; c0 += SYM_CHUNK_TILES) {
         const int64_t c1 = c0 + SYM_CHUNK_TILES < T ? c0 + SYM_CHUNK_TILES : T;
         for (int64_t r = 0; r < c1; ++r) {
             const int64_t ct0 = r > c0 ? r : c0;
-            if ((tri++ % parts) != part) continue;
+            const int64_t owner = seen_tiles * parts / total_tiles;   // < parts: seen_tiles < total_tiles here
+            seen_tiles += c1 - ct0;
+            if (owner != part) continue;
             const int gate = g ? (int)((c1 - 1) / chunk_tiles_gate) : -1;   // column chunk >= row chunk
             table->push_back(unit_entry(r, ct0, (int)(c1 - ct0), 1, gate, 0, nocol == 0));
         }
@@ -1785,7 +1809,8 @@ static int plan_screen_gated(int64_t nq, int64_t n, int64_t self_offset, const G
 template <typename T>
 static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d, int d_pad, float eps, int* idx_out,
                             T* dist_out, int* stats_out, cudaStream_t st, int part, int parts, const GateSpec* gate,
-                            AfterScreenFn after, void* after_ctx, bool* overflowed);
+                            AfterScreenFn after, void* after_ctx, bool* overflowed, int mode = 0,
+                            const int* bests_in = nullptr, int* bests_out = nullptr);
 static bool screen_sym_allowed();
 constexpr int64_t SYM_MIN_ROWS_FWD = 16384;   // below: too few tiles to fill the machine with half of them
 
@@ -1917,6 +1942,12 @@ static bool screen_sym_allowed() {
     return cached != 0 && screen_ncta() == 2;
 }
 
+// order-preserving score encoding <-> the same order as SIGNED int32 (what an all-reduce MAX over int32 compares)
+__global__ void flip_sign_bit_kernel(const unsigned int* __restrict__ in, int64_t n, unsigned int* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] ^ 0x80000000u;
+}
+
 __global__ void fill_u32_kernel(unsigned int* out, int64_t n, unsigned int v) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = v;
@@ -2010,12 +2041,13 @@ __global__ void sym_unsettled_rows_kernel(int* __restrict__ idx_out, int64_t n, 
 template <typename T>
 static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d, int d_pad, float eps, int* idx_out,
                             T* dist_out, int* stats_out, cudaStream_t st, int part, int parts, const GateSpec* gate,
-                            AfterScreenFn after, void* after_ctx, bool* overflowed) {
+                            AfterScreenFn after, void* after_ctx, bool* overflowed, int mode, const int* bests_in,
+                            int* bests_out) {
     typedef typename DistBits<T>::type Bits;
     *overflowed = false;
     ScreenPlan pl;
     std::vector<int4> table;
-    SLIC_PROPAGATE(plan_screen_sym(n, part, parts, gate, &pl, &table));
+    SLIC_PROPAGATE(plan_screen_sym(n, part, parts, gate, &pl, &table, (SymMode)mode));
     int64_t exec_tiles = 0;
     for (const int4& e : table) exec_tiles += e.z & 0xffff;
     // sync_targets[g + 1] = epilogue-warp arrivals of all pre-pass units with gate <= g (index 0: ungated)
@@ -2030,7 +2062,8 @@ static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d,
     const int64_t grid = (pl.units < groups ? pl.units : groups) * 2;
     const int64_t regions = grid * TC_EPI_WARPS;
     // (small inputs log more per row - every row starts from scratch in the pre-pass - and spread it less evenly)
-    const int64_t capacity = (int64_t)SYM_LOG_PER_ROW * n > SYM_LOG_MIN ? (int64_t)SYM_LOG_PER_ROW * n : SYM_LOG_MIN;
+    int64_t capacity = (int64_t)SYM_LOG_PER_ROW * n > SYM_LOG_MIN ? (int64_t)SYM_LOG_PER_ROW * n : SYM_LOG_MIN;
+    if (mode == SYM_BESTS) capacity = SYM_LOG_MIN;   // the records of phase 1 are discarded (an overflow is harmless)
     const int64_t region = ceil_div(capacity, regions);
     SLIC_REQUIRE(region < ((int64_t)1 << 31), "symmetric screen: log region too large");
     Scratch table_dev, lq, lnb, ls, lcnt, flag, best, rmin, edist, ovr, stats, sync;
@@ -2053,16 +2086,34 @@ static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d,
     SLIC_CUDA_OK(cudaMemsetAsync(lcnt.ptr, 0, regions * sizeof(int), st));
     SLIC_CUDA_OK(cudaMemsetAsync(flag.ptr, 0, sizeof(int), st));
     SLIC_CUDA_OK(cudaMemsetAsync(rmin.ptr, 0xff, n * sizeof(Bits), st));   // all-ones: above every distance's bits
-    fill_u32_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(best.as<unsigned int>(), n, ENC_NEG_INF);
+    if (bests_in)   // exchanged row bests (signed-comparable form) seed the thresholds
+        flip_sign_bit_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>((const unsigned int*)bests_in, n, best.as<unsigned int>());
+    else
+        fill_u32_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(best.as<unsigned int>(), n, ENC_NEG_INF);
     SLIC_LAUNCH_OK();
-    fill_u32_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>((unsigned int*)idx_out, n, 0x7fffffffu);
-    SLIC_LAUNCH_OK();
+    if (idx_out) {
+        fill_u32_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>((unsigned int*)idx_out, n, 0x7fffffffu);
+        SLIC_LAUNCH_OK();
+    }
     SLIC_PROPAGATE(launch_screen(ub, n, ub, n, d_pad, 0, eps, 0, pl, lnb.as<int>(), ls.as<float>(), lcnt.as<int>(),
                                  flag.as<int>(), nullptr, stats.as<int>() + 4, st, 0, nullptr, table_dev.as<int4>(),
                                  gate ? gate->gates : nullptr, best.as<unsigned int>(), exec_tiles, lq.as<int>(),
                                  (int)region, sync.as<int>(), sync.as<int>() + 1));
     if (g_profile && parts > 1) g_last_flop /= (double)parts;   // this process's share of the algorithmic 2 n^2 d
     if (after) SLIC_PROPAGATE(after(after_ctx));
+    if (mode == SYM_BESTS) {   // phase 1 of the multi-GPU search: the row bests are the result, the log is discarded
+        flip_sign_bit_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(best.as<unsigned int>(), n, (unsigned int*)bests_out);
+        SLIC_LAUNCH_OK();
+        int host_err = 0;
+        SLIC_CUDA_OK(cudaMemcpyAsync(&host_err, stats.as<int>() + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SLIC_CUDA_OK(cudaStreamSynchronize(st));
+        if (host_err != 0) {
+            set_error(host_err == 2 ? "nn_screen_kernel: shared-memory window is not aligned as the symmetric layout assumes"
+                                    : "nn_screen_kernel: pipeline barrier timed out");
+            return SLIC_ERR_CUDA;
+        }
+        return SLIC_OK;
+    }
     sym_rerank_dist_kernel<T><<<(unsigned)regions, 256, 0, st>>>(unit, d, eps, (int)region, lq.as<int>(), lnb.as<int>(),
                                                                  ls.as<float>(), lcnt.as<int>(), best.as<unsigned int>(),
                                                                  rmin.as<Bits>(), edist.as<T>(), stats.as<int>());
@@ -2129,7 +2180,7 @@ static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d,
     return SLIC_OK;
 }
 
-// ---- multi-GPU symmetric self-search: every process screens every parts-th triangle unit ----------------
+// ---- multi-GPU symmetric self-search: every process screens a contiguous 1 / parts share of the triangle ----------------
 // key = (float32 distance bits << 32) | neighbour: distances are >= 0, so their bit patterns order like the values and
 // an element-wise MIN over the processes' key arrays (one all-reduce) picks the smallest distance and, among equal
 // distances, the lowest neighbour index - np.argmin's rule.  A row without a record keeps the largest key.
@@ -2215,9 +2266,28 @@ int slic_nn_top1(const void* q_unit_dev, const uint16_t* q_bf16_dev, int64_t nq,
                                       st);
 }
 
+int slic_sym_row_bests(const float* unit_dev, const uint16_t* bf16_dev, int64_t n, int32_t d, int32_t d_pad, int32_t part,
+                       int32_t parts, int32_t* bests_out_dev, slic_stream_t stream) {
+    using namespace slic;
+    SLIC_REQUIRE(n > 1 && n < ((int64_t)1 << 31), "sym_row_bests: bad shape");
+    SLIC_REQUIRE(d > 0 && d_pad >= d && d_pad % 64 == 0, "sym_row_bests: d_pad must be a multiple of 64 >= d");
+    SLIC_REQUIRE(unit_dev && bf16_dev && bests_out_dev, "sym_row_bests: null pointer");
+    SLIC_REQUIRE(parts >= 1 && part >= 0 && part < parts, "sym_row_bests: part must be in [0, parts)");
+    SLIC_REQUIRE((reinterpret_cast<uintptr_t>(bf16_dev) & 15) == 0, "sym_row_bests: bf16 matrix must be 16-byte aligned");
+    SLIC_PROPAGATE(slic_require_device());
+    if (!screen_self_search_is_symmetric(n)) {
+        set_error("sym_row_bests: the symmetric screen needs n >= %lld rows (and SLIC_SCREEN_SYM != 0)", (long long)SYM_MIN_ROWS_FWD);
+        return SLIC_ERR_UNSUPPORTED;
+    }
+    bool overflowed = false;
+    return nn_top1_sym_impl<float>(unit_dev, bf16_dev, n, d, d_pad, TC_DEFAULT_EPS, nullptr, nullptr, nullptr,
+                                   as_stream(stream), part, parts, nullptr, nullptr, nullptr, &overflowed, SYM_BESTS, nullptr,
+                                   bests_out_dev);
+}
+
 int slic_nn_top1_sym_part(const float* unit_dev, const uint16_t* bf16_dev, int64_t n, int32_t d, int32_t d_pad,
-                          int32_t part, int32_t parts, float eps, uint64_t* keys_out_dev, int32_t* stats_out_dev,
-                          slic_stream_t stream) {
+                          int32_t part, int32_t parts, const int32_t* row_bests_dev, float eps, uint64_t* keys_out_dev,
+                          int32_t* stats_out_dev, slic_stream_t stream) {
     using namespace slic;
     SLIC_REQUIRE(n > 1 && n < ((int64_t)1 << 31), "nn_top1_sym_part: bad shape");
     SLIC_REQUIRE(d > 0 && d_pad >= d && d_pad % 64 == 0, "nn_top1_sym_part: d_pad must be a multiple of 64 >= d");
@@ -2237,7 +2307,8 @@ int slic_nn_top1_sym_part(const float* unit_dev, const uint16_t* bf16_dev, int64
     SLIC_CUDA_OK(dist.alloc((size_t)n * sizeof(float), st));
     bool overflowed = false;
     SLIC_PROPAGATE(nn_top1_sym_impl<float>(unit_dev, bf16_dev, n, d, d_pad, eps, idx.as<int>(), dist.as<float>(),
-                                           stats_out_dev, st, part, parts, nullptr, nullptr, nullptr, &overflowed));
+                                           stats_out_dev, st, part, parts, nullptr, nullptr, nullptr, &overflowed,
+                                           row_bests_dev ? SYM_TRIANGLE : SYM_FULL, row_bests_dev, nullptr));
     sym_pack_keys_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(idx.as<int>(), dist.as<float>(), n,
                                                                      (unsigned long long*)keys_out_dev);
     SLIC_LAUNCH_OK();

@@ -1,7 +1,7 @@
 """Multi-GPU level-0 first-neighbour search across the ranks of one box, every rank holding the full
 embedding matrix.  Two ways to share the O(N^2 D) stage:
   * triangle parts (large float32 self-searches, the default): the symmetric screen computes only the tiles on
-    or right of the diagonal; rank r takes every world-th unit of that triangle and the per-row (distance,
+    or right of the diagonal; rank r takes a contiguous 1/world share of that triangle and the per-row (distance,
     neighbour) keys are merged by ONE all-reduce (MIN) over NCCL / NVLink - 8 (N + 1) bytes;
   * row shards (small inputs, retrieval, fallback): rank r searches rows [r * ceil(N / G), ...) against all
     columns; ids and distances (which the min_sim filter needs) are all-gathered.
@@ -37,9 +37,13 @@ def sharded_first_neighbors(be, group=None, timings=None, triangle=True):
         if world > 1 and triangle and hasattr(be, "first_neighbors_part") and be.supports_triangle_parts(mat):
             # The score matrix of a self-search is symmetric: the ranks share the tiles on or right of its diagonal
             # (half the flops of the row-sharded full square) and every rank ends up with, for EVERY row, the best
-            # neighbour among the pairs it saw.  The exchange step is one all-reduce (MIN) of 8 (N + 1) bytes of
-            # (distance, neighbour) keys; every rank sees the same merged array, hence takes the same branch below.
-            keys, unit = be.first_neighbors_part(mat, rank, world)
+            # neighbour among the pairs it saw, as (distance, neighbour) keys; every rank sees the same merged array,
+            # hence takes the same branch below.
+            # Two exchange steps: (1) all-reduce MAX of 4 N bytes of row bests - each rank screens 1 / G of the ROWS
+            # against a sample of the columns first, so that every rank's candidate filter starts tight for all rows;
+            # (2) all-reduce MIN of the 8 (N + 1) bytes of keys.
+            keys, unit = be.first_neighbors_part(
+                mat, rank, world, reduce_max=lambda t: dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group))
             dist.all_reduce(keys, op=dist.ReduceOp.MIN, group=group)
             nn, d, complete = be.unpack_neighbor_keys(keys)
             if complete:
