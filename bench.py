@@ -248,7 +248,7 @@ def run_b200(args):
     from video_similarity_search_b200 import _lib, synth
     from video_similarity_search_b200.backend import CudaBackend
     from video_similarity_search_b200.clustering.finch import FINCH
-    from video_similarity_search_b200.sharded import sharded_first_neighbors
+    from video_similarity_search_b200.sharded import FINCH_sharded, sharded_first_neighbors
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -296,8 +296,11 @@ def run_b200(args):
         return FINCH(x_dev, verbose=False, backend=be, first_neighbors=search)
 
     def step_e2e():
-        # the call a reference user makes: numpy in, numpy out (H2D of the embeddings, D2H of the labels inside)
-        return FINCH(x_pinned, verbose=False, backend=be, first_neighbors=search)
+        # the call a reference user makes: host matrix in, numpy out (H2D of the embeddings, D2H of the labels inside).
+        # N > 1: FINCH_sharded - every rank uploads 1 / N of the rows and an all-gather over NVLink assembles the matrix
+        if world > 1:
+            return FINCH_sharded(x_pinned, verbose=False, backend=be)
+        return FINCH(x_pinned, verbose=False, backend=be)
 
     def step_nn_only():
         return (search(x_dev) if search else be.first_neighbors(x_dev))
@@ -366,7 +369,8 @@ def run_b200(args):
         "finch_seconds": ms_step * 1e-3,
         "nn_stage": {"ms": ms_nn, "queries_per_s": n / (ms_nn * 1e-3)},
         "e2e": {"value": n / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(n * d * 4), "d2h_bytes_per_step": int(c.size * 4)},
+                # whole job: every rank uploads its 1 / N share of the rows (the rest arrives over NVLink); labels back per rank
+                "h2d_bytes_per_step": int(n * d * 4), "d2h_bytes_per_step": int(c.size * 4 * world)},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"kernel": "nn_screen_kernel (level 0, %d x %d x %d%s)" % (n, n, d_pad, "" if world == 1 else

@@ -66,6 +66,11 @@ def _worker(rank, world, port, name, golden_dir, out_dir):
             gi, gd = topk_neighbors_sharded(qq, xt, 5, same=same, backend=be)
             ei, ed = FakeBackend().topk_neighbors(qq, xt, 5, same=same)
             assert torch.equal(gi, ei) and torch.equal(gd, ed)
+        # host matrix in: every rank uploads its 1 / world of the rows, one all-gather assembles the matrix
+        from video_similarity_search_b200.sharded import upload_replicated
+        up = upload_replicated(x, backend=FakeBackend())
+        assert up.shape == x.shape and torch.equal(up, torch.from_numpy(x))
+        assert torch.equal(upload_replicated(torch.from_numpy(x.astype(np.float64)), backend=FakeBackend()), torch.from_numpy(x))
         c, num_clust, _ = FINCH_sharded(x, backend=FakeBackend(), verbose=False)
         np.save(os.path.join(out_dir, "c_rank%d.npy" % rank), c)
         g = np.load(os.path.join(golden_dir, name + ".npz"))

@@ -67,13 +67,38 @@ def sharded_first_neighbors(be, group=None, timings=None, triangle=True):
     return search
 
 
+def upload_replicated(data, group=None, backend=None):
+    """Host matrix held by EVERY rank -> full [N, D] float32 device matrix on every rank, with 1 / G of the PCIe
+    traffic per rank: rank r copies rows [r * ceil(N / G), ...) host -> device, then one all-gather over NVLink
+    assembles the matrix (the G ranks of a box share the host's memory and PCIe root, so G full uploads cost G times
+    the bytes over the same links).  Device-resident input is returned as it is."""
+    be = backend or _backend.default_backend()
+    if isinstance(data, torch.Tensor) and data.device.type != "cpu":
+        return be.to_device(data.detach(), torch.float32)
+    host = data.detach() if isinstance(data, torch.Tensor) else torch.as_tensor(data)
+    if not dist.is_initialized() or dist.get_world_size(group) == 1 or host.dim() != 2:
+        return be.to_device(host, torch.float32)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n, d = host.shape
+    r0, r1, per = shard_range(n, rank, world)
+    full = torch.empty((per * world, d), dtype=torch.float32, device=be.device)
+    mine = torch.empty((per, d), dtype=torch.float32, device=be.device)
+    if r1 > r0:
+        mine[: r1 - r0].copy_(host[r0:r1], non_blocking=True)
+    if r1 - r0 < per:
+        mine[r1 - r0:].zero_()                         # padding rows of the ragged last shards
+    dist.all_gather_into_tensor(full, mine, group=group)
+    return full[:n]
+
+
 def FINCH_sharded(data, group=None, backend=None, **kwargs):
-    """FINCH with the level-0 nearest-neighbour stage row-sharded over the process group.  Every rank
-    must pass the same `data`; every rank returns the same (c, num_clust, req_c)."""
+    """FINCH with the level-0 nearest-neighbour stage shared by the ranks of the process group.  Every rank
+    must pass the same `data` (host or device); every rank returns the same (c, num_clust, req_c)."""
     be = backend or _backend.default_backend()
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return FINCH(data, backend=be, **kwargs)
-    return FINCH(data, backend=be, first_neighbors=sharded_first_neighbors(be, group), **kwargs)
+    dev = upload_replicated(data, group=group, backend=be)
+    return FINCH(dev, backend=be, first_neighbors=sharded_first_neighbors(be, group), **kwargs)
 
 
 def topk_neighbors_sharded(q, x, k, same=False, group=None, backend=None):
