@@ -134,7 +134,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": n / sec, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "FINCH full hierarchy, N=%d x D=%d Gaussian mixture (K=%d, seed %d)" % (n, d, k, seed)},
+        "config": {"workload": "FINCH full hierarchy, N=%d x D=%d Gaussian mixture (K=%d, seed %d), cosine" % (n, d, k, seed)},
         "finch_seconds": sec,
         "cpu_baseline": {"value": n / sec, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "level-0 NN stage on %d of %d query rows x all columns, scaled linearly in rows; "
