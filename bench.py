@@ -54,7 +54,7 @@ def parse_args():
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed
 # `ncu --set full` capture (profiles/r1_sym_screen_kernel_ncu_full.txt); keyed by (workload, ranks).  Not measured live:
 # a number taken under the profiler's replay is evidence of traffic, never of time.
-NCU_TRAFFIC_BYTES = {("C3", 1): 2.101503e9 + 102.8736e6}
+NCU_TRAFFIC_BYTES = {("C3", 1): 2.115234e9 + 102.021376e6}
 
 
 def load_peaks():

@@ -41,14 +41,18 @@ out["cluster_metrics"] = {"ms": ms, "algorithmic_bytes": 8 * 240000 + 4 * R * C,
                           "nmi": metrics.normalized_mutual_info_score(lab, pred, backend=be), "nmi_cpu": nmi_cpu}
 ms, _ = timed(lambda: be.cluster_metrics(lt, lp, R, C, False))
 out["cluster_metrics"]["ms_without_emi"] = ms
-ms, _ = timed(lambda: be.center_columns(xd))
+from video_similarity_search_b200 import _lib
+cen = torch.empty_like(xd)
+ms, _ = timed(lambda: _lib.call("slic_center_columns", xd.data_ptr(), 240000, 512, cen.data_ptr(), None, None))
 out["center_columns"] = {"ms": ms, "algorithmic_bytes": 3 * x.nbytes, "gbs": 3 * x.nbytes / ms / 1e6,
                          "frac_of_hbm_peak": 3 * x.nbytes / ms / 1e6 / peaks["hbm_gbs"]}
 idx = torch.randperm(240000, device=be.device)
 ms, _ = timed(lambda: be.scatter_last_wins(lp, idx, 240000))
 t0 = time.perf_counter(); mo.unshuffled_assignments(pred.tolist(), idx.cpu().tolist(), 240000); t_py = time.perf_counter() - t0
 out["scatter_last_wins"] = {"ms": ms, "algorithmic_bytes": 12 * 240000 + 8 * 240000, "cpu_python_loop_s": t_py}
-ms, _ = timed(lambda: be.normalize_rows(xd))
+unit_buf, bf_buf = torch.empty_like(xd), torch.empty((240000, 512), dtype=torch.bfloat16, device=xd.device)
+ms, _ = timed(lambda: _lib.call("slic_normalize_rows", xd.data_ptr(), 240000, 512, 0, unit_buf.data_ptr(), None,
+                                bf_buf.data_ptr(), 512, None))
 out["normalize_rows"] = {"ms": ms, "algorithmic_bytes": int(x.nbytes * 2.5), "gbs": x.nbytes * 2.5 / ms / 1e6,
                          "frac_of_hbm_peak": x.nbytes * 2.5 / ms / 1e6 / peaks["hbm_gbs"]}
 ms, _ = timed(lambda: be.cluster_sums(xd, lp, C))

@@ -43,29 +43,48 @@ __global__ void __launch_bounds__(NORM_THREADS) normalize_rows_kernel(const T* _
 // ---- column centring (coclr_classify.py:788-789: feature - feature.mean(dim=0, keepdim=True)) ----------------
 // HBM-bound: x is read twice (sums, subtract) and written once.  Column sums are taken in float64 over fixed row slabs
 // and the slab partials added in slab order: deterministic.
-constexpr int CENTER_SLAB = 1024;
+constexpr int CENTER_SLAB = 256;
 __global__ void __launch_bounds__(256) column_partial_sums_kernel(const float* __restrict__ x, int64_t n, int d,
                                                                  double* __restrict__ partial) {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= d) return;
     const int64_t r0 = (int64_t)blockIdx.y * CENTER_SLAB;
     const int64_t r1 = r0 + CENTER_SLAB < n ? r0 + CENTER_SLAB : n;
-    double acc = 0.0;
-    for (int64_t r = r0; r < r1; ++r) acc += (double)x[r * d + col];   // consecutive threads: consecutive columns
-    partial[(int64_t)blockIdx.y * d + col] = acc;
+    // consecutive threads read consecutive columns (coalesced); four independent chains keep loads in flight
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int64_t r = r0;
+    for (; r + 4 <= r1; r += 4) {
+        a0 += (double)x[r * d + col];
+        a1 += (double)x[(r + 1) * d + col];
+        a2 += (double)x[(r + 2) * d + col];
+        a3 += (double)x[(r + 3) * d + col];
+    }
+    for (; r < r1; ++r) a0 += (double)x[r * d + col];
+    partial[(int64_t)blockIdx.y * d + col] = (a0 + a1) + (a2 + a3);
 }
+// one warp per column: lanes stride the slabs, fixed-order shuffle reduction
 __global__ void __launch_bounds__(256) column_means_kernel(const double* __restrict__ partial, int64_t slabs, int d, int64_t n,
                                                           float* __restrict__ means) {
-    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int col = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (col >= d) return;
     double acc = 0.0;
-    for (int64_t s = 0; s < slabs; ++s) acc += partial[s * d + col];
-    means[col] = (float)(acc / (double)n);
+    for (int64_t s = lane; s < slabs; s += 32) acc += partial[s * d + col];
+    acc = warp_sum(acc);
+    if (lane == 0) means[col] = (float)(acc / (double)n);
 }
 __global__ void __launch_bounds__(256) subtract_columns_kernel(const float* __restrict__ x, int64_t total, int d,
                                                               const float* __restrict__ means, float* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < total) out[i] = x[i] - means[i % d];
+}
+// d % 4 == 0 and 16-byte aligned rows: 128-bit loads and stores
+__global__ void __launch_bounds__(256) subtract_columns_v4_kernel(const float4* __restrict__ x, int64_t total4, int d4,
+                                                                 const float4* __restrict__ means, float4* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const float4 v = x[i], m = __ldg(means + (i % d4));
+    out[i] = make_float4(v.x - m.x, v.y - m.y, v.z - m.z, v.w - m.w);
 }
 
 int normalize_kernel_shape(int* threads, int* regs) {
@@ -103,16 +122,22 @@ extern "C" int slic_center_columns(const float* x_dev, int64_t n, int32_t d, flo
     SLIC_REQUIRE(n >= 1 && d >= 1 && x_dev && out_dev, "center_columns: bad arguments");
     cudaStream_t st = as_stream(stream);
     const int64_t slabs = ceil_div(n, CENTER_SLAB);
-    SLIC_REQUIRE(slabs <= 65535, "center_columns: more than 67 M rows");
+    SLIC_REQUIRE(slabs <= 65535, "center_columns: more than 16.7 M rows");
     Scratch partial, means;
     SLIC_CUDA_OK(partial.alloc((size_t)slabs * d * sizeof(double), st));
     SLIC_CUDA_OK(means.alloc((size_t)d * sizeof(float), st));
     dim3 grid((unsigned)ceil_div(d, 256), (unsigned)slabs);
     column_partial_sums_kernel<<<grid, 256, 0, st>>>(x_dev, n, d, partial.as<double>());
     SLIC_LAUNCH_OK();
-    column_means_kernel<<<(unsigned)ceil_div(d, 256), 256, 0, st>>>(partial.as<double>(), slabs, d, n, means.as<float>());
+    column_means_kernel<<<(unsigned)ceil_div((int64_t)d * 32, 256), 256, 0, st>>>(partial.as<double>(), slabs, d, n,
+                                                                                  means.as<float>());
     SLIC_LAUNCH_OK();
-    subtract_columns_kernel<<<(unsigned)ceil_div(n * d, 256), 256, 0, st>>>(x_dev, n * d, d, means.as<float>(), out_dev);
+    const bool v4 = d % 4 == 0 && ((reinterpret_cast<uintptr_t>(x_dev) | reinterpret_cast<uintptr_t>(out_dev)) & 15) == 0;
+    if (v4)
+        subtract_columns_v4_kernel<<<(unsigned)ceil_div(n * d / 4, 256), 256, 0, st>>>(
+            (const float4*)x_dev, n * d / 4, d / 4, (const float4*)means.as<float>(), (float4*)out_dev);
+    else
+        subtract_columns_kernel<<<(unsigned)ceil_div(n * d, 256), 256, 0, st>>>(x_dev, n * d, d, means.as<float>(), out_dev);
     SLIC_LAUNCH_OK();
     if (means_out_dev) SLIC_CUDA_OK(cudaMemcpyAsync(means_out_dev, means.ptr, (size_t)d * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return SLIC_OK;
