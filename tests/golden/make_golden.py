@@ -32,12 +32,22 @@ CASES = {
     "gmm_2500x96_flann":  dict(gen="gmm", n=2500, d=96, k=25, seed=11, flann_threshold=1000),
     "gmm_777x200_odd":    dict(gen="gmm", n=777, d=200, k=9, seed=13),
     "c1_9537x512":        dict(gen="gmm", n=9537, d=512, k=101, seed=0),
+    # degenerate shapes: the smallest inputs, and all-zero rows (unit row = 0, every distance exactly 1.0: the
+    # first neighbour is the lowest other index, np.argmin's tie rule with no rounding involved)
+    "tiny_2x8":           dict(gen="iid", n=2, d=8, seed=21),
+    "tiny_3x8":           dict(gen="iid", n=3, d=8, seed=22),
+    "tiny_5x16":          dict(gen="iid", n=5, d=16, seed=23),
+    "zeros_500x32":       dict(gen="gmm_zero_rows", n=500, d=32, k=6, seed=24, zero_rows=[0, 7, 8, 250, 499]),
 }
 
 
 def make_input(case):
     if case["gen"] == "gmm":
         return synth.gaussian_mixture(case["n"], case["d"], case["k"], case["seed"])
+    if case["gen"] == "gmm_zero_rows":
+        x = synth.gaussian_mixture(case["n"], case["d"], case["k"], case["seed"])
+        x[case["zero_rows"]] = 0
+        return x
     return synth.iid_normal(case["n"], case["d"], case["seed"])
 
 
