@@ -299,7 +299,12 @@ class CudaBackend:
         level-0 screen.  -> (c int32 [N, P] numpy, num_clust list, min_sim or None)."""
         n, d = x.shape
         cap = self.FINCH_CAPACITY
-        out = np.empty(n * cap, dtype=np.int32)
+        # labels come back into the cached pinned staging buffer (a pageable destination makes the runtime stage the copy
+        # itself, at a fraction of the PCIe rate); only the [N, P] prefix that was written is copied out
+        nbytes = n * cap * 4
+        if self._stage is None or self._stage.numel() < nbytes:
+            self._stage = torch.empty(max(nbytes, 1 << 22), dtype=torch.uint8, pin_memory=True)
+        out = self._stage[:nbytes].view(torch.int32).numpy()
         num = (ctypes.c_int32 * cap)()
         levels, has = ctypes.c_int32(0), ctypes.c_int32(0)
         ms = ctypes.c_float(0)
@@ -313,7 +318,7 @@ class CudaBackend:
                       int(bool(ensure_early_exit)), cap, out.ctypes.data, ctypes.addressof(num), ctypes.addressof(levels),
                       ctypes.addressof(ms), ctypes.addressof(has))
         p = levels.value
-        return out[: n * p].reshape(n, p), [int(v) for v in num[:p]], (np.float32(ms.value) if has.value else None)
+        return out[: n * p].reshape(n, p).copy(), [int(v) for v in num[:p]], (np.float32(ms.value) if has.value else None)
 
     # -- K4 --------------------------------------------------------------------------------------
     def label_mask(self, a, b, prepend_ones=False, negate=False):

@@ -27,7 +27,7 @@ static int64_t FLANN_THRESHOLD = 70000;
 constexpr int64_t SCREEN_MIN_ROWS = 2048;    // below: the tensor-core screen is launch overhead, use the exact kernel
 constexpr int FINCH_MAX_LEVELS = 64;
 constexpr int64_t GATED_MIN_ROWS = 32768;    // host entry: below this the upload is too short to be worth pipelining
-constexpr int GATED_CHUNKS = 4;
+constexpr int GATED_CHUNKS = 8;             // measured at C3 (492 MB): 4 / 8 / 12 chunks -> 31.6 / 30.6 / 30.4 ms end to end
 
 // experiments: SLIC_GATED_CHUNKS=<c> overrides the chunk count of the pipelined upload (<= 1: no pipelining)
 static int gated_chunks() {
