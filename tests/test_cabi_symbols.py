@@ -50,3 +50,28 @@ def test_argument_validation_needs_no_gpu():
     assert lib.slic_normalize_rows(None, -1, 0, 0, None, None, None, 0, None) == -1
     assert b"normalize_rows" in lib.slic_last_error()
     assert lib.slic_rows_topk(None, 1, 10, 10, 0, 11, None, None, None) == -1
+
+
+def test_argument_validation_of_the_multi_gpu_and_widening_entries_needs_no_gpu():
+    lib = _lib.load()
+    assert lib.slic_nn_top1_sym_part(None, None, 20000, 64, 64, 0, 2, None, 0.0, None, None, None) == -1      # null pointers
+    assert b"nn_top1_sym_part" in lib.slic_last_error()
+    assert lib.slic_nn_top1_sym_part(None, None, 20000, 64, 60, 0, 2, None, 0.0, None, None, None) == -1      # d_pad % 64
+    assert lib.slic_sym_row_bests(None, None, 20000, 64, 64, 2, 2, None, None) == -1                          # part >= parts (after nulls)
+    assert lib.slic_unpack_neighbor_keys(None, 0, None, None, None, None) == -1
+    assert lib.slic_scatter_last_wins(None, None, -1, 10, -1, None, None, None) == -1
+    assert lib.slic_center_columns(None, 0, 0, None, None, None) == -1
+    # 70 000 x 70 000 contingency cells exceed the dense limit: refused before any device work
+    buf = ctypes.create_string_buffer(64)
+    assert lib.slic_cluster_metrics(buf, buf, 70000, 70000, 70000, 1, buf, None) == -3                         # SLIC_ERR_UNSUPPORTED
+    assert b"contingency" in lib.slic_last_error()
+
+
+def test_bench_without_a_gpu_fails_loudly_and_names_the_cpu_arm():
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)

@@ -82,10 +82,9 @@ constexpr int TC_EPI_WARPS = 8;   // two per TMEM lane quadrant: each takes one 
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 // Symmetric kernels: an eleventh warp does nothing but publish the column thresholds of the coming tiles (two tiles
 // ahead, double-buffered, mbarrier hand-shake), so that no epilogue warp ever waits for another one at a tile boundary.
-// (false: the first epilogue warp of each 128-column half writes them and the half meets at a named barrier per tile -
-// measured: 22 % of the epilogue's stall samples.)
-constexpr bool TC_SYM_THR_WARP = true;
-constexpr int TC_THREADS_SYM = TC_THREADS + (TC_SYM_THR_WARP ? 32 : 0);
+// (Before: the first epilogue warp of each 128-column half wrote them and the half met at a named barrier per tile -
+// measured at 22 % of the epilogue's stall samples, profiles/r1_sym_screen_kernel_ncu_full.txt.)
+constexpr int TC_THREADS_SYM = TC_THREADS + 32;
 constexpr int TC_TMEM_COLS = 512;
 // Screen error allowance: a bf16-rounded operand carries relative error <= 2^-9, a product of two <= 2^-8 (+2^-18),
 // so for unit rows |screened - exact| <= 2^-8 * sum|a_k b_k| <= 2^-8, plus fp32 accumulation (<= d * 2^-24 relative to
@@ -929,7 +928,7 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
                 atomicAdd(p.trace + 3, (unsigned long long)(clock64() - t_begin));   // MMA issuer total
             }
         }
-    } else if (SYM && TC_SYM_THR_WARP && warp == 2 + TC_EPI_WARPS) {
+    } else if (SYM && warp == 2 + TC_EPI_WARPS) {
         // ===================== SYM: column-threshold publisher =====================
         // For every tile strictly right of the diagonal (the epilogue's "column role"): threshold of column c =
         // best score published for row c so far - eps, as float16 rounded DOWN (a lower threshold only adds candidates;
@@ -975,7 +974,7 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
         const int row_in_tile = quad * 32 + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
-        unsigned long long t_full = 0, n_trig = 0, n_chunks = 0;
+        unsigned long long t_full = 0;
         const long long t_begin = tracing ? clock64() : 0;
         EpiCtx<TOPK> cx;
         cx.p = &p;
@@ -986,7 +985,6 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
         unsigned int* s_logcnt = reinterpret_cast<unsigned int*>(bars + 20) + (warp - 2);   // spare bytes of the barrier block
         uint16_t* thr_buf = reinterpret_cast<uint16_t*>(smem + Cfg::OPERAND_BYTES + 256);   // SYM: float16 [2 parities][2 halves][128]
         unsigned tile_seq = 0;
-        unsigned nbc0 = 0u, nbc1 = 0u, nbc2 = 0u, nbc3 = 0u;   // SYM, first warp of a half: next tile's published column bests
         const int64_t log_region_id = (int64_t)blockIdx.x * TC_EPI_WARPS + (warp - 2);
         if constexpr (SYM) {
             if (lane == 0) *s_logcnt = 0u;
@@ -1033,12 +1031,12 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
             for (int kt = 0; kt < ui.count; ++kt) {
                 const int64_t ct = ui.ct0 + (int64_t)kt * ui.stride;
                 const int64_t col0 = ct * TC_BN + half * 128;
-                // SYM: tiles strictly right of the diagonal also serve their columns as queries; fetch the columns'
-                // published bests now, the accumulator wait below hides the latency
+                // SYM: tiles strictly right of the diagonal also serve their columns as queries; their thresholds come from
+                // the threshold warp through shared memory
                 bool cdir = false;
                 uint32_t thr_tile = 0u;   // shared-memory address of this tile's 128 column thresholds
                 uint32_t thr_done_bar = 0u;
-                if constexpr (SYM && TC_SYM_THR_WARP) {
+                if constexpr (SYM) {
                     cdir = ui.coldir && ct != ui.row_unit;
                     if (cdir) {   // the threshold warp runs two tiles ahead: this wait is normally a single poll
                         const uint32_t buf = tile_seq & 1u, ph = (tile_seq >> 1) & 1u;
@@ -1047,45 +1045,6 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
                         mbar_wait(bar_thr_full + 8 * buf, ph, p.error_flag);
                         ++tile_seq;
                     }
-                } else if constexpr (SYM) {
-                    // column thresholds of this tile's 128-column half: written to shared memory by the half's first warp
-                    // (double-buffered by tile parity), then one named barrier of the half's four warps.  The writer fetched
-                    // the published bests one tile ahead (nbc*), so that no L2 round trip sits in front of the barrier.
-                    cdir = ui.coldir && ct != ui.row_unit;
-                    uint16_t* tb = thr_buf + (((tile_seq & 1) * 2 + half) * 128);
-                    if (quad == 0) {
-                        constexpr unsigned ENC_POS_INF = 0xff800000u;
-                        if (kt == 0 && cdir) {   // first tile of the unit: nothing was prefetched
-                            const int64_t c = col0 + lane;
-                            nbc0 = c < p.n ? __ldcg(p.best_enc + c) : ENC_POS_INF;
-                            nbc1 = c + 32 < p.n ? __ldcg(p.best_enc + c + 32) : ENC_POS_INF;
-                            nbc2 = c + 64 < p.n ? __ldcg(p.best_enc + c + 64) : ENC_POS_INF;
-                            nbc3 = c + 96 < p.n ? __ldcg(p.best_enc + c + 96) : ENC_POS_INF;
-                        }
-                        if (cdir) {
-                            // float16, rounded DOWN (a lower threshold only adds candidates; 2^-11 against eps = 2^-7), with a
-                            // finite lower bound: the threshold minus a masked (-inf) score is then +inf, never NaN
-                            const unsigned short t0 = __half_as_ushort(__float2half_rd(fmaxf(dec_score(nbc0) - p.eps, -60000.f)));
-                            const unsigned short t1 = __half_as_ushort(__float2half_rd(fmaxf(dec_score(nbc1) - p.eps, -60000.f)));
-                            const unsigned short t2 = __half_as_ushort(__float2half_rd(fmaxf(dec_score(nbc2) - p.eps, -60000.f)));
-                            const unsigned short t3 = __half_as_ushort(__float2half_rd(fmaxf(dec_score(nbc3) - p.eps, -60000.f)));
-                            const uint32_t ta = smem_u32(tb) + 2u * lane;
-                            asm volatile("st.shared.b16 [%0], %1;" ::"r"(ta), "h"(t0) : "memory");
-                            asm volatile("st.shared.b16 [%0], %1;" ::"r"(ta + 64u), "h"(t1) : "memory");
-                            asm volatile("st.shared.b16 [%0], %1;" ::"r"(ta + 128u), "h"(t2) : "memory");
-                            asm volatile("st.shared.b16 [%0], %1;" ::"r"(ta + 192u), "h"(t3) : "memory");
-                        }
-                        if (ui.coldir && kt + 1 < ui.count) {   // next tile of this unit (never the diagonal: ct grows)
-                            const int64_t c = col0 + (int64_t)ui.stride * TC_BN + lane;
-                            nbc0 = c < p.n ? __ldcg(p.best_enc + c) : ENC_POS_INF;
-                            nbc1 = c + 32 < p.n ? __ldcg(p.best_enc + c + 32) : ENC_POS_INF;
-                            nbc2 = c + 64 < p.n ? __ldcg(p.best_enc + c + 64) : ENC_POS_INF;
-                            nbc3 = c + 96 < p.n ? __ldcg(p.best_enc + c + 96) : ENC_POS_INF;
-                        }
-                    }
-                    asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
-                    thr_tile = smem_u32(tb);
-                    ++tile_seq;
                 }
                 mbar_wait_traced(bar_acc_full + 8 * acc, acc_phase, p.error_flag, t_full, tracing);
                 tc_fence_after();
@@ -1163,7 +1122,7 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
                         }
                         epi_chunk<false, SYM>(cx, vb, col0 + 64 * h + 32, plain, cdir, thr_tile + 128u * h + 64u);
                     }
-                    if constexpr (SYM && TC_SYM_THR_WARP) {
+                    if constexpr (SYM) {
                         if (cdir) {   // this warp no longer reads the tile's thresholds
                             __syncwarp();
                             if (lane == 0) mbar_arrive(thr_done_bar);
