@@ -1694,6 +1694,7 @@ static int plan_screen_sym(int64_t n, int part, int parts, const GateSpec* g, Sc
     // stronger sample pays off from 4 parts on (measured at 8 parts, C3: 16 / 32 / 64 tiles -> 3.96 / 3.64 / 3.30 ms for
     // the triangle share against +0.1 ms per 16 tiles here)
     int samples = mode == SYM_BESTS ? (parts >= 4 ? 4 * SYM_SAMPLE_TILES : SYM_SAMPLE_TILES) : SYM_SAMPLE_TILES / parts;
+    if (mode == SYM_BESTS && samples > span / 4) samples = (int)(span / 4);   // small inputs: a sample, not the whole square
     if (samples < 4) samples = 4;
     if (const char* e = getenv("SLIC_SYM_SAMPLES")) {   // experiments only
         const int v = atoi(e);
