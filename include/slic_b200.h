@@ -253,6 +253,13 @@ int slic_scatter_last_wins(const int32_t* values_dev, const int64_t* positions_d
                            int64_t n_out, int32_t fill, int32_t* out_dev, int32_t* out_of_range_dev,
                            slic_stream_t stream);
 
+/* np.unique(labels, return_inverse=True) for int32 labels of any sign (sklearn's check_clusterings / contingency_matrix
+ * behind online_train.py:634,640; datasets/triplets_dataset.py:99-104 for non-dense labels): dense_out[i] = rank of
+ * labels[i] among the distinct values (ascending), uniq_out [capacity n, optional] = the distinct values,
+ * num_out_dev[0] = how many.  Stable radix sort of (label, row), boundary flags, scan. */
+int slic_dense_labels(const int32_t* labels_dev, int64_t n, int32_t* dense_out_dev, int32_t* uniq_out_dev,
+                      int32_t* num_out_dev, slic_stream_t stream);
+
 /* ---- cluster-quality scores ----------------------------------------- */
 /* online_train.py:633-642 calls sklearn's normalized_mutual_info_score and adjusted_mutual_info_score on the true
  * labels and the FINCH labels.  This entry computes their ingredients on the device, following sklearn's arithmetic

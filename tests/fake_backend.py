@@ -125,6 +125,10 @@ class FakeBackend:
         return torch.from_numpy(nn), torch.from_numpy(d.copy()), complete
 
     # label hand-over / cluster-quality scores (slic_scatter_last_wins, slic_cluster_metrics)
+    def dense_labels(self, labels):
+        uniq, inv = np.unique(_np(labels), return_inverse=True)
+        return torch.from_numpy(inv.astype(np.int32)), torch.from_numpy(uniq.astype(np.int32)), len(uniq)
+
     def scatter_last_wins(self, values, positions, n_out, fill=-1):
         v, p = _np(values), _np(positions)
         out = np.full(n_out, fill, dtype=np.int32)

@@ -127,3 +127,22 @@ def test_pdist_matches_torch_restatement(be):
                                    rtol=0, atol=tol)
         np.testing.assert_allclose(cr.pdist(a, 1e-6, metric, backend=be).cpu().numpy(), ro.pdist_v2(a, a, 1e-6, metric),
                                    rtol=0, atol=tol if metric == "cosine" else 4e-3)   # euclidean self-distances: eps * sqrt(d) in the reference
+
+
+@pytest.mark.parametrize("n,lo,hi,seed", [(1, 5, 6, 0), (1000, -50, 50, 1), (240000, 0, 21436, 2), (100000, -2**31, 2**31 - 1, 3),
+                                          (5000, 7, 8, 4)])
+def test_dense_labels_equal_numpy_unique(be, n, lo, hi, seed):
+    """slic_dense_labels = np.unique(labels, return_inverse=True) for int32 labels of either sign (bit-exact)."""
+    from video_similarity_search_b200.clustering import cluster_masks as cm
+    rng = np.random.default_rng(seed)
+    lab = rng.integers(lo, hi, n, dtype=np.int64).astype(np.int32)
+    dense, uniq, count = be.dense_labels(torch.from_numpy(lab).cuda())
+    eu, einv = np.unique(lab, return_inverse=True)
+    assert count == len(eu)
+    assert np.array_equal(uniq.cpu().numpy(), eu) and np.array_equal(dense.cpu().numpy(), einv.astype(np.int32))
+    if n <= 5000:
+        table = cm.label_to_indices(lab, backend=be)
+        assert sorted(table) == eu.tolist()
+        assert all(np.array_equal(table[v], np.where(lab == v)[0]) for v in eu.tolist())
+    with pytest.raises(TypeError):
+        metrics.normalized_mutual_info_score(lab.astype(np.float32), lab, backend=be)

@@ -44,6 +44,7 @@ SIGNATURES = {
     "slic_merge_cluster_sums": [_ptr, _ptr, _ptr, _i64, _i32, _i32, _ptr, _ptr, _ptr, _ptr],
     "slic_label_mask_u8": [_ptr, _i64, _ptr, _i64, _i32, _i32, _ptr, _ptr],
     "slic_label_mask_bits": [_ptr, _i64, _ptr, _i64, _i32, _ptr, _ptr],
+    "slic_dense_labels": [_ptr, _i64, _ptr, _ptr, _ptr, _ptr],
     "slic_scatter_last_wins": [_ptr, _ptr, _i64, _i64, _i32, _ptr, _ptr, _ptr],
     "slic_cluster_metrics": [_ptr, _ptr, _i64, _i32, _i32, _i32, _ptr, _ptr],
     "slic_group_by_label": [_ptr, _i64, _i32, _ptr, _ptr, _ptr],

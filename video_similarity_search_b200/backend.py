@@ -333,6 +333,17 @@ class CudaBackend:
         _lib.call("slic_label_mask_bits", _p(a), na, _p(b), nb, int(negate), _p(out), self._stream())
         return out
 
+    def dense_labels(self, labels):
+        """np.unique(labels, return_inverse=True) on the device for int32 labels (slic_dense_labels).
+        -> (dense int32 [n], uniq int32 [count], count)."""
+        n = labels.shape[0]
+        dense = torch.empty(n, dtype=torch.int32, device=labels.device)
+        uniq = torch.empty(n, dtype=torch.int32, device=labels.device)
+        num = torch.empty(1, dtype=torch.int32, device=labels.device)
+        _lib.call("slic_dense_labels", _p(labels), n, _p(dense), _p(uniq), _p(num), self._stream())
+        count = int(num.item())
+        return dense, uniq[:count], count
+
     def scatter_last_wins(self, values, positions, n_out, fill=-1):
         """out[positions[i]] = values[i] in order of i (slic_scatter_last_wins).  -> (out int32 [n_out], out_of_range int)."""
         out = torch.empty(n_out, dtype=torch.int32, device=values.device)

@@ -98,11 +98,13 @@ def group_by_label(labels, num_labels=None, backend=None):
 
 def label_to_indices(data_labels, backend=None):
     """datasets/triplets_dataset.py:99-104 for arbitrary (not necessarily dense) integer labels:
-    {label: ascending row indices}.  The dense relabelling is host bookkeeping; the grouping runs on
-    the device."""
-    arr = np.asarray(data_labels.cpu() if isinstance(data_labels, torch.Tensor) else data_labels)
-    uniq, inv = np.unique(arr, return_inverse=True)
+    {label: ascending row indices}.  Dense relabelling (slic_dense_labels) and grouping both run on the device."""
     be = backend or _backend.default_backend()
-    order, offsets = group_by_label(inv.astype(np.int32), len(uniq), backend=be)
-    order, offsets = be.to_host(order), be.to_host(offsets)
-    return {uniq[c].item(): order[offsets[c]:offsets[c + 1]].astype(np.int64) for c in range(len(uniq))}
+    if isinstance(data_labels, torch.Tensor):
+        lab = be.to_device(data_labels.detach().reshape(-1), torch.int32)
+    else:
+        lab = be.to_device(np.asarray(data_labels).reshape(-1).astype(np.int32, copy=False), torch.int32)
+    dense, uniq, count = be.dense_labels(lab)                        # np.unique(..., return_inverse=True) on the device
+    order, offsets = be.group_by_label(dense, count)
+    order, offsets, uniq = be.to_host(order), be.to_host(offsets), be.to_host(uniq)
+    return {uniq[c].item(): order[offsets[c]:offsets[c + 1]].astype(np.int64) for c in range(count)}

@@ -8,6 +8,7 @@
 // Each thread produces 16 output bytes (one 128-bit store, coalesced across the warp); the column
 // labels of the 16 columns come through the read-only path and are reused across the rows a CTA walks.
 #include "common.cuh"
+#include "primitives.cuh"
 
 namespace slic {
 
@@ -131,9 +132,53 @@ __global__ void scatter_copy_kernel(const int* __restrict__ values, const int* _
     out[p] = w >= 0 ? values[w] : fill;
 }
 
+// ---- dense relabelling: np.unique(labels, return_inverse=True) for int32 labels ------------------------------
+__global__ void bias_keys_kernel(const int* __restrict__ labels, int64_t n, int* __restrict__ keys) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = labels[i] ^ (int)0x80000000;   // signed order -> order of the bit pattern (what the radix passes see)
+}
+__global__ void flag_boundaries_kernel(const int* __restrict__ sorted_keys, int64_t n, int* __restrict__ flags) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = (i == 0 || sorted_keys[i] != sorted_keys[i - 1]) ? 1 : 0;
+}
+__global__ void assign_dense_ids_kernel(const int* __restrict__ sorted_keys, const int* __restrict__ order,
+                                        const int* __restrict__ flags, const int* __restrict__ before, int64_t n,
+                                        int* __restrict__ dense, int* __restrict__ uniq) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int id = before[i] + flags[i] - 1;   // boundaries at or before position i, minus one
+    dense[order[i]] = id;
+    if (uniq && flags[i]) uniq[id] = sorted_keys[i] ^ (int)0x80000000;
+}
+
 }  // namespace slic
 
 extern "C" {
+
+int slic_dense_labels(const int32_t* labels_dev, int64_t n, int32_t* dense_out_dev, int32_t* uniq_out_dev,
+                      int32_t* num_out_dev, slic_stream_t stream) {
+    using namespace slic;
+    SLIC_REQUIRE(n >= 1 && n < ((int64_t)1 << 31), "dense_labels: bad shape");
+    SLIC_REQUIRE(labels_dev && dense_out_dev && num_out_dev, "dense_labels: null pointer");
+    cudaStream_t st = as_stream(stream);
+    Scratch keys, sorted, order, flags, before;
+    SLIC_CUDA_OK(keys.alloc((size_t)n * sizeof(int), st));
+    SLIC_CUDA_OK(sorted.alloc((size_t)n * sizeof(int), st));
+    SLIC_CUDA_OK(order.alloc((size_t)n * sizeof(int), st));
+    SLIC_CUDA_OK(flags.alloc((size_t)n * sizeof(int), st));
+    SLIC_CUDA_OK(before.alloc((size_t)n * sizeof(int), st));
+    const unsigned blocks = (unsigned)ceil_div(n, 256);
+    bias_keys_kernel<<<blocks, 256, 0, st>>>(labels_dev, n, keys.as<int>());
+    SLIC_LAUNCH_OK();
+    SLIC_PROPAGATE(stable_sort_pairs_i32(keys.as<int>(), nullptr, n, 32, sorted.as<int>(), order.as<int>(), st));
+    flag_boundaries_kernel<<<blocks, 256, 0, st>>>(sorted.as<int>(), n, flags.as<int>());
+    SLIC_LAUNCH_OK();
+    SLIC_PROPAGATE(exclusive_scan_i32(flags.as<int>(), before.as<int>(), n, num_out_dev, st));
+    assign_dense_ids_kernel<<<blocks, 256, 0, st>>>(sorted.as<int>(), order.as<int>(), flags.as<int>(), before.as<int>(), n,
+                                                    dense_out_dev, uniq_out_dev);
+    SLIC_LAUNCH_OK();
+    return SLIC_OK;
+}
 
 int slic_scatter_last_wins(const int32_t* values_dev, const int64_t* positions_dev, int64_t n, int64_t n_out,
                            int32_t fill, int32_t* out_dev, int32_t* out_of_range_dev, slic_stream_t stream) {

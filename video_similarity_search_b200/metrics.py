@@ -14,16 +14,31 @@ from . import backend as _backend
 _EPS = float(np.finfo("float64").eps)
 
 
+_I32 = (-(1 << 31), (1 << 31) - 1)
+
+
 def _dense(be, labels):
     """np.unique(labels, return_inverse=True)[1] (sklearn check_clusterings + contingency_matrix): labels of any
-    integer values -> dense ids; returns (device int32 [n], number of distinct values)."""
+    integer values -> dense ids, computed on the device (slic_dense_labels); returns (int32 [n], distinct values).
+    Integer labels must fit int32 (class and cluster ids do); other label types are rejected."""
     if isinstance(labels, torch.Tensor):
-        t = labels.detach().to(be.device).reshape(-1)
-        uniq, inv = torch.unique(t, return_inverse=True)
-        return inv.to(torch.int32).contiguous(), int(uniq.numel())
-    arr = np.asarray(labels).reshape(-1)
-    uniq, inv = np.unique(arr, return_inverse=True)
-    return be.to_device(inv.astype(np.int32), torch.int32), len(uniq)
+        t = labels.detach().reshape(-1)
+        if t.dtype.is_floating_point or t.dtype == torch.bool:
+            raise TypeError("labels must be integers")
+        if t.dtype == torch.int64 and t.numel() and (int(t.min()) < _I32[0] or int(t.max()) > _I32[1]):
+            raise ValueError("integer labels must fit int32")
+        dev = be.to_device(t, torch.int32)
+    else:
+        arr = np.asarray(labels).reshape(-1)
+        if arr.dtype.kind not in "iu":
+            raise TypeError("labels must be integers")
+        if arr.size and (int(arr.min()) < _I32[0] or int(arr.max()) > _I32[1]):
+            raise ValueError("integer labels must fit int32")
+        dev = be.to_device(arr.astype(np.int32, copy=False), torch.int32)
+    if dev.shape[0] == 0:
+        return dev, 0
+    dense, _, count = be.dense_labels(dev)
+    return dense, count
 
 
 def _generalized_average(u, v, average_method):
