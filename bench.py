@@ -400,7 +400,12 @@ def run_b200(args):
         clear = gap > 2e-6
         parity_nn = bool(np.array_equal(nn_host[rows][clear], enn[clear]))
         t0 = time.perf_counter()
-        co, no, _ = fo.finch(x_host, initial_rank=nn_host)
+        if n <= fo.FLANN_THRESHOLD:
+            # dense mode of the reference (distances kept, min_sim cut): the oracle runs it in full, only its level-0
+            # neighbours are replaced by the GPU's so that float32 tie rows cannot change the partition
+            co, no, _ = fo.finch(x_host, nn0_override=nn_host)
+        else:
+            co, no, _ = fo.finch(x_host, initial_rank=nn_host)
         t_rest = time.perf_counter() - t0
         parity_partition = bool(no == num_clust and np.array_equal(co, c))
         est = t_nn * n / float(sample) + t_rest
