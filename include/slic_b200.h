@@ -142,6 +142,14 @@ int slic_nn_top1_sym_part(const float* unit_dev, const uint16_t* unit_bf16_dev, 
 int slic_unpack_neighbor_keys(const uint64_t* keys_dev, int64_t n, int32_t* idx_out_dev,
                               float* dist_out_dev, int32_t* status_out_dev, slic_stream_t stream);
 
+/* Test hook, host only (no device work): the unit list the symmetric screen would execute for a self-search of n rows
+ * as part `part` of `parts` - mode 0: pre-pass + triangle share, 1: row-bests pre-pass only, 2: triangle share only;
+ * gated_chunks > 0: with upload gates (slic_finch_host).  units_out_host [capacity, 6] int32 (optional) receives per unit
+ * {row unit, first column tile, tile count, tile stride, gate or -1, column-direction flag}; a unit covers the 256 x 256
+ * tiles (row unit, first + k * stride), k < count.  Lets a CPU test check that the parts tile the triangle exactly. */
+int slic_debug_sym_plan(int64_t n, int32_t part, int32_t parts, int32_t mode, int32_t gated_chunks,
+                        int32_t* units_out_host, int64_t capacity, int64_t* num_units_out_host);
+
 /* Debug / test hook: raw bf16-screen scores of one 128 x 256 tile region, written as float
  * [nq, n] (small shapes only).  Lets the tests check the tcgen05 path element by element. */
 int slic_screen_scores_debug(const uint16_t* q_bf16_dev, int64_t nq, const uint16_t* x_bf16_dev,

@@ -2280,6 +2280,37 @@ int slic_nn_top1_sym_part(const float* unit_dev, const uint16_t* bf16_dev, int64
     return SLIC_OK;
 }
 
+int slic_debug_sym_plan(int64_t n, int32_t part, int32_t parts, int32_t mode, int32_t gated_chunks, int32_t* units_out_host,
+                        int64_t capacity, int64_t* num_units_out_host) {
+    using namespace slic;
+    SLIC_REQUIRE(n > 1 && n < ((int64_t)1 << 31) && num_units_out_host, "debug_sym_plan: bad arguments");
+    SLIC_REQUIRE(mode >= 0 && mode <= 2, "debug_sym_plan: mode must be 0 (full), 1 (row bests) or 2 (triangle)");
+    SLIC_REQUIRE(gated_chunks >= 0 && gated_chunks < 4095, "debug_sym_plan: bad chunk count");
+    GateSpec gs = {reinterpret_cast<const int*>(num_units_out_host) /* never dereferenced by the planner */, 0, 0};
+    if (gated_chunks > 0) {
+        gs.chunk_rows = ceil_div(ceil_div(n, gated_chunks), 256) * 256;
+        gs.num_chunks = (int)ceil_div(n, gs.chunk_rows);
+    }
+    ScreenPlan pl;
+    std::vector<int4> table;
+    SLIC_PROPAGATE(plan_screen_sym(n, part, parts, gated_chunks > 0 ? &gs : nullptr, &pl, &table, (SymMode)mode));
+    *num_units_out_host = (int64_t)table.size();
+    if (units_out_host) {
+        SLIC_REQUIRE(capacity >= (int64_t)table.size(), "debug_sym_plan: unit buffer too small");
+        for (size_t u = 0; u < table.size(); ++u) {
+            const int4 e = table[u];
+            int32_t* o = units_out_host + 6 * u;
+            o[0] = e.x;                                  // row unit (256 rows)
+            o[1] = e.y;                                  // first column tile
+            o[2] = e.z & 0xffff;                         // tile count
+            o[3] = (int)((unsigned)e.z >> 16);           // tile stride
+            o[4] = (e.w & 0xfff) - 1;                    // gate (-1: none)
+            o[5] = (e.w >> 28) & 1;                      // column direction (triangle unit)
+        }
+    }
+    return SLIC_OK;
+}
+
 int slic_unpack_neighbor_keys(const uint64_t* keys_dev, int64_t n, int32_t* idx_out_dev, float* dist_out_dev,
                               int32_t* status_out_dev, slic_stream_t stream) {
     using namespace slic;
