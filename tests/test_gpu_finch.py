@@ -180,3 +180,30 @@ def test_host_entry_initial_rank_and_overflow_path(be, monkeypatch):
     assert num2 == no and np.array_equal(c2, co)
     c3, num3, _ = FINCH(torch.from_numpy(x).cuda(), initial_rank=rank, backend=be, verbose=False)
     assert num3 == no and np.array_equal(c3, co)
+
+
+def test_finch_large_initial_rank_exercises_the_wide_label_sort(be):
+    """600 000 rows with caller-supplied first neighbours (groups of 64 rows): the driver cannot assume every
+    component has two members, sizes its label sort for up to N clusters (20 key bits: three one-sweep passes, sorted
+    keys not kept) and reads the real count (9 375) from the device.  Compared with the oracle on the same neighbours."""
+    from video_similarity_search_b200.clustering.finch import FINCH
+    n, d, g = 600000, 16, 64
+    rng = np.random.default_rng(5)
+    centres = rng.standard_normal((n // g, d)).astype(np.float32) * 4
+    x = (np.repeat(centres, g, axis=0) + 0.1 * rng.standard_normal((n, d))).astype(np.float32)
+    rank = (np.arange(n) // g) * g
+    rank[::g] += 1                      # the group's first row points at its second
+    c, num_clust, _ = FINCH(x, initial_rank=rank, backend=be, verbose=False)
+    co, no, _ = fo.finch(x, initial_rank=rank)
+    assert num_clust[0] == n // g and num_clust == no
+    assert np.array_equal(c, co)
+
+
+def test_finch_rejects_out_of_range_initial_rank(be):
+    from video_similarity_search_b200 import _lib
+    from video_similarity_search_b200.clustering.finch import FINCH
+    x = synth.gaussian_mixture(500, 32, 5, 1)
+    rank = np.arange(500)[::-1].copy()
+    rank[17] = 500
+    with pytest.raises(_lib.SlicError):
+        FINCH(x, initial_rank=rank, backend=be, verbose=False)

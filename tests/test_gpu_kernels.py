@@ -33,7 +33,11 @@ def dev(be, a, dtype=None):
 # integer primitives through their public users
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n,c", [(1, 1), (33, 5), (5000, 700), (4097, 4097), (300000, 21436), (100000, 3),
-                                 (70000, 70000)])
+                                 (70000, 70000),
+                                 # one-sweep sort: 17-18 key bits take two 9-bit passes, 19-24 three 8-bit passes,
+                                 # 25+ four; tile boundaries (4096 keys) and the scan's (2048 items) at +-1
+                                 (300000, 150000), (1000003, 400000), (4096, 2048), (4097, 2049), (8191, 4095),
+                                 (2048, 300), (2049, 2049), (600000, 20000000)])
 def test_group_by_label_bit_exact(be, n, c):
     rng = np.random.default_rng(n + c)
     lab = rng.integers(0, c, n).astype(np.int32)

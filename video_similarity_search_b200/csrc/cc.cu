@@ -11,6 +11,7 @@
 // Bound: latency / HBM.  Algorithmic bytes ~ 8 n (nn in, labels out); sibling-pair distances are the
 // only floating-point work and touch 2 rows per pair.
 #include "common.cuh"
+#include "lookback.cuh"
 #include "primitives.cuh"
 
 namespace slic {
@@ -38,20 +39,29 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
     }
 }
 
-__global__ void cc_init_kernel(int* parent, int64_t n) {
+__global__ void cc_init_kernel(int* parent, int* size, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) parent[i] = (int)i;
+    if (i < n) {
+        parent[i] = (int)i;
+        if (size) size[i] = 0;
+    }
 }
 
 // direct links i - nn[i]; with the filter a link survives iff w * d <= min_sim (finch.py:51-52)
 template <typename T>
 __global__ void cc_union_direct_kernel(const int* __restrict__ nn, int64_t n, const T* __restrict__ dist_nn,
-                                       int use_filter, double min_sim, int* parent) {
+                                       int use_filter, double min_sim, const float* __restrict__ min_sim_dev, int* parent,
+                                       int* __restrict__ bad) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int j = nn[i];
-    if (j < 0 || j >= n || j == i) return;
+    if (j < 0 || j >= n) {   // the reference's sparse matrix constructor raises on such an index
+        if (bad) atomicAdd(bad, 1);
+        return;
+    }
+    if (j == i) return;
     if (use_filter) {
+        if (min_sim_dev) min_sim = (double)*min_sim_dev;   // the float32 value of finch.py:144, still on the device
         double w = (nn[j] == (int)i) ? 2.0 : 1.0;
         if ((double)dist_nn[i] * w > min_sim) return;
     }
@@ -69,8 +79,10 @@ __global__ void __launch_bounds__(256) sibling_pairs_kernel(const int* __restric
                                                             const T* __restrict__ unit, int d, double min_sim,
                                                             int* parent, unsigned int* max_bits,
                                                             unsigned long long* aux_out = nullptr,
-                                                            const unsigned long long* aux_in = nullptr) {
+                                                            const unsigned long long* aux_in = nullptr,
+                                                            const float* __restrict__ min_sim_dev = nullptr) {
     const int lane = threadIdx.x & 31;
+    if (MODE == 0 && min_sim_dev) min_sim = (double)*min_sim_dev;
     const int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (p >= n) return;
     const int hub = sorted_nn[p];
@@ -140,18 +152,60 @@ __global__ void unpack_pair_kernel(const unsigned long long* packed, int* pair_o
     pair_out[1] = (int)(*packed & 0xffffffffull);
 }
 
-__global__ void cc_flatten_kernel(int* parent, int64_t n, int* root, int* is_root) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int r = uf_find(parent, (int)i);
-    root[i] = r;
-    is_root[i] = (r == (int)i) ? 1 : 0;
+// root[i] = smallest member of i's component; size[root] (optional) = members of the component
+__global__ void cc_flatten_kernel(int* parent, int64_t n, int* root, int* size) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < n;
+    int r = -1 - lane;
+    if (valid) {
+        r = uf_find(parent, (int)i);
+        root[i] = r;
+    }
+    if (size) {   // warp-aggregated: neighbouring rows often share a root
+        const unsigned peers = __match_any_sync(0xffffffffu, r);
+        if (valid && (__ffs(peers) - 1) == lane) atomicAdd(&size[r], __popc(peers));
+    }
 }
 
+// ONE scan over the rows yields, at every root, its rank among the roots (= scipy's component number: components are
+// numbered by smallest member) and the exclusive sum of the earlier roots' sizes (= the CSR offset of its cluster)
+struct RootScanOp {
+    const int* root;
+    const int* csize;   // nullptr: ranks only
+    int64_t n;
+    int* rank;
+    int* off;
+    int* num_clust;
+    __device__ int64_t size() const { return n; }
+    __device__ unsigned long long load(int64_t i) const {
+        const bool is_root = root[i] == (int)i;
+        return lb_pair(is_root ? 1 : 0, (is_root && csize) ? csize[i] : 0);
+    }
+    __device__ void store(int64_t i, unsigned long long excl, unsigned long long) const {
+        rank[i] = lb_a(excl);
+        if (off) off[i] = lb_b(excl);
+    }
+    __device__ void finish(unsigned long long t) const { *num_clust = lb_a(t); }
+};
+
+// labels[i] = rank of i's root; with csr outputs every root also writes its cluster's CSR offset and row count
 __global__ void cc_relabel_kernel(const int* __restrict__ root, const int* __restrict__ rank, int64_t n,
-                                  int* __restrict__ labels) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) labels[i] = rank[root[i]];
+                                  int* __restrict__ labels, const int* __restrict__ off, const int* __restrict__ size,
+                                  const int* __restrict__ num_clust, int* __restrict__ csr_offsets,
+                                  int* __restrict__ csr_counts) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int r = root[i];
+    const int lab = rank[r];
+    labels[i] = lab;
+    if (csr_offsets) {
+        if (r == (int)i) {
+            csr_offsets[lab] = off[i];
+            if (csr_counts) csr_counts[lab] = size[i];
+        }
+        if (i == 0) csr_offsets[*num_clust] = (int)n;
+    }
 }
 
 __global__ void compose_kernel(const int* __restrict__ prev, const int* __restrict__ u, int64_t n,
@@ -178,17 +232,24 @@ static int group_rows(const int* labels, int64_t n, int64_t num_labels, int* ord
 }
 
 template <typename T>
-static int components_impl(const int* nn, int64_t n, int use_filter, double min_sim, const T* unit, int d,
-                           const T* dist_nn, int* labels, int* num_clust, cudaStream_t st) {
+static int components_impl(const int* nn, int64_t n, int use_filter, double min_sim, const float* min_sim_dev,
+                           const T* unit, int d, const T* dist_nn, int* labels, int* num_clust, int* csr_offsets,
+                           int* csr_counts, cudaStream_t st, int* bad = nullptr) {
     const unsigned blocks = (unsigned)ceil_div(n, 256);
-    Scratch parent, root, is_root, rank;
+    const bool csr = csr_offsets != nullptr;
+    Scratch parent, root, rank, size, off, state;
     SLIC_CUDA_OK(parent.alloc(n * sizeof(int), st));
     SLIC_CUDA_OK(root.alloc(n * sizeof(int), st));
-    SLIC_CUDA_OK(is_root.alloc(n * sizeof(int), st));
     SLIC_CUDA_OK(rank.alloc(n * sizeof(int), st));
-    cc_init_kernel<<<blocks, 256, 0, st>>>(parent.as<int>(), n);
+    if (csr) {
+        SLIC_CUDA_OK(size.alloc(n * sizeof(int), st));
+        SLIC_CUDA_OK(off.alloc(n * sizeof(int), st));
+    }
+    SLIC_CUDA_OK(state.alloc(lookback_state_bytes(n), st));
+    SLIC_CUDA_OK(cudaMemsetAsync(state.ptr, 0, lookback_state_bytes(n), st));
+    cc_init_kernel<<<blocks, 256, 0, st>>>(parent.as<int>(), csr ? size.as<int>() : nullptr, n);
     SLIC_LAUNCH_OK();
-    cc_union_direct_kernel<T><<<blocks, 256, 0, st>>>(nn, n, dist_nn, use_filter, min_sim, parent.as<int>());
+    cc_union_direct_kernel<T><<<blocks, 256, 0, st>>>(nn, n, dist_nn, use_filter, min_sim, min_sim_dev, parent.as<int>(), bad);
     SLIC_LAUNCH_OK();
     if (use_filter) {
         // without the filter every sibling pair is already joined through its hub
@@ -198,15 +259,32 @@ static int components_impl(const int* nn, int64_t n, int use_filter, double min_
         SLIC_CUDA_OK(offsets.alloc((n + 1) * sizeof(int), st));
         SLIC_PROPAGATE(group_rows(nn, n, n, order.as<int>(), sorted.as<int>(), offsets.as<int>(), st));
         sibling_pairs_kernel<T, 0><<<(unsigned)ceil_div(n, 8), 256, 0, st>>>(
-            order.as<int>(), sorted.as<int>(), offsets.as<int>(), n, unit, d, min_sim, parent.as<int>(), nullptr);
+            order.as<int>(), sorted.as<int>(), offsets.as<int>(), n, unit, d, min_sim, parent.as<int>(), nullptr, nullptr,
+            nullptr, min_sim_dev);
         SLIC_LAUNCH_OK();
     }
-    cc_flatten_kernel<<<blocks, 256, 0, st>>>(parent.as<int>(), n, root.as<int>(), is_root.as<int>());
+    cc_flatten_kernel<<<blocks, 256, 0, st>>>(parent.as<int>(), n, root.as<int>(), csr ? size.as<int>() : nullptr);
     SLIC_LAUNCH_OK();
-    SLIC_PROPAGATE(exclusive_scan_i32(is_root.as<int>(), rank.as<int>(), n, num_clust, st));
-    cc_relabel_kernel<<<blocks, 256, 0, st>>>(root.as<int>(), rank.as<int>(), n, labels);
+    RootScanOp op = {root.as<int>(), csr ? size.as<int>() : nullptr, n, rank.as<int>(), csr ? off.as<int>() : nullptr,
+                     num_clust};
+    lookback_scan_kernel<RootScanOp><<<lookback_grid(n), LB_THREADS, 0, st>>>(op, state.as<unsigned long long>());
+    SLIC_LAUNCH_OK();
+    cc_relabel_kernel<<<blocks, 256, 0, st>>>(root.as<int>(), rank.as<int>(), n, labels, off.as<int>(), size.as<int>(),
+                                              num_clust, csr_offsets, csr_counts);
     SLIC_LAUNCH_OK();
     return SLIC_OK;
+}
+
+// driver-internal form (finch_driver.cu): min_sim may still live on the device, and the CSR row pointers / row counts
+// of the clusters (what the means need) come out of the same scan.  csr_offsets: room for (clusters + 1) ints.
+int finch_components_csr(const int* nn, int64_t n, int use_filter, const float* min_sim_dev, const void* unit, int d,
+                         int dtype, const void* dist_nn, int* labels, int* num_clust_dev, int* csr_offsets,
+                         int* csr_counts, cudaStream_t st, int* bad_count_dev) {
+    if (use_filter && dtype == SLIC_F64)
+        return components_impl<double>(nn, n, 1, 0.0, min_sim_dev, (const double*)unit, d, (const double*)dist_nn, labels,
+                                       num_clust_dev, csr_offsets, csr_counts, st, bad_count_dev);
+    return components_impl<float>(nn, n, use_filter, 0.0, min_sim_dev, (const float*)unit, d, (const float*)dist_nn, labels,
+                                  num_clust_dev, csr_offsets, csr_counts, st, bad_count_dev);
 }
 
 template <typename T>
@@ -285,10 +363,12 @@ int slic_finch_components(const int32_t* nn_dev, int64_t n, int32_t use_filter, 
         return SLIC_OK;
     }
     if (use_filter && dtype == SLIC_F64)
-        return slic::components_impl<double>(nn_dev, n, 1, min_sim, (const double*)unit_dev, d,
-                                             (const double*)dist_nn_dev, labels_out_dev, num_clust_out_dev, st);
-    return slic::components_impl<float>(nn_dev, n, use_filter, min_sim, (const float*)unit_dev, d,
-                                        (const float*)dist_nn_dev, labels_out_dev, num_clust_out_dev, st);
+        return slic::components_impl<double>(nn_dev, n, 1, min_sim, nullptr, (const double*)unit_dev, d,
+                                             (const double*)dist_nn_dev, labels_out_dev, num_clust_out_dev, nullptr,
+                                             nullptr, st);
+    return slic::components_impl<float>(nn_dev, n, use_filter, min_sim, nullptr, (const float*)unit_dev, d,
+                                        (const float*)dist_nn_dev, labels_out_dev, num_clust_out_dev, nullptr, nullptr,
+                                        st);
 }
 
 int slic_finch_min_sim(const int32_t* nn_dev, int64_t n, const void* unit_dev, int32_t d, int32_t dtype,

@@ -86,12 +86,57 @@ bool screen_can_overlap_upload(int64_t n, int d_pad, int guest_threads, int gues
 int normalize_kernel_shape(int* threads, int* regs);
 // true: a self-search of n rows runs the symmetric screen (upper-triangular tiles, row + column filters)
 bool screen_self_search_is_symmetric(int64_t n);
+// stats_ext (device, 8 ints, optional): asynchronous mode - the call never waits for the device and leaves
+// {[1] rows still to be finished exactly, [4] pipeline error, [5] candidate-log overflow} there; any non-zero value
+// means the result is incomplete and the search must be repeated through the synchronous path (slic_nn_top1).
 int nn_top1_f32_gated(const float* q_unit, const uint16_t* q_bf16, int64_t nq, const float* x_unit,
                       const uint16_t* x_bf16, int64_t n, int d, int d_pad, int64_t self_offset, float eps, int* idx_out,
                       float* dist_out, int* stats_out, const GateSpec* gate, AfterScreenFn after, void* after_ctx,
-                      cudaStream_t st);
+                      cudaStream_t st, int* stats_ext = nullptr);
+// self-search of all rows (first neighbour + distance in `dtype`), asynchronous as above
+int nn_top1_self_async(const void* unit, const uint16_t* ub, int64_t n, int d, int d_pad, int dtype, int* idx_out,
+                       void* dist_out, int* stats_ext, cudaStream_t st);
 
 __host__ __device__ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- driver-internal forms of K2 / K3 (finch_driver.cu): counts stay on the device --------------------------------
+// cc.cu: components of the first-neighbour graph; min_sim (when filtering) is read from device memory; csr_offsets
+// [clusters + 1] / csr_counts [clusters] (optional) receive the CSR row pointers and row counts of the clusters.
+int finch_components_csr(const int* nn, int64_t n, int use_filter, const float* min_sim_dev, const void* unit, int d,
+                         int dtype, const void* dist_nn, int* labels, int* num_clust_dev, int* csr_offsets,
+                         int* csr_counts, cudaStream_t st, int* bad_count_dev = nullptr /* += indices outside [0, n) */);
+// segmean.cu: order = stable argsort(labels); num_labels_bound only sizes the radix passes
+int order_rows_by_label(const int* labels, int64_t n, int64_t num_labels_bound, int* order, cudaStream_t st);
+// segmean.cu: sums / counts / means of the clusters from their CSR grouping; num_clust_dev (optional) = actual count
+// on the device, num_clust then being an upper bound that sizes temporaries and grids
+template <typename T>
+int cluster_sums_csr(const T* data, const int* weights, const int* order, const int* offsets, int64_t n, int d,
+                     int num_clust, const int* num_clust_dev, double* sums_out, int* counts_out, double* means_out,
+                     cudaStream_t st);
+
+// finch_small.cu: all remaining levels of a hierarchy whose current level has <= SMALL_LEVEL_MAX_ROWS clusters, in one
+// cooperative launch with the level loop and the exit rules of finch.py:151-163 on the device.
+constexpr int SMALL_LEVEL_MAX_ROWS = 2048;
+struct SmallLevelsArgs {
+    int64_t n_rows;          // N: rows of the original matrix
+    int d;
+    int capacity;            // label columns available in `cols`
+    int* cols;               // [capacity][N] composed labels, column l = partition l (columns < levels are filled)
+    int* summary;            // [0] levels kept (in / out), [1] status out (0 ok, 1 more levels than capacity, 2 the
+                             // entering level has more than SMALL_LEVEL_MAX_ROWS clusters), [2 + l] clusters of level l
+    double* sums[2];         // [rows of the entering level, d] each; index 0 holds the entering level's state
+    int* counts[2];
+    double* means[2];
+    double* unit;            // [rows, d]
+    double* gram;            // small_levels_gram_elems(rows) doubles
+    int* nn;                 // [rows]
+    double* dist;            // [rows]
+    int* parent;             // [rows]
+    int use_filter;          // finch.py:51-52 applies (level 0 had dense distances and ensure_early_exit)
+    const float* min_sim_dev;
+};
+size_t small_levels_gram_elems(int64_t m);
+int launch_small_levels(const SmallLevelsArgs& args, cudaStream_t st);
 
 // ---- device helpers ---------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {

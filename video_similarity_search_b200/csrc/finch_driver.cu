@@ -47,34 +47,36 @@ static cudaEvent_t g_up0 = nullptr, g_up1 = nullptr, g_t0 = nullptr, g_t_search 
 
 static int d_pad_of(int d) { return (d + 63) / 64 * 64; }
 
-// 64-byte pinned mailbox for the per-level scalar read-backs (a pageable D2H costs an extra staging hop)
-static int mailbox(void** out) {
-    static thread_local void* box = nullptr;
-    if (!box) SLIC_CUDA_OK(cudaHostAlloc(&box, 64, cudaHostAllocDefault));
-    *out = box;
-    return SLIC_OK;
-}
-
-static int read_back(void* dst_host, const void* src_dev, size_t bytes, cudaStream_t st) {
-    void* box;
-    SLIC_PROPAGATE(mailbox(&box));
-    SLIC_CUDA_OK(cudaMemcpyAsync(box, src_dev, bytes, cudaMemcpyDeviceToHost, st));
-    SLIC_CUDA_OK(cudaStreamSynchronize(st));
-    memcpy(dst_host, box, bytes);
-    return SLIC_OK;
-}
-
-struct ColumnPtrs {
-    const int* col[FINCH_MAX_LEVELS];
+// Pinned mailbox for the read-backs of a call (a pageable D2H costs an extra staging hop): ints [0, 16) receive the
+// per-level block {search counters [8], cluster count}, ints [16, 16 + 2 + 64] the final summary, then min_sim.
+constexpr int MB_LEVEL = 0, MB_SUMMARY = 16, MB_MIN_SIM = MB_SUMMARY + 2 + FINCH_MAX_LEVELS, MB_INTS = MB_MIN_SIM + 2;
+struct Mailbox {
+    int* in = nullptr;    // device -> host
+    int* out = nullptr;   // host -> device (the summary seed)
+    cudaEvent_t ev = nullptr;
 };
+static int mailbox(Mailbox** out) {
+    static thread_local Mailbox mb;
+    if (!mb.in) {
+        SLIC_CUDA_OK(cudaHostAlloc((void**)&mb.in, MB_INTS * sizeof(int), cudaHostAllocDefault));
+        SLIC_CUDA_OK(cudaHostAlloc((void**)&mb.out, MB_INTS * sizeof(int), cudaHostAllocDefault));
+        SLIC_CUDA_OK(cudaEventCreateWithFlags(&mb.ev, cudaEventDisableTiming));
+    }
+    *out = &mb;
+    return SLIC_OK;
+}
 
-// out[i, l] = col[l][i]: the [N, P] C-contiguous matrix np.column_stack builds (finch.py:157)
-__global__ void stack_columns_kernel(ColumnPtrs cols, int levels, int64_t n, int* __restrict__ out) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n * levels) return;
-    const int64_t i = t / levels;
-    const int l = (int)(t % levels);
-    out[t] = cols.col[l][i];
+// out[i, l] = cols[l][i] for l < *levels: the [N, P] C-contiguous matrix np.column_stack builds (finch.py:157).
+// P is read from device memory (the level loop may have ended on the device, finch_small.cu).
+__global__ void stack_columns_kernel(const int* __restrict__ cols, const int* __restrict__ levels_dev, int64_t n,
+                                     int* __restrict__ out) {
+    const int levels = *levels_dev;
+    const int64_t total = n * levels, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int64_t i = t / levels;
+        const int l = (int)(t % levels);
+        out[t] = cols[(int64_t)l * n + i];
+    }
 }
 
 // opens upload gate `g` (own kernel, one warp: a cudaMemsetAsync may be a driver kernel of unknown shape, and whatever
@@ -86,9 +88,13 @@ __global__ void open_gate_kernel(int* gate) {
     }
 }
 
-__global__ void convert_rank_kernel(const int64_t* __restrict__ in, int64_t n, int* __restrict__ out) {
+// initial_rank (int64, finch.py:22-23) -> int32; entries outside [0, n) are counted (the reference would raise)
+__global__ void convert_rank_kernel(const int64_t* __restrict__ in, int64_t n, int* __restrict__ out, int* __restrict__ bad) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (int)in[i];
+    if (i >= n) return;
+    const int64_t v = in[i];
+    out[i] = (int)v;
+    if (v < 0 || v >= n) atomicAdd(bad, 1);
 }
 
 typedef std::unique_ptr<Scratch> ScratchPtr;
@@ -99,98 +105,245 @@ struct Level0 {
     const float* dist;    // [n] or nullptr
     const float* unit;    // [n, d] or nullptr
     bool dense;           // the reference would hold a dense distance matrix (len(orig_dist) != 0, finch.py:142)
+    // The level-0 search was launched asynchronously: its counters land in async_stats (device, 16 ints: [1] rows left
+    // unsettled, [4] pipeline error, [5] log overflow; [8] is the driver's cluster count slot).  When any is set the
+    // driver repeats the search synchronously through slic_nn_top1 on (retry_unit, retry_ub).
+    int* async_stats = nullptr;
+    const uint16_t* retry_ub = nullptr;
+    int* retry_nn = nullptr;
+    float* retry_dist = nullptr;
+    // every row has a first neighbour other than itself (our own searches): each component then has >= 2 rows
+    bool no_self_links = false;
 };
 
-// clust_rank (finch.py:22-38) for a float64 level: unit rows, first neighbours, distances
-static int rank_f64(const double* mat, int64_t n, int d, Scratch& unit, Scratch& nn, Scratch& dist, cudaStream_t st) {
-    const int dp = d_pad_of(d);
-    const bool screen = n >= SCREEN_MIN_ROWS;
-    Scratch ub;
-    SLIC_CUDA_OK(unit.alloc((size_t)n * d * sizeof(double), st));
-    SLIC_CUDA_OK(nn.alloc((size_t)n * sizeof(int), st));
-    SLIC_CUDA_OK(dist.alloc((size_t)n * sizeof(double), st));
-    if (screen) SLIC_CUDA_OK(ub.alloc((size_t)n * dp * 2, st));
-    SLIC_PROPAGATE(slic_normalize_rows(mat, n, d, SLIC_F64, unit.ptr, nullptr, screen ? ub.as<uint16_t>() : nullptr, dp, st));
-    if (screen)
-        return slic_nn_top1(unit.ptr, ub.as<uint16_t>(), n, unit.ptr, ub.as<uint16_t>(), n, d, dp, SLIC_F64, 0, 0.f,
-                            nn.as<int32_t>(), dist.ptr, nullptr, st);
-    return slic_nn_exact_top1(unit.ptr, nullptr, n, unit.ptr, n, d, SLIC_F64, 0, nn.as<int32_t>(), dist.ptr, st);
-}
+static int d_pad_of_(int d) { return (d + 63) / 64 * 64; }
 
 // Everything after the level-0 search.  labels_out: device [n, capacity] ints, filled as [n, P] row-major.
+//
+// Host synchronisations: one per level driven from here (levels of more than 2048 clusters: the cluster count sizes
+// the next level's launches) + one at the end; every one of them is placed AFTER the next batch of device work has
+// been enqueued, so the device never waits for the host.  Levels of <= 2048 clusters run inside ONE cooperative
+// launch with the loop on the device (finch_small.cu).
 static int finch_levels(const float* data, int64_t n, int d, const Level0& l0, bool ensure_early_exit, int capacity,
                         int* labels_out, int* num_clust_host, int* num_levels_host, float* min_sim_host,
                         int* has_min_sim_host, cudaStream_t st) {
-    std::vector<ScratchPtr> cols;     // composed labels of every kept level, [n] each
+    Mailbox* mb;
+    SLIC_PROPAGATE(mailbox(&mb));
+    const int dp = d_pad_of_(d);
     std::vector<int> num_clust;
-    Scratch count_dev;
-    SLIC_CUDA_OK(count_dev.alloc(sizeof(int), st));
-
-    // level 0: components of the first-neighbour graph (finch.py:136), centroids (:137)
-    cols.push_back(new_scratch());
-    SLIC_CUDA_OK(cols[0]->alloc((size_t)n * sizeof(int), st));
-    SLIC_PROPAGATE(slic_finch_components(l0.nn, n, 0, 0.0, nullptr, 0, SLIC_F32, nullptr, cols[0]->as<int32_t>(),
-                                         count_dev.as<int32_t>(), st));
-    int cur = 0;
-    SLIC_PROPAGATE(read_back(&cur, count_dev.ptr, sizeof(int), st));
-    num_clust.push_back(cur);
-    ScratchPtr sums = new_scratch(), counts = new_scratch(), means = new_scratch();
-    SLIC_CUDA_OK(sums->alloc((size_t)cur * d * sizeof(double), st));
-    SLIC_CUDA_OK(counts->alloc((size_t)cur * sizeof(int), st));
-    SLIC_CUDA_OK(means->alloc((size_t)cur * d * sizeof(double), st));
-    SLIC_PROPAGATE(slic_cluster_sums(data, cols[0]->as<int32_t>(), n, d, cur, sums->as<double>(), counts->as<int32_t>(),
-                                     means->as<double>(), st));
-
-    bool have_min_sim = false;
-    float min_sim = 0.f;
-    if (ensure_early_exit && l0.dense && l0.dist && l0.unit && n > 1) {    // finch.py:142-144
-        Scratch ms;
-        SLIC_CUDA_OK(ms.alloc(sizeof(float), st));
-        SLIC_PROPAGATE(slic_finch_min_sim(l0.nn, n, l0.unit, d, SLIC_F32, l0.dist, ms.as<float>(), st));
-        SLIC_PROPAGATE(read_back(&min_sim, ms.ptr, sizeof(float), st));
-        have_min_sim = true;
+    Scratch cols, blk0, ms, csr_off, csr_cnt, summary;
+    SLIC_CUDA_OK(cols.alloc((size_t)n * capacity * sizeof(int), st));
+    SLIC_CUDA_OK(csr_off.alloc((size_t)(n + 1) * sizeof(int), st));
+    SLIC_CUDA_OK(csr_cnt.alloc((size_t)n * sizeof(int), st));
+    SLIC_CUDA_OK(ms.alloc(2 * sizeof(float), st));
+    SLIC_CUDA_OK(summary.alloc((2 + FINCH_MAX_LEVELS) * sizeof(int), st));
+    int* blk = l0.async_stats;
+    if (!blk) {
+        SLIC_CUDA_OK(blk0.alloc(16 * sizeof(int), st));
+        SLIC_CUDA_OK(cudaMemsetAsync(blk0.ptr, 0, 16 * sizeof(int), st));
+        blk = blk0.as<int>();
     }
+    const bool have_min_sim = ensure_early_exit && l0.dense && l0.dist && l0.unit && n > 1;    // finch.py:142-144
 
+    // ---- level 0: components of the first-neighbour graph (finch.py:136), centroids (:137), min_sim (:142-144) ----
+    ScratchPtr sums = new_scratch(), means = new_scratch(), counts_own = new_scratch();
+    int* counts = csr_cnt.as<int>();   // level 0: the row counts come out of the components pass
+    int cur = 0;
+    int64_t bound = (l0.no_self_links && n > 1) ? n / 2 : n;
+    for (int attempt = 0;; ++attempt) {
+        SLIC_PROPAGATE(finch_components_csr(l0.nn, n, 0, nullptr, nullptr, 0, SLIC_F32, nullptr, cols.as<int>(), blk + 8,
+                                            csr_off.as<int>(), csr_cnt.as<int>(), st, blk + 9));
+        SLIC_CUDA_OK(cudaMemcpyAsync(mb->in + MB_LEVEL, blk, 10 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        SLIC_CUDA_OK(cudaEventRecord(mb->ev, st));
+        // the means are enqueued before the host knows the cluster count (it lives on the device; `bound` sizes buffers)
+        sums = new_scratch();
+        means = new_scratch();
+        SLIC_CUDA_OK(sums->alloc((size_t)bound * d * sizeof(double), st));
+        SLIC_CUDA_OK(means->alloc((size_t)bound * d * sizeof(double), st));
+        {
+            Scratch order;
+            SLIC_CUDA_OK(order.alloc((size_t)n * sizeof(int), st));
+            SLIC_PROPAGATE(order_rows_by_label(cols.as<int>(), n, bound, order.as<int>(), st));
+            SLIC_PROPAGATE(cluster_sums_csr<float>(data, nullptr, order.as<int>(), csr_off.as<int>(), n, d, (int)bound,
+                                                   blk + 8, sums->as<double>(), nullptr, means->as<double>(), st));
+        }
+        if (have_min_sim)
+            SLIC_PROPAGATE(slic_finch_min_sim(l0.nn, n, l0.unit, d, SLIC_F32, l0.dist, ms.as<float>(), st));
+        SLIC_CUDA_OK(cudaEventSynchronize(mb->ev));
+        const int* s = mb->in + MB_LEVEL;
+        cur = s[8];
+        if (s[9] != 0 && !(s[1] | s[4] | s[5])) {   // finch.py:41-43 would raise on such an index (scipy: out of bounds)
+            set_error("finch: %d first-neighbour indices lie outside [0, n)", s[9]);
+            return SLIC_ERR_INVALID_ARG;
+        }
+        if (l0.retry_nn && attempt == 0 && (s[1] | s[4] | s[5])) {
+            if (s[4] != 0 && s[4] != 2) {
+                set_error("nn_screen_kernel: pipeline barrier timed out");
+                return SLIC_ERR_CUDA;
+            }
+            // rows left to the exact finisher, or a full candidate log (degenerate input): the synchronous entry has the
+            // fallbacks; everything enqueued above is repeated on its result
+            SLIC_PROPAGATE(slic_nn_top1(l0.unit, l0.retry_ub, n, l0.unit, l0.retry_ub, n, d, dp, SLIC_F32, 0, 0.f,
+                                        l0.retry_nn, l0.retry_dist, nullptr, st));
+            SLIC_CUDA_OK(cudaMemsetAsync(blk, 0, 16 * sizeof(int), st));
+            continue;
+        } else if (s[1] | s[4] | s[5]) {
+            set_error("finch: the level-0 neighbour search did not complete (counters %d %d %d)", s[1], s[4], s[5]);
+            return SLIC_ERR_CUDA;
+        }
+        if (cur > bound) {   // (a caller-supplied neighbour array with self links) - repeat with room for n clusters
+            bound = n;
+            continue;
+        }
+        break;
+    }
+    num_clust.push_back(cur);
+
+    // ---- levels driven from the host: more clusters than the device-side loop takes ------------------------------
     int exit_clust = 2;
-    while (exit_clust > 1) {                                              // finch.py:151
+    bool loop_open = true;   // finch.py:151 still running
+    while (loop_open && num_clust.back() > SMALL_LEVEL_MAX_ROWS) {
         const int64_t m = num_clust.back();
-        if (m == 1) break;   // a single centroid links to itself: one cluster, the level is dropped (:160-163)
-        Scratch unit, nn, dist, u;
-        SLIC_PROPAGATE(rank_f64(means->as<double>(), m, d, unit, nn, dist, st));
-        SLIC_CUDA_OK(u.alloc((size_t)m * sizeof(int), st));
+        const int levels = (int)num_clust.size();
         const bool filter = have_min_sim && m <= FLANN_THRESHOLD;          // finch.py:51-52 (needs dense distances)
-        SLIC_PROPAGATE(slic_finch_components(nn.as<int32_t>(), m, filter ? 1 : 0, (double)min_sim, unit.ptr, d, SLIC_F64,
-                                             dist.ptr, u.as<int32_t>(), count_dev.as<int32_t>(), st));
-        SLIC_PROPAGATE(read_back(&cur, count_dev.ptr, sizeof(int), st));
-        exit_clust = num_clust.back() - cur;
-        if (cur == 1 || exit_clust < 1) break;                             // finch.py:160-163: level dropped
-        if ((int)cols.size() >= capacity || (int)cols.size() >= FINCH_MAX_LEVELS) {
-            set_error("finch: more than %d partitions; enlarge the label buffer", (int)cols.size());
+        Scratch unit, ub, nn, dist, u, blkl, off2;
+        SLIC_CUDA_OK(unit.alloc((size_t)m * d * sizeof(double), st));
+        SLIC_CUDA_OK(ub.alloc((size_t)m * dp * 2, st));
+        SLIC_CUDA_OK(nn.alloc((size_t)m * sizeof(int), st));
+        SLIC_CUDA_OK(dist.alloc((size_t)m * sizeof(double), st));
+        SLIC_CUDA_OK(u.alloc((size_t)m * sizeof(int), st));
+        SLIC_CUDA_OK(blkl.alloc(16 * sizeof(int), st));
+        SLIC_CUDA_OK(off2.alloc((size_t)(m + 1) * sizeof(int), st));
+        SLIC_PROPAGATE(slic_normalize_rows(means->ptr, m, d, SLIC_F64, unit.ptr, nullptr, ub.as<uint16_t>(), dp, st));
+        ScratchPtr s2, c2, m2;
+        int64_t bound_l = filter ? m : m / 2;   // without the cut every component has >= 2 members
+        for (int attempt = 0;; ++attempt) {
+            if (attempt == 0) {
+                SLIC_CUDA_OK(cudaMemsetAsync(blkl.ptr, 0, 16 * sizeof(int), st));
+                SLIC_PROPAGATE(nn_top1_self_async(unit.ptr, ub.as<uint16_t>(), m, d, dp, SLIC_F64, nn.as<int>(), dist.ptr,
+                                                  blkl.as<int>(), st));
+            }
+            SLIC_PROPAGATE(finch_components_csr(nn.as<int>(), m, filter ? 1 : 0, ms.as<float>(), unit.ptr, d, SLIC_F64,
+                                                dist.ptr, u.as<int>(), blkl.as<int>() + 8, off2.as<int>(), nullptr, st));
+            SLIC_CUDA_OK(cudaMemcpyAsync(mb->in + MB_LEVEL, blkl.ptr, 9 * sizeof(int), cudaMemcpyDeviceToHost, st));
+            SLIC_CUDA_OK(cudaEventRecord(mb->ev, st));
+            // optimistic: compose the labels and merge the sums while the host waits for the count
+            if (levels < capacity)
+                SLIC_PROPAGATE(slic_compose_labels(cols.as<int>() + (size_t)(levels - 1) * n, u.as<int>(), n,
+                                                   cols.as<int>() + (size_t)levels * n, st));   // get_merge, finch.py:74-79
+            s2 = new_scratch();
+            c2 = new_scratch();
+            m2 = new_scratch();
+            SLIC_CUDA_OK(s2->alloc((size_t)bound_l * d * sizeof(double), st));
+            SLIC_CUDA_OK(c2->alloc((size_t)bound_l * sizeof(int), st));
+            SLIC_CUDA_OK(m2->alloc((size_t)bound_l * d * sizeof(double), st));
+            {
+                Scratch order;
+                SLIC_CUDA_OK(order.alloc((size_t)m * sizeof(int), st));
+                SLIC_PROPAGATE(order_rows_by_label(u.as<int>(), m, bound_l, order.as<int>(), st));
+                SLIC_PROPAGATE(cluster_sums_csr<double>(sums->as<double>(), counts, order.as<int>(), off2.as<int>(), m, d,
+                                                        (int)bound_l, blkl.as<int>() + 8, s2->as<double>(), c2->as<int>(),
+                                                        m2->as<double>(), st));
+            }
+            SLIC_CUDA_OK(cudaEventSynchronize(mb->ev));
+            const int* s = mb->in + MB_LEVEL;
+            cur = s[8];
+            if (attempt == 0 && (s[1] | s[4] | s[5])) {
+                if (s[4] != 0 && s[4] != 2) {
+                    set_error("nn_screen_kernel: pipeline barrier timed out");
+                    return SLIC_ERR_CUDA;
+                }
+                SLIC_PROPAGATE(slic_nn_top1(unit.ptr, ub.as<uint16_t>(), m, unit.ptr, ub.as<uint16_t>(), m, d, dp, SLIC_F64, 0,
+                                            0.f, nn.as<int32_t>(), dist.ptr, nullptr, st));
+                continue;
+            }
+            if (cur > bound_l) {
+                bound_l = m;
+                continue;
+            }
+            break;
+        }
+        exit_clust = (int)m - cur;
+        if (cur == 1 || exit_clust < 1) {                                  // finch.py:160-163: level dropped
+            loop_open = false;
+            break;
+        }
+        if (levels >= capacity || levels >= FINCH_MAX_LEVELS) {
+            set_error("finch: more than %d partitions; enlarge the label buffer", levels);
             return SLIC_ERR_OVERFLOW;
         }
-        cols.push_back(new_scratch());
-        SLIC_CUDA_OK(cols.back()->alloc((size_t)n * sizeof(int), st));
-        SLIC_PROPAGATE(slic_compose_labels(cols[cols.size() - 2]->as<int32_t>(), u.as<int32_t>(), n,
-                                           cols.back()->as<int32_t>(), st));             // get_merge, finch.py:74-79
-        ScratchPtr s2 = new_scratch(), c2 = new_scratch(), m2 = new_scratch();
-        SLIC_CUDA_OK(s2->alloc((size_t)cur * d * sizeof(double), st));
-        SLIC_CUDA_OK(c2->alloc((size_t)cur * sizeof(int), st));
-        SLIC_CUDA_OK(m2->alloc((size_t)cur * d * sizeof(double), st));
-        SLIC_PROPAGATE(slic_merge_cluster_sums(sums->as<double>(), counts->as<int32_t>(), u.as<int32_t>(), m, d, cur,
-                                               s2->as<double>(), c2->as<int32_t>(), m2->as<double>(), st));
         sums.swap(s2);
-        counts.swap(c2);
         means.swap(m2);
+        counts_own.swap(c2);
+        counts = counts_own->as<int>();
         num_clust.push_back(cur);
+        if (exit_clust <= 1) loop_open = false;                            // finch.py:151
     }
 
-    const int levels = (int)cols.size();
-    ColumnPtrs cp;
-    for (int l = 0; l < levels; ++l) cp.col[l] = cols[l]->as<int>();
-    stack_columns_kernel<<<(unsigned)ceil_div(n * levels, 256), 256, 0, st>>>(cp, levels, n, labels_out);
-    SLIC_LAUNCH_OK();
-    for (int l = 0; l < levels; ++l) num_clust_host[l] = num_clust[l];
+    // ---- the remaining levels: one cooperative launch, loop and exit rules on the device ------------------------
+    int* seed = mb->out;
+    seed[0] = (int)num_clust.size();
+    seed[1] = 0;
+    for (size_t l = 0; l < num_clust.size(); ++l) seed[2 + l] = num_clust[l];
+    SLIC_CUDA_OK(cudaMemcpyAsync(summary.ptr, seed, (2 + num_clust.size()) * sizeof(int), cudaMemcpyHostToDevice, st));
+    Scratch sl_sums, sl_counts, sl_means, sl_unit, sl_gram, sl_nn, sl_dist, sl_parent;
+    const int64_t m_in = num_clust.back();
+    if (loop_open && m_in > 1) {
+        SLIC_CUDA_OK(sl_sums.alloc((size_t)m_in * d * sizeof(double), st));
+        SLIC_CUDA_OK(sl_counts.alloc((size_t)m_in * sizeof(int), st));
+        SLIC_CUDA_OK(sl_means.alloc((size_t)m_in * d * sizeof(double), st));
+        SLIC_CUDA_OK(sl_unit.alloc((size_t)m_in * d * sizeof(double), st));
+        SLIC_CUDA_OK(sl_gram.alloc(small_levels_gram_elems(m_in) * sizeof(double), st));
+        SLIC_CUDA_OK(sl_nn.alloc((size_t)m_in * sizeof(int), st));
+        SLIC_CUDA_OK(sl_dist.alloc((size_t)m_in * sizeof(double), st));
+        SLIC_CUDA_OK(sl_parent.alloc((size_t)m_in * sizeof(int), st));
+        SmallLevelsArgs a;
+        a.n_rows = n;
+        a.d = d;
+        a.capacity = capacity < FINCH_MAX_LEVELS ? capacity : FINCH_MAX_LEVELS;
+        a.cols = cols.as<int>();
+        a.summary = summary.as<int>();
+        a.sums[0] = sums->as<double>();
+        a.sums[1] = sl_sums.as<double>();
+        a.counts[0] = counts;
+        a.counts[1] = sl_counts.as<int>();
+        a.means[0] = means->as<double>();
+        a.means[1] = sl_means.as<double>();
+        a.unit = sl_unit.as<double>();
+        a.gram = sl_gram.as<double>();
+        a.nn = sl_nn.as<int>();
+        a.dist = sl_dist.as<double>();
+        a.parent = sl_parent.as<int>();
+        a.use_filter = (have_min_sim && m_in <= FLANN_THRESHOLD) ? 1 : 0;
+        a.min_sim_dev = ms.as<float>();
+        SLIC_PROPAGATE(launch_small_levels(a, st));
+    }
+    {
+        const int64_t want = ceil_div(n * 8, 256);
+        const int64_t cap_blocks = (int64_t)num_sms() * 16;
+        stack_columns_kernel<<<(unsigned)(want < cap_blocks ? want : cap_blocks), 256, 0, st>>>(cols.as<int>(), summary.as<int>(),
+                                                                                          n, labels_out);
+        SLIC_LAUNCH_OK();
+    }
+    SLIC_CUDA_OK(cudaMemcpyAsync(mb->in + MB_SUMMARY, summary.ptr, (2 + FINCH_MAX_LEVELS) * sizeof(int), cudaMemcpyDeviceToHost,
+                                 st));
+    if (have_min_sim)
+        SLIC_CUDA_OK(cudaMemcpyAsync(mb->in + MB_MIN_SIM, ms.ptr, sizeof(float), cudaMemcpyDeviceToHost, st));
+    SLIC_CUDA_OK(cudaStreamSynchronize(st));
+    const int* fin = mb->in + MB_SUMMARY;
+    if (fin[1] == 1) {
+        set_error("finch: more than %d partitions; enlarge the label buffer", capacity);
+        return SLIC_ERR_OVERFLOW;
+    }
+    if (fin[1] != 0) {
+        set_error("finch: device-side level loop reported status %d", fin[1]);
+        return SLIC_ERR_CUDA;
+    }
+    const int levels = fin[0];
+    for (int l = 0; l < levels; ++l) num_clust_host[l] = fin[2 + l];
     *num_levels_host = levels;
+    float min_sim = 0.f;
+    if (have_min_sim) memcpy(&min_sim, mb->in + MB_MIN_SIM, sizeof(float));
     if (min_sim_host) *min_sim_host = min_sim;
     if (has_min_sim_host) *has_min_sim_host = have_min_sim ? 1 : 0;
     return SLIC_OK;
@@ -260,17 +413,25 @@ static int finch_host_impl(const float* x_host, int64_t n, int d, const int64_t*
                            float* min_sim_host, int* has_min_sim_host, HostStreams& hs) {
     const int dp = d_pad_of(d);
     cudaStream_t st = hs.main;
-    Scratch data, unit, ub, nn, dist, gates, labels, rank64;
+    Scratch data, unit, ub, nn, dist, gates, labels, rank64, blk;
     SLIC_CUDA_OK(data.alloc((size_t)n * d * sizeof(float), st));
     SLIC_CUDA_OK(nn.alloc((size_t)n * sizeof(int), st));
     SLIC_CUDA_OK(labels.alloc((size_t)n * capacity * sizeof(int), st));
-    Level0 l0 = {nn.as<int>(), nullptr, nullptr, false};
+    SLIC_CUDA_OK(blk.alloc(16 * sizeof(int), st));
+    SLIC_CUDA_OK(cudaMemsetAsync(blk.ptr, 0, 16 * sizeof(int), st));
+    Level0 l0;
+    l0.nn = nn.as<int>();
+    l0.dist = nullptr;
+    l0.unit = nullptr;
+    l0.dense = false;
+    l0.async_stats = blk.as<int>();
 
     if (initial_rank_host) {
         // finch.py:22-23: the caller's neighbours are used as they are; no distances => no min_sim (:142)
         SLIC_CUDA_OK(rank64.alloc((size_t)n * sizeof(int64_t), st));
         SLIC_CUDA_OK(cudaMemcpyAsync(rank64.ptr, initial_rank_host, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-        convert_rank_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(rank64.as<int64_t>(), n, nn.as<int>());
+        convert_rank_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(rank64.as<int64_t>(), n, nn.as<int>(),
+                                                                      blk.as<int>() + 9);
         SLIC_LAUNCH_OK();
         SLIC_CUDA_OK(cudaMemcpyAsync(data.ptr, x_host, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, st));
     } else if (n == 1) {
@@ -308,7 +469,7 @@ static int finch_host_impl(const float* x_host, int64_t n, int d, const int64_t*
             GateSpec gs = {gates.as<int>(), up.num_chunks, up.chunk_rows};
             SLIC_PROPAGATE(nn_top1_f32_gated(unit.as<float>(), ub.as<uint16_t>(), n, unit.as<float>(), ub.as<uint16_t>(), n,
                                              d, dp, 0, 0.f, nn.as<int>(), dist.as<float>(), nullptr, &gs, run_upload, &up,
-                                             st));
+                                             st, blk.as<int>()));
         } else {
             SLIC_CUDA_OK(cudaEventRecord(hs.ready, st));
             SLIC_CUDA_OK(cudaStreamWaitEvent(hs.copy, hs.ready, 0));
@@ -316,8 +477,9 @@ static int finch_host_impl(const float* x_host, int64_t n, int d, const int64_t*
             // one chunk, no gates: copy + normalise on the copy stream, then search
             if (screen) {
                 SLIC_PROPAGATE(run_upload(&up));
-                SLIC_PROPAGATE(slic_nn_top1(unit.ptr, ub.as<uint16_t>(), n, unit.ptr, ub.as<uint16_t>(), n, d, dp, SLIC_F32, 0,
-                                            0.f, nn.as<int32_t>(), dist.ptr, nullptr, st));
+                SLIC_PROPAGATE(nn_top1_f32_gated(unit.as<float>(), ub.as<uint16_t>(), n, unit.as<float>(), ub.as<uint16_t>(), n,
+                                                 d, dp, 0, 0.f, nn.as<int>(), dist.as<float>(), nullptr, nullptr, nullptr,
+                                                 nullptr, st, blk.as<int>()));
             } else {
                 SLIC_CUDA_OK(cudaMemcpyAsync(data.ptr, x_host, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, st));
                 SLIC_PROPAGATE(slic_normalize_rows(data.ptr, n, d, SLIC_F32, unit.ptr, nullptr, nullptr, dp, st));
@@ -328,6 +490,10 @@ static int finch_host_impl(const float* x_host, int64_t n, int d, const int64_t*
         l0.dist = dist.as<float>();
         l0.unit = unit.as<float>();
         l0.dense = n <= FLANN_THRESHOLD;
+        l0.retry_ub = ub.as<uint16_t>();
+        l0.retry_nn = nn.as<int>();
+        l0.retry_dist = dist.as<float>();
+        l0.no_self_links = true;
         if (g_host_trace) SLIC_CUDA_OK(cudaEventRecord(g_t_search, st));
     }
     int levels = 0;
@@ -380,8 +546,11 @@ int slic_finch(const float* data_dev, int64_t n, int32_t d, const int32_t* nn0_d
     SLIC_PROPAGATE(slic_require_device());
     cudaStream_t st = as_stream(stream);
     const int dp = d_pad_of(d);
-    Scratch unit, ub, nn, dist;
+    Scratch unit, ub, nn, dist, blk;
+    SLIC_CUDA_OK(blk.alloc(16 * sizeof(int), st));
+    SLIC_CUDA_OK(cudaMemsetAsync(blk.ptr, 0, 16 * sizeof(int), st));
     Level0 l0;
+    l0.async_stats = blk.as<int>();
     if (nn0_dev) {
         l0.nn = nn0_dev;
         l0.dist = dist0_dev;
@@ -403,8 +572,9 @@ int slic_finch(const float* data_dev, int64_t n, int32_t d, const int32_t* nn0_d
         SLIC_PROPAGATE(slic_normalize_rows(data_dev, n, d, SLIC_F32, unit.ptr, nullptr, screen ? ub.as<uint16_t>() : nullptr,
                                            dp, st));
         if (screen)
-            SLIC_PROPAGATE(slic_nn_top1(unit.ptr, ub.as<uint16_t>(), n, unit.ptr, ub.as<uint16_t>(), n, d, dp, SLIC_F32, 0, 0.f,
-                                        nn.as<int32_t>(), dist.ptr, nullptr, st));
+            SLIC_PROPAGATE(nn_top1_f32_gated(unit.as<float>(), ub.as<uint16_t>(), n, unit.as<float>(), ub.as<uint16_t>(), n, d,
+                                             dp, 0, 0.f, nn.as<int>(), dist.as<float>(), nullptr, nullptr, nullptr, nullptr,
+                                             st, blk.as<int>()));
         else
             SLIC_PROPAGATE(slic_nn_exact_top1(unit.ptr, nullptr, n, unit.ptr, n, d, SLIC_F32, 0, nn.as<int32_t>(), dist.ptr,
                                               st));
@@ -412,6 +582,10 @@ int slic_finch(const float* data_dev, int64_t n, int32_t d, const int32_t* nn0_d
         l0.dist = dist.as<float>();
         l0.unit = unit.as<float>();
         l0.dense = n <= FLANN_THRESHOLD;
+        l0.retry_ub = ub.as<uint16_t>();
+        l0.retry_nn = nn.as<int>();
+        l0.retry_dist = dist.as<float>();
+        l0.no_self_links = true;
     }
     return finch_levels(data_dev, n, d, l0, ensure_early_exit != 0, capacity, labels_out_dev, num_clust_out_host,
                         num_levels_out_host, min_sim_out_host, has_min_sim_out_host, st);

@@ -30,6 +30,7 @@
 #include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 #include <math_constants.h>
 
 #include <algorithm>
@@ -1637,6 +1638,37 @@ static int launch_screen(const uint16_t* q_bf16, int64_t nq, const uint16_t* x_b
     return SLIC_OK;
 }
 
+// Small host -> device transfers of launch metadata (unit tables, barrier targets) go through a ring of pinned
+// buffers: a cudaMemcpyAsync from pageable memory may wait for the stream's earlier work before it returns, which
+// would stall the host in the middle of an otherwise asynchronous level.  An entry is reused only after the copy
+// that last read it has completed (event).
+struct PinnedSlot {
+    void* host = nullptr;
+    size_t cap = 0;
+    cudaEvent_t done = nullptr;
+    bool used = false;
+};
+static int stage_to_device(void* dst_dev, const void* src, size_t bytes, cudaStream_t st) {
+    constexpr int SLOTS = 8;
+    static thread_local PinnedSlot ring[SLOTS];
+    static thread_local int next = 0;
+    if (bytes == 0) return SLIC_OK;
+    PinnedSlot& s = ring[next];
+    next = (next + 1) % SLOTS;
+    if (s.used) SLIC_CUDA_OK(cudaEventSynchronize(s.done));
+    if (s.cap < bytes) {
+        if (s.host) SLIC_CUDA_OK(cudaFreeHost(s.host));
+        s.cap = bytes < 4096 ? 4096 : bytes + bytes / 2;
+        SLIC_CUDA_OK(cudaHostAlloc(&s.host, s.cap, cudaHostAllocDefault));
+    }
+    if (!s.done) SLIC_CUDA_OK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    memcpy(s.host, src, bytes);
+    SLIC_CUDA_OK(cudaMemcpyAsync(dst_dev, s.host, bytes, cudaMemcpyHostToDevice, st));
+    SLIC_CUDA_OK(cudaEventRecord(s.done, st));
+    s.used = true;
+    return SLIC_OK;
+}
+
 constexpr int TC_CAP = 32;
 
 // Gated launch: the database arrives in `num_chunks` row chunks (host -> device copy + normalise on another stream).
@@ -1770,7 +1802,7 @@ template <typename T>
 static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d, int d_pad, float eps, int* idx_out,
                             T* dist_out, int* stats_out, cudaStream_t st, int part, int parts, const GateSpec* gate,
                             AfterScreenFn after, void* after_ctx, bool* overflowed, int mode = 0,
-                            const int* bests_in = nullptr, int* bests_out = nullptr);
+                            const int* bests_in = nullptr, int* bests_out = nullptr, int* stats_ext = nullptr);
 static bool screen_sym_allowed();
 constexpr int64_t SYM_MIN_ROWS_FWD = 16384;   // below: too few tiles to fill the machine with half of them
 
@@ -1778,12 +1810,13 @@ template <typename T>
 static int nn_top1_impl(const T* q_unit, const uint16_t* q_bf16, int64_t nq, const T* x_unit, const uint16_t* x_bf16,
                         int64_t n, int d, int d_pad, int64_t self_offset, float eps, int* idx_out, T* dist_out,
                         int* stats_out, cudaStream_t st, const GateSpec* gate = nullptr, AfterScreenFn after = nullptr,
-                        void* after_ctx = nullptr) {
+                        void* after_ctx = nullptr, int* stats_ext = nullptr) {
+    // stats_ext: asynchronous mode, see nn_top1_sym_impl ([1] rows to finish exactly, [4] pipeline error, [5] log overflow)
     if (q_bf16 == x_bf16 && q_unit == x_unit && nq == n && self_offset == 0 && n >= SYM_MIN_ROWS_FWD && screen_sym_allowed()) {
         bool overflowed = false;
         SLIC_PROPAGATE(nn_top1_sym_impl<T>(x_unit, x_bf16, n, d, d_pad, eps, idx_out, dist_out, stats_out, st, 0, 1, gate,
-                                           after, after_ctx, &overflowed));
-        if (!overflowed) return SLIC_OK;
+                                           after, after_ctx, &overflowed, 0, nullptr, nullptr, stats_ext));
+        if (stats_ext || !overflowed) return SLIC_OK;
         // (degenerate input: almost every pair within eps of the best) - the full square with per-row lists and the
         // exact finisher handles it; the upload, if any, has been enqueued and joined already
         gate = nullptr;
@@ -1795,8 +1828,7 @@ static int nn_top1_impl(const T* q_unit, const uint16_t* q_bf16, int64_t nq, con
     if (gate) {
         SLIC_PROPAGATE(plan_screen_gated(nq, n, self_offset, *gate, &pl, &table));
         SLIC_CUDA_OK(table_dev.alloc(table.size() * sizeof(int4), st));
-        // pageable source: the runtime stages the bytes before returning, the vector may go out of scope
-        SLIC_CUDA_OK(cudaMemcpyAsync(table_dev.ptr, table.data(), table.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+        SLIC_PROPAGATE(stage_to_device(table_dev.ptr, table.data(), table.size() * sizeof(int4), st));
     }
     const int64_t slots = (int64_t)pl.splits * 2 * nq;   // one list per (split, 128-column half of the tiles, row)
     Scratch ci, cs, cc, cf, ovr, stats;
@@ -1805,20 +1837,25 @@ static int nn_top1_impl(const T* q_unit, const uint16_t* q_bf16, int64_t nq, con
     SLIC_CUDA_OK(cc.alloc(slots * sizeof(int), st));
     SLIC_CUDA_OK(cf.alloc(slots * sizeof(int), st));
     SLIC_CUDA_OK(ovr.alloc(nq * sizeof(int), st));
-    SLIC_CUDA_OK(stats.alloc(8 * sizeof(int), st));
-    SLIC_CUDA_OK(cudaMemsetAsync(stats.ptr, 0, 8 * sizeof(int), st));
+    int* stats_dev = stats_ext;
+    if (!stats_dev) {
+        SLIC_CUDA_OK(stats.alloc(8 * sizeof(int), st));
+        stats_dev = stats.as<int>();
+    }
+    SLIC_CUDA_OK(cudaMemsetAsync(stats_dev, 0, 8 * sizeof(int), st));
     SLIC_PROPAGATE(launch_screen(q_bf16, nq, x_bf16, n, d_pad, self_offset, eps, TC_CAP, pl, ci.as<int>(), cs.as<float>(),
-                                 cc.as<int>(), cf.as<int>(), nullptr, stats.as<int>() + 4, st, 0, nullptr,
+                                 cc.as<int>(), cf.as<int>(), nullptr, stats_dev + 4, st, 0, nullptr,
                                  gate ? table_dev.as<int4>() : nullptr, gate ? gate->gates : nullptr));
     // gated: the caller now enqueues the upload that feeds the running kernel and makes `st` wait for its end
     if (after) SLIC_PROPAGATE(after(after_ctx));
     rerank_top1_kernel<T><<<(unsigned)ceil_div(nq, 8), 256, 0, st>>>(q_unit, x_unit, nq, d, eps, TC_CAP, 2 * pl.splits,
                                                                      ci.as<int>(), cs.as<float>(), cc.as<int>(),
                                                                      cf.as<int>(), idx_out, dist_out, ovr.as<int>(),
-                                                                     stats.as<int>());
+                                                                     stats_dev);
     SLIC_LAUNCH_OK();
+    if (stats_ext) return SLIC_OK;   // asynchronous mode: rows flagged in stats_ext[1] are finished by the caller's retry
     int host_stats[8];
-    SLIC_CUDA_OK(cudaMemcpyAsync(host_stats, stats.ptr, sizeof(host_stats), cudaMemcpyDeviceToHost, st));
+    SLIC_CUDA_OK(cudaMemcpyAsync(host_stats, stats_dev, sizeof(host_stats), cudaMemcpyDeviceToHost, st));
     SLIC_CUDA_OK(cudaStreamSynchronize(st));
     if (host_stats[4] != 0) {
         set_error("nn_screen_kernel: pipeline barrier timed out");
@@ -1835,7 +1872,7 @@ static int nn_top1_impl(const T* q_unit, const uint16_t* q_bf16, int64_t nq, con
                                                                                 od.as<T>(), idx_out, dist_out);
         SLIC_LAUNCH_OK();
     }
-    if (stats_out) SLIC_CUDA_OK(cudaMemcpyAsync(stats_out, stats.ptr, 4 * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    if (stats_out) SLIC_CUDA_OK(cudaMemcpyAsync(stats_out, stats_dev, 4 * sizeof(int), cudaMemcpyDeviceToDevice, st));
     return SLIC_OK;
 }
 
@@ -2002,7 +2039,10 @@ template <typename T>
 static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d, int d_pad, float eps, int* idx_out,
                             T* dist_out, int* stats_out, cudaStream_t st, int part, int parts, const GateSpec* gate,
                             AfterScreenFn after, void* after_ctx, bool* overflowed, int mode, const int* bests_in,
-                            int* bests_out) {
+                            int* bests_out, int* stats_ext) {
+    // stats_ext (device, 8 ints, optional): ASYNCHRONOUS mode - nothing here waits for the device.  The counters
+    // {[1] rows without a neighbour, [4] pipeline error, [5] log overflow} land in stats_ext; if any is non-zero the
+    // result is incomplete and the caller repeats the search through the synchronous path (which has the fallbacks).
     typedef typename DistBits<T>::type Bits;
     *overflowed = false;
     ScreenPlan pl;
@@ -2026,25 +2066,28 @@ static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d,
     if (mode == SYM_BESTS) capacity = SYM_LOG_MIN;   // the records of phase 1 are discarded (an overflow is harmless)
     const int64_t region = ceil_div(capacity, regions);
     SLIC_REQUIRE(region < ((int64_t)1 << 31), "symmetric screen: log region too large");
-    Scratch table_dev, lq, lnb, ls, lcnt, flag, best, rmin, edist, ovr, stats, sync;
+    Scratch table_dev, lq, lnb, ls, lcnt, best, rmin, edist, ovr, stats, sync;
     SLIC_CUDA_OK(table_dev.alloc(table.size() * sizeof(int4), st));
-    SLIC_CUDA_OK(cudaMemcpyAsync(table_dev.ptr, table.data(), table.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+    SLIC_PROPAGATE(stage_to_device(table_dev.ptr, table.data(), table.size() * sizeof(int4), st));
     SLIC_CUDA_OK(sync.alloc((targets.size() + 1) * sizeof(int), st));   // [0] counter, [1..] targets
     SLIC_CUDA_OK(cudaMemsetAsync(sync.ptr, 0, sizeof(int), st));
-    SLIC_CUDA_OK(cudaMemcpyAsync(sync.as<int>() + 1, targets.data(), targets.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    SLIC_PROPAGATE(stage_to_device(sync.as<int>() + 1, targets.data(), targets.size() * sizeof(int), st));
     SLIC_CUDA_OK(lq.alloc(regions * region * sizeof(int), st));
     SLIC_CUDA_OK(lnb.alloc(regions * region * sizeof(int), st));
     SLIC_CUDA_OK(ls.alloc(regions * region * sizeof(float), st));
     SLIC_CUDA_OK(edist.alloc(regions * region * sizeof(T), st));
     SLIC_CUDA_OK(lcnt.alloc(regions * sizeof(int), st));
-    SLIC_CUDA_OK(flag.alloc(sizeof(int), st));
     SLIC_CUDA_OK(best.alloc(n * sizeof(unsigned int), st));
     SLIC_CUDA_OK(rmin.alloc(n * sizeof(Bits), st));
     SLIC_CUDA_OK(ovr.alloc(n * sizeof(int), st));
-    SLIC_CUDA_OK(stats.alloc(8 * sizeof(int), st));
-    SLIC_CUDA_OK(cudaMemsetAsync(stats.ptr, 0, 8 * sizeof(int), st));
+    int* stats_dev = stats_ext;
+    if (!stats_dev) {
+        SLIC_CUDA_OK(stats.alloc(8 * sizeof(int), st));
+        stats_dev = stats.as<int>();
+    }
+    int* flag_dev = stats_dev + 5;   // the log-overflow flag lives in the same block: one read-back fetches everything
+    SLIC_CUDA_OK(cudaMemsetAsync(stats_dev, 0, 8 * sizeof(int), st));
     SLIC_CUDA_OK(cudaMemsetAsync(lcnt.ptr, 0, regions * sizeof(int), st));
-    SLIC_CUDA_OK(cudaMemsetAsync(flag.ptr, 0, sizeof(int), st));
     SLIC_CUDA_OK(cudaMemsetAsync(rmin.ptr, 0xff, n * sizeof(Bits), st));   // all-ones: above every distance's bits
     if (bests_in)   // exchanged row bests (signed-comparable form) seed the thresholds
         flip_sign_bit_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>((const unsigned int*)bests_in, n, best.as<unsigned int>());
@@ -2056,7 +2099,7 @@ static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d,
         SLIC_LAUNCH_OK();
     }
     SLIC_PROPAGATE(launch_screen(ub, n, ub, n, d_pad, 0, eps, 0, pl, lnb.as<int>(), ls.as<float>(), lcnt.as<int>(),
-                                 flag.as<int>(), nullptr, stats.as<int>() + 4, st, 0, nullptr, table_dev.as<int4>(),
+                                 flag_dev, nullptr, stats_dev + 4, st, 0, nullptr, table_dev.as<int4>(),
                                  gate ? gate->gates : nullptr, best.as<unsigned int>(), exec_tiles, lq.as<int>(),
                                  (int)region, sync.as<int>(), sync.as<int>() + 1));
     if (g_profile && parts > 1) g_last_flop /= (double)parts;   // this process's share of the algorithmic 2 n^2 d
@@ -2065,7 +2108,7 @@ static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d,
         flip_sign_bit_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(best.as<unsigned int>(), n, (unsigned int*)bests_out);
         SLIC_LAUNCH_OK();
         int host_err = 0;
-        SLIC_CUDA_OK(cudaMemcpyAsync(&host_err, stats.as<int>() + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SLIC_CUDA_OK(cudaMemcpyAsync(&host_err, stats_dev + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
         SLIC_CUDA_OK(cudaStreamSynchronize(st));
         if (host_err != 0) {
             set_error(host_err == 2 ? "nn_screen_kernel: shared-memory window is not aligned as the symmetric layout assumes"
@@ -2076,16 +2119,16 @@ static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d,
     }
     sym_rerank_dist_kernel<T><<<(unsigned)regions, 256, 0, st>>>(unit, d, eps, (int)region, lq.as<int>(), lnb.as<int>(),
                                                                  ls.as<float>(), lcnt.as<int>(), best.as<unsigned int>(),
-                                                                 rmin.as<Bits>(), edist.as<T>(), stats.as<int>());
+                                                                 rmin.as<Bits>(), edist.as<T>(), stats_dev);
     SLIC_LAUNCH_OK();
     sym_rerank_pick_kernel<T><<<(unsigned)regions, 256, 0, st>>>((int)region, lq.as<int>(), lnb.as<int>(), lcnt.as<int>(),
                                                                  rmin.as<Bits>(), edist.as<T>(), idx_out, dist_out);
     SLIC_LAUNCH_OK();
-    sym_unsettled_rows_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(idx_out, n, ovr.as<int>(), stats.as<int>());
+    sym_unsettled_rows_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(idx_out, n, ovr.as<int>(), stats_dev);
     SLIC_LAUNCH_OK();
-    SLIC_CUDA_OK(cudaMemcpyAsync(stats.as<int>() + 5, flag.ptr, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    if (stats_ext) return SLIC_OK;   // asynchronous mode: the caller reads stats_ext with its own read-back
     int host_stats[8];
-    SLIC_CUDA_OK(cudaMemcpyAsync(host_stats, stats.ptr, sizeof(host_stats), cudaMemcpyDeviceToHost, st));
+    SLIC_CUDA_OK(cudaMemcpyAsync(host_stats, stats_dev, sizeof(host_stats), cudaMemcpyDeviceToHost, st));
     SLIC_CUDA_OK(cudaStreamSynchronize(st));
     if (host_stats[4] == 2) {
         set_error("nn_screen_kernel: shared-memory window is not aligned as the symmetric layout assumes (set SLIC_SCREEN_SYM=0)");
@@ -2136,7 +2179,7 @@ static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d,
                                                                                 od.as<T>(), idx_out, dist_out);
         SLIC_LAUNCH_OK();
     }
-    if (stats_out) SLIC_CUDA_OK(cudaMemcpyAsync(stats_out, stats.ptr, 4 * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    if (stats_out) SLIC_CUDA_OK(cudaMemcpyAsync(stats_out, stats_dev, 4 * sizeof(int), cudaMemcpyDeviceToDevice, st));
     return SLIC_OK;
 }
 
@@ -2195,10 +2238,19 @@ bool screen_can_overlap_upload(int64_t n, int d_pad, int guest_threads, int gues
 int nn_top1_f32_gated(const float* q_unit, const uint16_t* q_bf16, int64_t nq, const float* x_unit,
                       const uint16_t* x_bf16, int64_t n, int d, int d_pad, int64_t self_offset, float eps, int* idx_out,
                       float* dist_out, int* stats_out, const GateSpec* gate, AfterScreenFn after, void* after_ctx,
-                      cudaStream_t st) {
+                      cudaStream_t st, int* stats_ext) {
     if (eps <= 0.f) eps = TC_DEFAULT_EPS;
     return nn_top1_impl<float>(q_unit, q_bf16, nq, x_unit, x_bf16, n, d, d_pad, self_offset, eps, idx_out, dist_out,
-                               stats_out, st, gate, after, after_ctx);
+                               stats_out, st, gate, after, after_ctx, stats_ext);
+}
+
+int nn_top1_self_async(const void* unit, const uint16_t* ub, int64_t n, int d, int d_pad, int dtype, int* idx_out,
+                       void* dist_out, int* stats_ext, cudaStream_t st) {
+    if (dtype == SLIC_F32)
+        return nn_top1_impl<float>((const float*)unit, ub, n, (const float*)unit, ub, n, d, d_pad, 0, TC_DEFAULT_EPS,
+                                   idx_out, (float*)dist_out, nullptr, st, nullptr, nullptr, nullptr, stats_ext);
+    return nn_top1_impl<double>((const double*)unit, ub, n, (const double*)unit, ub, n, d, d_pad, 0, TC_DEFAULT_EPS, idx_out,
+                                (double*)dist_out, nullptr, st, nullptr, nullptr, nullptr, stats_ext);
 }
 
 }  // namespace slic
