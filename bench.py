@@ -1,27 +1,34 @@
 #!/usr/bin/env python
 """bench.py - the hot path of BASELINE.json measured on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload C3|C1|C5]
   (N > 1: launched by torch.distributed.run, one rank per GPU, NCCL)
 
-Workload (config.workload): BASELINE configs[2]/[3] - FINCH full hierarchy on N = 240 000 x D = 512
-synthetic Gaussian-mixture embeddings (Kinetics-400 train size), seed 0 (video_similarity_search_b200.synth).
-A "step" is one complete FINCH call on that batch (all levels: first neighbours, components, means).
+Workload (config.workload), default BASELINE configs[2]/[3]: FINCH full hierarchy on N = 240 000 x D = 512 synthetic
+Gaussian-mixture embeddings (Kinetics-400 train size), seed 0 (video_similarity_search_b200.synth).  A "step" is one
+complete FINCH call on that batch (all levels: first neighbours, components, means).  --workload C5 is BASELINE
+configs[4] (N = 1 000 000 x D = 1 024 FINCH + top-50 retrieval of 100 000 queries), meant for --gpus 8.
 
-  value    embeddings/s through the whole hierarchy with the matrix already resident in HBM
-           (= N / seconds per step; the BASELINE metric "FINCH full-hierarchy seconds" is `finch_seconds`)
-  e2e      the same through the reference-facing call FINCH(numpy array): host->device copy of the
-           embeddings and device->host copy of the label matrix inside the timed region
-  roofline the dominant kernel (nn_screen_kernel, tcgen05): 2 * nq * n * d_pad flop per launch over its
-           CUDA-event duration on its own stream, against MEASURED_PEAKS.json
-  cpu_baseline the oracle port of the reference (numpy / scipy / sklearn) on this box's host cores, on a
-           bounded sample (see `sample`)
-At N > 1 the level-0 nearest-neighbour stage is row-sharded over the ranks (strong scaling: total work fixed).
+  value        embeddings/s through the whole hierarchy with the matrix already resident in HBM
+               (= N / seconds per step; the BASELINE metric "FINCH full-hierarchy seconds" is `finch_seconds`)
+  e2e          the same through the reference-facing call FINCH(host matrix): host->device copy of the embeddings
+               (pinned source) and device->host copy of the label matrix inside the timed region;
+               e2e_pageable: the same call on a plain numpy array, as clustering/cluster_masks.py:80 hands it over
+  roofline     the dominant kernel (nn_screen_kernel, tcgen05, float16 operands / float32 accumulate): flop the tensor
+               cores EXECUTED per launch over its CUDA-event duration on its own stream, against the measured dense
+               peak of MEASURED_PEAKS.json.  (`algorithmic_tflops` counts the full 2 n^2 d of SURVEY.md 8(d); the
+               self-search computes only the tiles on or right of the diagonal, `symmetry_gain` is the ratio.)
+  retrieval    the second half of BASELINE.json's metric: top-50 retrieval through the same screen (configs[1] and
+               the configs[4] retrieval shape), ms / queries per second / fraction of the tensor peak
+  cpu_baseline the oracle port of the reference (numpy / scipy / sklearn) on this box's host cores, bounded sample
+At N > 1 the level-0 nearest-neighbour stage is shared by the ranks (strong scaling: total work fixed).
 
---impl reference: the reference's CPU implementation (oracle port; the reference itself is pure Python that
-needs pyflann above 70 000 rows, see oracle/finch_oracle.py) on the same workload, bounded sample per step.
+--impl reference: the reference's CPU implementation (oracle port; the reference itself is pure Python that needs
+pyflann above 70 000 rows, see oracle/finch_oracle.py) on the same workload: a bounded sample per step, plus ONE
+full pass of the level-0 stage that checks the sample's linear extrapolation (--no-full-nn skips it).
 """
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -37,6 +44,7 @@ sys.path.insert(0, ROOT)
 WORKLOAD = "C3"          # N=240000, D=512, K=400, seed 0
 METRIC = "finch_full_hierarchy_embeddings_per_s"
 UNIT = "embeddings/s"
+C5_QUERIES = 100000      # BASELINE configs[4] does not fix Q; SURVEY.md 8(d) chose 100 000 (seed 1), k = 50
 
 
 def parse_args():
@@ -45,16 +53,19 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=WORKLOAD, help="C1 | C3 | C5 (default C3; others for local experiments)")
-    ap.add_argument("--cpu-sample-rows", type=int, default=4096)
+    ap.add_argument("--workload", default=WORKLOAD, help="C3 (default) | C1 | C5")
+    ap.add_argument("--cpu-sample-rows", type=int, default=4096, help="query rows of the timed CPU sample")
+    ap.add_argument("--parity-rows", type=int, default=16384, help="rows checked against the oracle's first neighbours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-nn", action="store_true", help="reference arm: skip the one full pass of the level-0 stage")
+    ap.add_argument("--no-retrieval", action="store_true")
     return ap.parse_args()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed
-# `ncu --set full` capture (profiles/r1_sym_screen_kernel_ncu_full.txt); keyed by (workload, ranks).  Not measured live:
-# a number taken under the profiler's replay is evidence of traffic, never of time.
-NCU_TRAFFIC_BYTES = {("C3", 1): 2.115234e9 + 102.021376e6}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from a committed `ncu --set full`
+# capture; keyed by (workload, ranks).  A constant taken from that capture, not re-measured per run (a number taken under
+# the profiler's replay is evidence of traffic, never of time) - the line says so in `traffic_source`.
+NCU_TRAFFIC = {("C3", 1): (2.115234e9 + 102.021376e6, "profiles/r1_sym_screen_kernel_ncu_full.txt (round-1 kernel, bf16 operands)")}
 
 
 def load_peaks():
@@ -69,6 +80,19 @@ def load_peaks():
 # --------------------------------------------------------------------------------------------------
 # CPU side: the oracle port of the reference, bounded sample
 # --------------------------------------------------------------------------------------------------
+def use_all_cores():
+    """BLAS threads = all host cores, whatever OMP_NUM_THREADS says (torch.distributed.run exports OMP_NUM_THREADS=1,
+    which would time the reference's sgemm on one core).  Returns (limiter, threads in use)."""
+    want = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        lim = threadpool_limits(limits=want)
+        got = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+        return lim, got
+    except Exception:
+        return None, 1
+
+
 def within_component_neighbors(x, lab):
     """First neighbours restricted to rows of the same mixture component - a cheap way to obtain a realistic
     level-0 neighbour array for TIMING the CPU levels >= 1 (equal to the global first neighbour on all but a
@@ -106,40 +130,50 @@ def cpu_reference_step(x, nn_for_rest, sample_rows):
                      num_clust=[int(v) for v in num_clust])
 
 
-def blas_threads():
-    try:
-        from threadpoolctl import threadpool_info
-        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
-    except Exception:
-        return os.cpu_count() or 1
+def workload_string(n, d, k, seed):
+    return "FINCH full hierarchy, N=%d x D=%d Gaussian mixture (K=%d, seed %d), cosine" % (n, d, k, seed)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    from oracle import finch_oracle as fo
     from video_similarity_search_b200 import synth
+    _lim, cores = use_all_cores()
     n, d, k, seed = synth.CONFIGS[args.workload]
     x, lab, _ = synth.gaussian_mixture(n, d, k, seed, return_labels=True)
     nn = within_component_neighbors(x, lab)
     sample = min(args.cpu_sample_rows, n)
     times, detail = [], None
-    for i in range(args.warmup + args.steps):
+    cpu_warmup = min(args.warmup, 1)     # (a CPU BLAS pass has nothing to warm beyond its first call; keeps the arm to minutes)
+    for i in range(cpu_warmup + args.steps):
         est, detail = cpu_reference_step(x, nn, sample)
-        if i >= args.warmup:
+        if i >= cpu_warmup:
             times.append(est)
     sec = statistics.mean(times)
-    cores = blas_threads()
+    full = None
+    if not args.no_full_nn and n * float(n) * d <= 7e13:
+        # ONE complete pass of the level-0 stage (all rows x all columns): checks that scaling the sample is fair
+        t0 = time.perf_counter()
+        fo.first_neighbors_blocked(x)
+        full = time.perf_counter() - t0
+        detail["nn_stage_full_s"] = full
+        detail["nn_stage_full_over_estimate"] = full / detail["nn_stage_est_s"]
     line = {
         "impl": "reference", "metric": METRIC, "value": n / sec, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "FINCH full hierarchy, N=%d x D=%d Gaussian mixture (K=%d, seed %d), cosine" % (n, d, k, seed)},
+        "steps": args.steps, "warmup": args.warmup, "cpu_warmup_steps_run": cpu_warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_string(n, d, k, seed)},
         "finch_seconds": sec,
         "cpu_baseline": {"value": n / sec, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "level-0 NN stage on %d of %d query rows x all columns, scaled linearly in rows; "
                                    "levels >= 1, components and means timed in full (oracle port of finch.py with "
-                                   "the exact-NN stand-in the reference needs above 70 000 rows)" % (sample, n),
+                                   "the exact-NN stand-in the reference needs above 70 000 rows); BLAS threads pinned to "
+                                   "all %d host cores whatever OMP_NUM_THREADS says%s"
+                                   % (sample, n, cores, "" if full is None else
+                                      "; one full pass of the level-0 stage took %.1f s against %.1f s extrapolated"
+                                      % (full, detail["nn_stage_est_s"])),
                          "detail": detail},
         "e2e": {"value": n / sec, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -242,6 +276,69 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons), "how": "nvidia-smi -lms 100 during the timed steps"}
 
 
+def device_mixture(torch, n, d, k, seed, device):
+    """Gaussian mixture generated ON the device (same Philox stream on every rank): the C5 shapes (4 GB per matrix)
+    would otherwise cost every rank minutes of numpy time and 8 GB of host memory."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    centres = torch.randn(k, d, device=device, generator=g)
+    out = torch.empty(n, d, device=device)
+    for s in range(0, n, 65536):
+        e = min(n, s + 65536)
+        lab = torch.randint(0, k, (e - s,), device=device, generator=g)
+        out[s:e] = centres[lab] + torch.randn(e - s, d, device=device, generator=g)
+    return out, centres
+
+
+def retrieval_record(torch, be, lib, peaks, q, x, k, steps, world, label, check_exact):
+    """Top-k retrieval (iic_retrieve_clips.py:295-296 / evaluate.py:226-231 shape) through the tensor-core screen:
+    CUDA-event time of the whole call (normalise + screen + exact re-rank + sort), the screen kernel alone, and the
+    fraction of the tensor peak.  world > 1: query rows sharded over the ranks, ids all-gathered."""
+    import torch.distributed as dist
+    from video_similarity_search_b200 import _lib
+    from video_similarity_search_b200.sharded import topk_neighbors_sharded
+
+    def call():
+        if world > 1:
+            return topk_neighbors_sharded(q, x, k, backend=be)
+        return be.topk_neighbors(q, x, k)
+
+    call()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    lib.slic_profile_screen(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = None
+    for _ in range(steps):
+        out = call()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    kms, fl = ctypes.c_float(0), ctypes.c_double(0)
+    _lib.check(lib.slic_last_screen_time(ctypes.byref(kms), ctypes.byref(fl)), "slic_last_screen_time")
+    lib.slic_profile_screen(0)
+    if world > 1:
+        t = torch.tensor([ms, kms.value], dtype=torch.float64, device=be.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, kernel_ms = float(t[0]), float(t[1])
+    else:
+        kernel_ms = kms.value
+    nq, n, d = q.shape[0], x.shape[0], x.shape[1]
+    d_pad = (d + 63) // 64 * 64
+    tf = fl.value / (kernel_ms * 1e-3) / 1e12          # this rank's share of 2 Q N d over its kernel time
+    rec = {"shape": "%d queries x %d database x %d, k=%d" % (nq, n, d, k), "ms": ms, "queries_per_s": nq / (ms * 1e-3),
+           "screen_kernel_ms": kernel_ms, "screen_tflops_per_gpu": tf, "frac_of_peak": tf / peaks["bf16_tflops"],
+           "flop_per_launch": fl.value, "d_pad": d_pad, "n_gpus": world, "data": label}
+    if check_exact and world == 1:
+        # identical indices from the exact float64-accumulating kernels (no screen): the parity of the top-k path
+        ux, _ = be.normalize_rows(x, want_f16=False)
+        uq, _ = be.normalize_rows(q, want_f16=False)
+        ei, _ = be.topk_cosine(uq, ux, k)
+        rec["indices_equal_exact_kernels"] = bool(torch.equal(ei, out[0]))
+    return rec
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -262,9 +359,14 @@ def run_b200(args):
     lib = _lib.load()
 
     n, d, k, seed = synth.CONFIGS[args.workload]
-    x_host, lab_host, _ = synth.gaussian_mixture(n, d, k, seed, return_labels=True)
-    x_pinned = torch.from_numpy(x_host).pin_memory()
-    x_dev = x_pinned.to(be.device, non_blocking=True)
+    big = args.workload == "C5"     # generated on the device; no host copy per rank (see device_mixture)
+    if big:
+        x_dev, centres_dev = device_mixture(torch, n, d, k, seed, be.device)
+        x_host = x_pinned = None
+    else:
+        x_host, lab_host, _ = synth.gaussian_mixture(n, d, k, seed, return_labels=True)
+        x_pinned = torch.from_numpy(x_host).pin_memory()
+        x_dev = x_pinned.to(be.device, non_blocking=True)
     torch.cuda.synchronize()
     search = sharded_first_neighbors(be) if world > 1 else None
 
@@ -295,20 +397,19 @@ def run_b200(args):
     def step_resident():
         return FINCH(x_dev, verbose=False, backend=be, first_neighbors=search)
 
-    def step_e2e():
+    def host_step(src):
         # the call a reference user makes: host matrix in, numpy out (H2D of the embeddings, D2H of the labels inside).
         # N > 1: FINCH_sharded - every rank uploads 1 / N of the rows and an all-gather over NVLink assembles the matrix
         if world > 1:
-            return FINCH_sharded(x_pinned, verbose=False, backend=be)
-        return FINCH(x_pinned, verbose=False, backend=be)
+            return lambda: FINCH_sharded(src, verbose=False, backend=be)
+        return lambda: FINCH(src, verbose=False, backend=be)
 
     def step_nn_only():
         return (search(x_dev) if search else be.first_neighbors(x_dev))
 
-    # warm-up (also builds the stream-ordered memory pool)
-    for _ in range(max(args.warmup, 3)):
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):          # (also builds the stream-ordered memory pool)
         step_resident()
-    lib.slic_profile_screen(1)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -318,14 +419,13 @@ def run_b200(args):
     clocks = sampler.stop() if rank == 0 else None
     c, num_clust, _ = result
 
-    # dominant kernel: per-launch CUDA-event time of nn_screen_kernel at level 0 (the last profiled launches are the
-    # small levels, so time the level-0 search alone, K launches, events recorded around the kernel on its stream)
-    import ctypes
+    # dominant kernel: per-launch CUDA-event time of nn_screen_kernel at level 0 (events recorded around the kernel on its
+    # stream; the level-0 call is the only screen launch in step_nn_only)
+    lib.slic_profile_screen(1)
     screen_ms = []
     flop, exec_flop = ctypes.c_double(0), ctypes.c_double(0)
     for _ in range(args.steps):
         step_nn_only()
-        # the level-0 call is the only screen launch in step_nn_only
         ms = ctypes.c_float(0)
         _lib.check(lib.slic_last_screen_time(ctypes.byref(ms), ctypes.byref(flop)), "slic_last_screen_time")
         _lib.check(lib.slic_last_screen_exec_flop(ctypes.byref(exec_flop)), "slic_last_screen_exec_flop")
@@ -333,9 +433,19 @@ def run_b200(args):
     lib.slic_profile_screen(0)
     screen_ms_avg = max_over_ranks(statistics.mean(screen_ms))
     ms_nn, _ = timed(step_nn_only, args.steps)
-    for _ in range(2):
-        step_e2e()
-    ms_e2e, _ = timed(step_e2e, args.steps)
+    # everything after the level-0 search (components, means, all further levels, labels to the host): one FINCH call
+    # with the level-0 neighbours handed in
+    cached = step_nn_only()
+    ms_tail, _ = timed(lambda: FINCH(x_dev, verbose=False, backend=be, first_neighbors=lambda m: cached), args.steps)
+    del cached
+    ms_e2e = ms_e2e_pageable = None
+    if not big:
+        for _ in range(2):
+            host_step(x_pinned)()
+        ms_e2e, _ = timed(host_step(x_pinned), args.steps)
+        for _ in range(2):
+            host_step(x_host)()
+        ms_e2e_pageable, _ = timed(host_step(x_host), args.steps)
 
     sharded_equal = None
     if world > 1:
@@ -346,79 +456,153 @@ def run_b200(args):
         ok = torch.tensor([int(torch.equal(nn_s, nn_1) and torch.equal(d_s, d_1))], device=be.device)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         sharded_equal = bool(ok.item())
+
+    peaks = load_peaks()
+    retrieval = None
+    if not args.no_retrieval:
+        retrieval = {}
+        if not big:
+            tr, _, te, _ = synth.c2_retrieval()
+            retrieval["C2_top50"] = retrieval_record(torch, be, lib, peaks, be.to_device(te), be.to_device(tr), 50,
+                                                     max(args.steps, 10), world, "BASELINE configs[1], host-generated", True)
+        if big or (world == 1 and args.workload == "C3"):
+            if big:
+                xq = x_dev
+                cen = centres_dev
+            else:
+                xq, cen = device_mixture(torch, 1000000, 1024, 1000, 0, be.device)
+            g = torch.Generator(device=be.device).manual_seed(1)
+            q5 = cen[torch.randint(0, cen.shape[0], (C5_QUERIES,), device=be.device, generator=g)] + \
+                torch.randn(C5_QUERIES, cen.shape[1], device=be.device, generator=g)
+            retrieval["C5_top50"] = retrieval_record(torch, be, lib, peaks, q5, xq, 50, 3, world,
+                                                     "BASELINE configs[4] retrieval shape (Q not fixed by BASELINE: 100 000), "
+                                                     "device-generated mixture", False)
+            del q5
+            if not big:
+                del xq
+                torch.cuda.empty_cache()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    peaks = load_peaks()
-    achieved_tf = flop.value / (screen_ms_avg * 1e-3) / 1e12
-    executed_tf = exec_flop.value / (screen_ms_avg * 1e-3) / 1e12
+    exec_tf = exec_flop.value / (screen_ms_avg * 1e-3) / 1e12
+    algo_tf = flop.value / (screen_ms_avg * 1e-3) / 1e12
     d_pad = (d + 63) // 64 * 64
+    traffic = NCU_TRAFFIC.get((args.workload, world))
+    if world == 1:
+        par = "1 GPU"
+    else:
+        par = ("level-0 NN: the %d ranks share the tiles of the symmetric screen's triangle; on the critical path: one NCCL "
+               "all-reduce MAX of 4N bytes (row bests) and one all-reduce MIN of 8(N+1) bytes ((distance, neighbour) keys); "
+               "levels >= 1 replicated" % world)
     line = {
         "metric": METRIC, "value": n / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "bf16 screen + f32/f64 exact re-rank", "data": "synthetic",
-        "config": {"workload": "FINCH full hierarchy, N=%d x D=%d Gaussian mixture (K=%d, seed %d), cosine" % (n, d, k, seed),
-                   "l2": "inputs exceed L2 (%.0f MB fp32 + %.0f MB bf16 per step)" % (n * d * 4 / 1e6, n * d_pad * 2 / 1e6),
+        "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f16 screen (f32 accumulate) + f32/f64 exact re-rank", "data": "synthetic",
+        "config": {"workload": workload_string(n, d, k, seed),
+                   "l2": "inputs exceed L2 (%.0f MB fp32 + %.0f MB fp16 per step)" % (n * d * 4 / 1e6, n * d_pad * 2 / 1e6),
                    "partitions": [int(v) for v in num_clust],
-                   "parallelism": ("1 GPU" if world == 1 else
-                                   "level-0 NN: the %d ranks share the tiles of the symmetric screen's triangle, (distance, "
-                                   "neighbour) keys merged by one NCCL all-reduce MIN of 8(N+1) bytes; levels >= 1 replicated"
-                                   % world)},
+                   "parallelism": par,
+                   "data_source": "device-generated (torch Philox, same stream on every rank)" if big else "numpy, seeded"},
         "finch_seconds": ms_step * 1e-3,
         "nn_stage": {"ms": ms_nn, "queries_per_s": n / (ms_nn * 1e-3)},
-        "e2e": {"value": n / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-                # whole job: every rank uploads its 1 / N share of the rows (the rest arrives over NVLink); labels back per rank
-                "h2d_bytes_per_step": int(n * d * 4), "d2h_bytes_per_step": int(c.size * 4 * world)},
-        "gpu_launches": int(launches),
+        "tail_ms_given_level0_neighbours": ms_tail,
+        "gpu_launches": int(launches), "gpu_launches_per_step": launches / float(args.steps),
         "clocks": clocks,
         "roofline": {"kernel": "nn_screen_kernel (level 0, %d x %d x %d%s)" % (n, n, d_pad, "" if world == 1 else
                                                                                ", this rank's 1/%d of the tiles" % world),
-                     "bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                     "frac": achieved_tf / peaks["bf16_tflops"], "peak_source": peaks["source"] + " burst bf16",
-                     "frac_of_sustained": (achieved_tf / peaks["bf16_tflops_sustained"]) if peaks.get("bf16_tflops_sustained") else None,
-                     "kernel_ms": screen_ms_avg, "flop_per_launch": flop.value,
-                     # the self-search computes only the tiles on or right of the diagonal of the symmetric score matrix
-                     # (each filtered along rows AND columns): `achieved` counts the ALGORITHMIC 2 n^2 d flop of SURVEY.md
-                     # section 8(d) (full square, no symmetry discount) and may therefore exceed the peak; `executed` is
-                     # what the tensor cores actually did, and `frac_executed` its fraction of the measured peak
-                     "executed_flop_per_launch": exec_flop.value, "executed": executed_tf,
-                     "frac_executed": executed_tf / peaks["bf16_tflops"],
-                     "traffic": NCU_TRAFFIC_BYTES.get((args.workload, world)), "traffic_unit": "bytes/launch (ncu dram read+write)"},
+                     "bound": "tensor", "achieved": exec_tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                     "frac": exec_tf / peaks["bf16_tflops"],
+                     "peak_source": peaks["source"] + " burst dense bf16 (cuBLAS; float16 operands run at the same rate)",
+                     "frac_of_sustained": (exec_tf / peaks["bf16_tflops_sustained"]) if peaks.get("bf16_tflops_sustained") else None,
+                     "kernel_ms": screen_ms_avg, "flop_per_launch": exec_flop.value,
+                     # the ALGORITHMIC figure of SURVEY.md 8(d) (full square, no symmetry discount) - not a hardware rate
+                     "algorithmic_flop_per_launch": flop.value, "algorithmic_tflops": algo_tf,
+                     "symmetry_gain": flop.value / exec_flop.value if exec_flop.value else None,
+                     "traffic": traffic[0] if traffic else None,
+                     "traffic_source": (traffic[1] + "; constant from that capture, not re-measured per run") if traffic else
+                                       "no ncu capture for this (workload, ranks)",
+                     "traffic_unit": "bytes/launch (ncu dram read+write)"},
     }
-    if world == 1 and not args.no_cpu_baseline:
-        nn_dev, _, _ = be.first_neighbors(x_dev)
-        sample = min(args.cpu_sample_rows, n)
-        # parity gate in the same run: oracle first neighbours on the sampled rows must equal the GPU's
+    if ms_e2e is not None:
+        h2d, d2h = int(n * d * 4), int(c.size * 4 * world)
+        # whole job: every rank uploads its 1 / N share of the rows (the rest arrives over NVLink); labels back per rank
+        line["e2e"] = {"value": n / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": d2h, "source": "pinned host memory"}
+        line["e2e_pageable"] = {"value": n / (ms_e2e_pageable * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_pageable,
+                                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                                "source": "plain numpy array (pageable), as clustering/cluster_masks.py:80 hands it over"}
+    else:
+        line["e2e"] = None
+        line["e2e_note"] = "C5 is generated on the device (8 x 4 GB of host staging avoided): no host-buffer leg"
+    if retrieval is not None:
+        line["retrieval"] = retrieval
+
+    parity = {}
+    if world == 1:
         from oracle import finch_oracle as fo
-        rows = np.linspace(0, n - 1, sample).astype(np.int64)
+        # (1) EVERY row: the tensor-core path against the exact float64-accumulating kernel (no screen)
+        nn_dev, dist_dev, unit = be.first_neighbors(x_dev)
         t0 = time.perf_counter()
-        enn, _, gap = fo.first_neighbors_blocked(x_host, rows=rows)
-        t_nn = time.perf_counter() - t0
-        nn_host = nn_dev.cpu().numpy().astype(np.int64)
-        clear = gap > 2e-6
-        parity_nn = bool(np.array_equal(nn_host[rows][clear], enn[clear]))
-        t0 = time.perf_counter()
-        if n <= fo.FLANN_THRESHOLD:
-            # dense mode of the reference (distances kept, min_sim cut): the oracle runs it in full, only its level-0
-            # neighbours are replaced by the GPU's so that float32 tie rows cannot change the partition
-            co, no, _ = fo.finch(x_host, nn0_override=nn_host)
+        exact_rows = n if not big else 65536
+        rows_t = None
+        if exact_rows == n:
+            nn_ex, _ = be.nn_exact_top1(unit, unit, self_offset=0)
+            same = bool(torch.equal(nn_ex, nn_dev))
+            mism = int((nn_ex != nn_dev).sum())
         else:
-            co, no, _ = fo.finch(x_host, initial_rank=nn_host)
-        t_rest = time.perf_counter() - t0
-        parity_partition = bool(no == num_clust and np.array_equal(co, c))
-        est = t_nn * n / float(sample) + t_rest
-        line["cpu_baseline"] = {
-            "value": n / est, "unit": UNIT, "cores": blas_threads(), "kind": "port",
-            "sample": "level-0 NN stage on %d of %d query rows x all columns (%.1f s), scaled linearly in rows; levels >= 1, "
-                      "components and means timed in full (%.1f s) - oracle port of finch.py with the exact-NN stand-in the "
-                      "reference needs above 70 000 rows" % (sample, n, t_nn, t_rest),
-            "finch_seconds_est": est}
-        line["parity"] = {"first_neighbors_equal_on_sample": parity_nn, "tie_rows_in_sample": int((~clear).sum()),
-                          "partition_equals_oracle": parity_partition}
+            rows_t = torch.linspace(0, n - 1, exact_rows, device=be.device).long().to(torch.int32)
+            nn_ex, _ = be.nn_exact_top1(unit, unit, self_offset=0, q_rows=rows_t)
+            mism = int((nn_ex != nn_dev[rows_t.long()]).sum())
+            same = mism == 0
+        torch.cuda.synchronize()
+        parity["first_neighbors_tc_equals_exact_kernel"] = {"rows_checked": int(exact_rows), "of": n, "equal": same,
+                                                            "mismatches": mism, "seconds": time.perf_counter() - t0}
+        del nn_ex
+        if x_host is None:
+            x_host = x_dev.cpu().numpy()
+        nn_host = nn_dev.cpu().numpy().astype(np.int64)
+        if not args.no_cpu_baseline:
+            _lim, cores = use_all_cores()
+            # (2) oracle first neighbours (the reference's arithmetic, blocked) on a row sample; the first
+            #     `cpu_sample_rows` of them are also the timed CPU sample
+            prow = min(args.parity_rows if not big else 2048, n)
+            sample = min(args.cpu_sample_rows, prow)
+            rows = np.linspace(0, n - 1, prow).astype(np.int64)
+            t0 = time.perf_counter()
+            enn_a, _, gap_a = fo.first_neighbors_blocked(x_host, rows=rows[:sample])
+            t_nn = time.perf_counter() - t0
+            if prow > sample:
+                enn_b, _, gap_b = fo.first_neighbors_blocked(x_host, rows=rows[sample:])
+                enn, gap = np.concatenate([enn_a, enn_b]), np.concatenate([gap_a, gap_b])
+            else:
+                enn, gap = enn_a, gap_a
+            clear = gap > 2e-6
+            parity["first_neighbors_equal_oracle"] = {
+                "rows_checked": int(prow), "tie_margin": 2e-6, "tie_rows": int((~clear).sum()),
+                "equal_outside_ties": bool(np.array_equal(nn_host[rows][clear], enn[clear])),
+                "mismatches_incl_ties": int((nn_host[rows] != enn).sum())}
+            # (3) levels >= 1: the oracle run from the GPU's level-0 neighbours must give the GPU's partition
+            t0 = time.perf_counter()
+            if n <= fo.FLANN_THRESHOLD:
+                co, no, _ = fo.finch(x_host, nn0_override=nn_host)
+            else:
+                co, no, _ = fo.finch(x_host, initial_rank=nn_host)
+            t_rest = time.perf_counter() - t0
+            parity["levels_ge1_equal_oracle_given_gpu_nn0"] = bool(no == num_clust and np.array_equal(co, c))
+            est = t_nn * n / float(sample) + t_rest
+            line["cpu_baseline"] = {
+                "value": n / est, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": "level-0 NN stage on %d of %d query rows x all columns (%.1f s), scaled linearly in rows; levels >= 1, "
+                          "components and means timed in full (%.1f s) - oracle port of finch.py with the exact-NN stand-in the "
+                          "reference needs above 70 000 rows; the reference arm (--impl reference) also runs the level-0 stage "
+                          "once in full" % (sample, n, t_nn, t_rest),
+                "finch_seconds_est": est}
     if sharded_equal is not None:
-        line["parity"] = {"sharded_first_neighbors_equal_single_gpu_on_every_rank": sharded_equal}
+        parity["sharded_first_neighbors_equal_single_gpu_on_every_rank"] = sharded_equal
+    line["parity"] = parity
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -70,18 +70,19 @@ int slic_last_screen_exec_flop(double* flop_out);
  * [0] cycles the TMA producer waited for a free smem stage, [1] cycles the MMA issuer waited for a free
  * accumulator (epilogue-bound), [2] for operands (TMA/L2-bound), [3] MMA issuer total, [4] cycles epilogue
  * warp 0 waited for a complete accumulator (MMA-bound), [5] epilogue warp 0 total, [6] 32-column chunks with
- * at least one candidate row and [7] chunks examined (top-k variant).  counters_out_host (optional, [8])
- * receives the counters accumulated so far; they are then reset.  enable = 0 releases the buffer. */
+ * at least one candidate row and [7] chunks examined, [8] cycles the MMA issuer waited for its next unit id (scheduler,
+ * pre-pass hand-over), [9] the same for epilogue warp 0, [10] units processed, [11] spare.  counters_out_host
+ * (optional, [12]) receives the counters accumulated so far; they are then reset.  enable = 0 releases the buffer. */
 int slic_screen_trace(int32_t enable, uint64_t* counters_out_host);
 
 /* ---- K1 prep: row normalisation --------------------------------------------------------- */
 /* sklearn cosine_similarity's normalize step behind clustering/finch.py:27, evaluate.py:213,
  * iic_retrieve_clips.py:295:  norm_i = sqrt(sum_k x_ik^2) (0 -> 1),  unit_i = x_i / norm_i in
- * `dtype`.  Optionally also emits the bf16 copy (row stride d_pad, zero padded; d_pad % 64 == 0)
- * that the tensor-core screen reads.  unit_dev / norms_dev / unit_bf16_dev may each be NULL. */
+ * `dtype`.  Optionally also emits the f16 copy (row stride d_pad, zero padded; d_pad % 64 == 0)
+ * that the tensor-core screen reads.  unit_dev / norms_dev / unit_f16_dev may each be NULL. */
 int slic_normalize_rows(const void* x_dev, int64_t n, int32_t d, int32_t dtype,
                         void* unit_dev, void* norms_dev,
-                        uint16_t* unit_bf16_dev, int32_t d_pad, slic_stream_t stream);
+                        uint16_t* unit_f16_dev, int32_t d_pad, slic_stream_t stream);
 
 /* coclr_classify.py:788-789: out = x - x.mean(dim=0, keepdim=True) for a float32 [n, d] matrix.
  * Column sums in float64 (deterministic), mean rounded to float32 before the subtraction as torch holds it.
@@ -101,14 +102,14 @@ int slic_nn_exact_top1(const void* q_unit_dev, const int32_t* q_rows_dev, int64_
                        slic_stream_t stream);
 
 /* ---- K1 tensor-core screen + exact re-rank ------------------------------------------------ */
-/* The same first-neighbour search as slic_nn_exact_top1, done as a bf16 tcgen05 GEMM with a
+/* The same first-neighbour search as slic_nn_exact_top1, done as a f16 tcgen05 GEMM with a
  * fused per-row candidate filter (scores never leave the SM) followed by an exact re-rank of
  * the surviving candidates in `dtype`.  eps is the screen's error allowance: every column whose
- * bf16 score is within eps of the row's best is re-ranked (eps <= 0 selects the provable
+ * f16 score is within eps of the row's best is re-ranked (eps <= 0 selects the provable
  * default 2^-7 + 2^-11).  Rows whose candidate list overflowed are finished by the exact kernel, so the
  * result never depends on the screen's precision.  q_* may equal x_* (FINCH self-search). */
-int slic_nn_top1(const void* q_unit_dev, const uint16_t* q_bf16_dev, int64_t nq,
-                 const void* x_unit_dev, const uint16_t* x_bf16_dev, int64_t n,
+int slic_nn_top1(const void* q_unit_dev, const uint16_t* q_f16_dev, int64_t nq,
+                 const void* x_unit_dev, const uint16_t* x_f16_dev, int64_t n,
                  int32_t d, int32_t d_pad, int32_t dtype, int64_t self_offset, float eps,
                  int32_t* idx_out_dev, void* dist_out_dev, int32_t* stats_out_dev /* [4] or NULL:
                  candidates re-ranked, rows finished by the exact kernel, list compactions, 0 */,
@@ -132,9 +133,9 @@ int slic_nn_top1(const void* q_unit_dev, const uint16_t* q_bf16_dev, int64_t nq,
  *   all-reduce MAX          of that [n] int32 array over the parts (4 n bytes);
  *   slic_nn_top1_sym_part   with row_bests_dev = the merged array: thresholds for ALL rows from the first tile on, no
  *                           pre-pass of its own.  row_bests_dev = NULL: single-phase (own pre-pass over all rows). */
-int slic_sym_row_bests(const float* unit_dev, const uint16_t* unit_bf16_dev, int64_t n, int32_t d, int32_t d_pad,
+int slic_sym_row_bests(const float* unit_dev, const uint16_t* unit_f16_dev, int64_t n, int32_t d, int32_t d_pad,
                        int32_t part, int32_t parts, int32_t* bests_out_dev, slic_stream_t stream);
-int slic_nn_top1_sym_part(const float* unit_dev, const uint16_t* unit_bf16_dev, int64_t n, int32_t d,
+int slic_nn_top1_sym_part(const float* unit_dev, const uint16_t* unit_f16_dev, int64_t n, int32_t d,
                           int32_t d_pad, int32_t part, int32_t parts, const int32_t* row_bests_dev, float eps,
                           uint64_t* keys_out_dev, int32_t* stats_out_dev /* [4] or NULL, as slic_nn_top1 */,
                           slic_stream_t stream);
@@ -150,9 +151,9 @@ int slic_unpack_neighbor_keys(const uint64_t* keys_dev, int64_t n, int32_t* idx_
 int slic_debug_sym_plan(int64_t n, int32_t part, int32_t parts, int32_t mode, int32_t gated_chunks,
                         int32_t* units_out_host, int64_t capacity, int64_t* num_units_out_host);
 
-/* Debug / test hook: raw bf16-screen scores of one 128 x 256 tile region, written as float
+/* Debug / test hook: raw f16-screen scores of one 128 x 256 tile region, written as float
  * [nq, n] (small shapes only).  Lets the tests check the tcgen05 path element by element. */
-int slic_screen_scores_debug(const uint16_t* q_bf16_dev, int64_t nq, const uint16_t* x_bf16_dev,
+int slic_screen_scores_debug(const uint16_t* q_f16_dev, int64_t nq, const uint16_t* x_f16_dev,
                              int64_t n, int32_t d_pad, float* out_dev, slic_stream_t stream);
 
 /* ---- K1 dense / top-k (retrieval) ------------------------------------------------------- */
@@ -175,13 +176,13 @@ int slic_topk_cosine(const void* q_unit_dev, int64_t nq, const void* x_unit_dev,
                      int32_t d, int32_t dtype, int32_t k, int64_t self_offset,
                      int32_t* idx_out_dev, void* dist_out_dev, slic_stream_t stream);
 
-/* The same top-k search on the tensor cores: bf16 tcgen05 screen with a fused per-row candidate
+/* The same top-k search on the tensor cores: f16 tcgen05 screen with a fused per-row candidate
  * filter (a column survives iff its screened score is within eps of the row's running k-th best),
  * then exact evaluation in `dtype` and a (distance, column) sort of the survivors.  Results are
  * those of slic_topk_cosine (rows the screen cannot settle are finished by the exact kernels);
  * k <= 64.  stats_out_dev as in slic_nn_top1. */
-int slic_topk_cosine_tc(const void* q_unit_dev, const uint16_t* q_bf16_dev, int64_t nq,
-                        const void* x_unit_dev, const uint16_t* x_bf16_dev, int64_t n,
+int slic_topk_cosine_tc(const void* q_unit_dev, const uint16_t* q_f16_dev, int64_t nq,
+                        const void* x_unit_dev, const uint16_t* x_f16_dev, int64_t n,
                         int32_t d, int32_t d_pad, int32_t dtype, int32_t k, int64_t self_offset,
                         float eps, int32_t* idx_out_dev, void* dist_out_dev,
                         int32_t* stats_out_dev, slic_stream_t stream);

@@ -39,7 +39,7 @@ def timeit(fn, reps):
     return e0.elapsed_time(e1) / reps, out
 
 lib.slic_profile_screen(1)
-ms_tc, (ti, tv) = timeit(lambda: be.topk_cosine(uq, ux, k, q_bf16=qb, x_bf16=xb), 3)
+ms_tc, (ti, tv) = timeit(lambda: be.topk_cosine(uq, ux, k, q_f16=qb, x_f16=xb), 3)
 import ctypes
 ms = ctypes.c_float(0); fl = ctypes.c_double(0)
 lib.slic_last_screen_time(ctypes.byref(ms), ctypes.byref(fl))

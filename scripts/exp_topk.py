@@ -23,7 +23,7 @@ def screen_ms(fn):
     if TRACE:
         lib.slic_screen_trace(1, None)
         fn(); torch.cuda.synchronize()
-        c = (ctypes.c_uint64 * 8)()
+        c = (ctypes.c_uint64 * 12)()
         lib.slic_screen_trace(0, c)
         c = [v / 148.0 / 1e6 for v in c]
         print("    trace (Mcycles per CTA): producer-wait %.2f | mma: wait-acc %.2f wait-operands %.2f total %.2f | epi0: wait-mma %.2f total %.2f | chunks triggered %.3f of %.3f M"
@@ -42,6 +42,6 @@ for shape in sys.argv[1:]:
         for sp in os.environ.get("SPLITS", "0").split(","):
             if sp != "0": os.environ["SLIC_TOPK_SPLITS"] = sp
             else: os.environ.pop("SLIC_TOPK_SPLITS", None)
-            ms, tf = screen_ms(lambda: be.topk_cosine(uq, ux, k, q_bf16=qb, x_bf16=xb))
+            ms, tf = screen_ms(lambda: be.topk_cosine(uq, ux, k, q_f16=qb, x_f16=xb))
             st = be.last_stats.cpu().tolist()
             print("%s top%d splits=%s: %.3f ms %.0f TF/s  reranked/row %.0f listed/row %.0f compactions %d" % (shape, k, sp, ms, tf, st[0] / nq, st[3] * 16.0 / nq, st[2]), flush=True)

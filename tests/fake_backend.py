@@ -33,12 +33,12 @@ class FakeBackend:
         return t.cpu().numpy()
 
     # K1
-    def normalize_rows(self, x, want_bf16=True):
+    def normalize_rows(self, x, want_f16=True):
         a = _np(x)
         nrm = np.sqrt(np.einsum("ij,ij->i", a.astype(np.float64), a.astype(np.float64))).astype(a.dtype)
         nrm[nrm == 0] = 1
         unit = torch.from_numpy(a / nrm[:, None])
-        return unit, (unit.to(torch.bfloat16) if want_bf16 else None)
+        return unit, (unit.to(torch.float16) if want_f16 else None)
 
     def center_columns(self, x):
         a = _np(x)
@@ -59,12 +59,12 @@ class FakeBackend:
         j = np.argmin(dmat, axis=1)                                      # ties -> lowest index (np.argmin)
         return torch.from_numpy(j.astype(np.int32)), torch.from_numpy(dmat[np.arange(len(q)), j])
 
-    def nn_top1(self, q_unit, q_bf16, x_unit, x_bf16, self_offset=-1, eps=0.0):
+    def nn_top1(self, q_unit, q_f16, x_unit, x_f16, self_offset=-1, eps=0.0):
         return self.nn_exact_top1(q_unit, x_unit, self_offset)
 
     def first_neighbors(self, x, row_range=None):
         self.calls.append(("first_neighbors", tuple(x.shape), str(x.dtype), row_range))
-        unit, _ = self.normalize_rows(x, want_bf16=False)
+        unit, _ = self.normalize_rows(x, want_f16=False)
         r0, r1 = (0, x.shape[0]) if row_range is None else row_range
         nn, d = self.nn_exact_top1(unit[r0:r1], unit, self_offset=r0)
         return nn, d, unit
@@ -82,7 +82,7 @@ class FakeBackend:
         in both directions and keeps, per row, the smallest (distance bits, neighbour) key.  reduce_max: the row-best
         exchange of the two-phase search - exercised with this part's rows' best similarity to a column sample."""
         self.calls.append(("first_neighbors_part", tuple(x.shape), part, parts))
-        unit, _ = self.normalize_rows(x, want_bf16=False)
+        unit, _ = self.normalize_rows(x, want_f16=False)
         u = _np(unit)
         n, b = len(u), self.PART_BLOCK
         if reduce_max is not None and parts > 1:
@@ -174,15 +174,15 @@ class FakeBackend:
         order = np.lexsort((np.broadcast_to(np.arange(m.shape[1]), m.shape), m), axis=1)[:, :k]
         return torch.from_numpy(order.astype(np.int32)), torch.from_numpy(np.take_along_axis(m, order, 1))
 
-    def topk_cosine(self, q_unit, x_unit, k, self_offset=-1, q_bf16=None, x_bf16=None, eps=0.0):
+    def topk_cosine(self, q_unit, x_unit, k, self_offset=-1, q_f16=None, x_f16=None, eps=0.0):
         m = _np(self.distance_matrix(q_unit, x_unit))
         if self_offset >= 0:
             m[np.arange(m.shape[0]), np.arange(m.shape[0]) + self_offset] = np.inf
         return self.rows_topk(torch.from_numpy(m), k)
 
     def topk_neighbors(self, q, x, k, same=False):
-        ux, _ = self.normalize_rows(x, want_bf16=False)
-        uq = ux if same else self.normalize_rows(q, want_bf16=False)[0]
+        ux, _ = self.normalize_rows(x, want_f16=False)
+        uq = ux if same else self.normalize_rows(q, want_f16=False)[0]
         return self.topk_cosine(uq, ux, k, self_offset=0 if same else -1)
 
     def hit_at_k(self, topk_idx, q_labels, x_labels, ks):

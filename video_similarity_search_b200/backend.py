@@ -70,12 +70,12 @@ class CudaBackend:
         return stage.numpy().copy()
 
     # -- K1 --------------------------------------------------------------------------------------
-    def normalize_rows(self, x, want_bf16=True):
-        """-> (unit [n,d] same dtype, unit_bf16 [n,d_pad] or None)."""
+    def normalize_rows(self, x, want_f16=True):
+        """-> (unit [n,d] same dtype, unit_f16 [n,d_pad] or None)."""
         n, d = x.shape
         unit = torch.empty_like(x)
         dp = d_pad_of(d)
-        ub = torch.empty((n, dp), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+        ub = torch.empty((n, dp), dtype=torch.float16, device=x.device) if want_f16 else None
         _lib.call("slic_normalize_rows", _p(x), n, d, _DT[x.dtype], _p(unit), None, _p(ub), dp, self._stream())
         return unit, ub
 
@@ -94,14 +94,14 @@ class CudaBackend:
                   self_offset, _p(idx), _p(dist), self._stream())
         return idx, dist
 
-    def nn_top1(self, q_unit, q_bf16, x_unit, x_bf16, self_offset=-1, eps=0.0):
+    def nn_top1(self, q_unit, q_f16, x_unit, x_f16, self_offset=-1, eps=0.0):
         """tcgen05 screen + exact re-rank (slic_nn_top1)."""
         nq = q_unit.shape[0]
         n, d = x_unit.shape
         idx = torch.empty(nq, dtype=torch.int32, device=x_unit.device)
         dist = torch.empty(nq, dtype=x_unit.dtype, device=x_unit.device)
         stats = torch.zeros(4, dtype=torch.int32, device=x_unit.device)
-        _lib.call("slic_nn_top1", _p(q_unit), _p(q_bf16), nq, _p(x_unit), _p(x_bf16), n, d, x_bf16.shape[1],
+        _lib.call("slic_nn_top1", _p(q_unit), _p(q_f16), nq, _p(x_unit), _p(x_f16), n, d, x_f16.shape[1],
                   _DT[x_unit.dtype], self_offset, float(eps), _p(idx), _p(dist), _p(stats), self._stream())
         self.last_stats = stats
         return idx, dist
@@ -111,7 +111,7 @@ class CudaBackend:
         -> (nn int32, dist x.dtype, unit).  Chooses the screen for large inputs, the exact kernel below."""
         n = x.shape[0]
         use_screen = n >= SCREEN_MIN_ROWS
-        unit, ub = self.normalize_rows(x, want_bf16=use_screen)
+        unit, ub = self.normalize_rows(x, want_f16=use_screen)
         r0, r1 = (0, n) if row_range is None else row_range
         if r1 <= r0:
             return (torch.empty(0, dtype=torch.int32, device=x.device), torch.empty(0, dtype=x.dtype, device=x.device),
@@ -138,7 +138,7 @@ class CudaBackend:
         -> (keys int64 [n + 1], unit): keys[i] = (distance bits << 32) | neighbour for the best pair this part saw,
         keys[n] = completeness flag; an element-wise MIN over the parts merges them."""
         n, d = x.shape
-        unit, ub = self.normalize_rows(x, want_bf16=True)
+        unit, ub = self.normalize_rows(x, want_f16=True)
         bests = None
         if reduce_max is not None and parts > 1:
             bests = torch.empty(n, dtype=torch.int32, device=x.device)
@@ -162,10 +162,10 @@ class CudaBackend:
         flags = torch.stack((keys[n], status[0].to(torch.int64))).tolist()
         return nn, dist, flags[0] == 1 and flags[1] == 0
 
-    def screen_scores_debug(self, q_bf16, x_bf16):
-        nq, n = q_bf16.shape[0], x_bf16.shape[0]
-        out = torch.zeros((nq, n), dtype=torch.float32, device=x_bf16.device)
-        _lib.call("slic_screen_scores_debug", _p(q_bf16), nq, _p(x_bf16), n, x_bf16.shape[1], _p(out), self._stream())
+    def screen_scores_debug(self, q_f16, x_f16):
+        nq, n = q_f16.shape[0], x_f16.shape[0]
+        out = torch.zeros((nq, n), dtype=torch.float32, device=x_f16.device)
+        _lib.call("slic_screen_scores_debug", _p(q_f16), nq, _p(x_f16), n, x_f16.shape[1], _p(out), self._stream())
         return out
 
     def distance_matrix(self, q, x, metric="cosine", same=False):
@@ -183,17 +183,17 @@ class CudaBackend:
         _lib.call("slic_rows_topk", _p(mat), nq, n, mat.stride(0), _DT[mat.dtype], k, _p(idx), _p(val), self._stream())
         return idx, val
 
-    def topk_cosine(self, q_unit, x_unit, k, self_offset=-1, q_bf16=None, x_bf16=None, eps=0.0):
-        """Top-k cosine neighbours, ascending distance, ties -> lowest column.  With the bf16 copies of both
+    def topk_cosine(self, q_unit, x_unit, k, self_offset=-1, q_f16=None, x_f16=None, eps=0.0):
+        """Top-k cosine neighbours, ascending distance, ties -> lowest column.  With the f16 copies of both
         sides and k <= 64 on a large database: tcgen05 screen + exact re-rank (slic_topk_cosine_tc);
         otherwise the exact kernels (slic_topk_cosine)."""
         nq, d = q_unit.shape
         n = x_unit.shape[0]
         idx = torch.empty((nq, k), dtype=torch.int32, device=x_unit.device)
         val = torch.empty((nq, k), dtype=x_unit.dtype, device=x_unit.device)
-        if q_bf16 is not None and x_bf16 is not None and k <= TOPK_SCREEN_MAX_K and n >= SCREEN_MIN_ROWS:
+        if q_f16 is not None and x_f16 is not None and k <= TOPK_SCREEN_MAX_K and n >= SCREEN_MIN_ROWS:
             stats = torch.zeros(4, dtype=torch.int32, device=x_unit.device)
-            _lib.call("slic_topk_cosine_tc", _p(q_unit), _p(q_bf16), nq, _p(x_unit), _p(x_bf16), n, d, x_bf16.shape[1],
+            _lib.call("slic_topk_cosine_tc", _p(q_unit), _p(q_f16), nq, _p(x_unit), _p(x_f16), n, d, x_f16.shape[1],
                       _DT[x_unit.dtype], k, self_offset, float(eps), _p(idx), _p(val), _p(stats), self._stream())
             self.last_stats = stats
             return idx, val
@@ -205,9 +205,9 @@ class CudaBackend:
         """Normalise both sides (sklearn's normalize) and return their top-k cosine neighbours; picks the
         tensor-core path when the shape allows it.  same=True: q is x, self excluded."""
         use_screen = x.shape[0] >= SCREEN_MIN_ROWS and k <= TOPK_SCREEN_MAX_K
-        ux, xb = self.normalize_rows(x, want_bf16=use_screen)
-        uq, qb = (ux, xb) if same else self.normalize_rows(q, want_bf16=use_screen)
-        return self.topk_cosine(uq, ux, k, self_offset=0 if same else -1, q_bf16=qb, x_bf16=xb)
+        ux, xb = self.normalize_rows(x, want_f16=use_screen)
+        uq, qb = (ux, xb) if same else self.normalize_rows(q, want_f16=use_screen)
+        return self.topk_cosine(uq, ux, k, self_offset=0 if same else -1, q_f16=qb, x_f16=xb)
 
     def hit_at_k(self, topk_idx, q_labels, x_labels, ks):
         ks_t = torch.tensor(list(ks), dtype=torch.int32, device=topk_idx.device)

@@ -8,7 +8,7 @@ Same call signature and return values as the reference's FINCH (finch.py:108-178
 What runs where
   host (this file): the level loop and its exit rules, exactly as finch.py:134-176 has them.
   device (libslic_b200.so through backend.CudaBackend):
-    a2  first neighbours   slic_normalize_rows + slic_nn_top1 (tcgen05 bf16 screen, exact re-rank in
+    a2  first neighbours   slic_normalize_rows + slic_nn_top1 (tcgen05 f16 screen, exact re-rank in
                            float32 at level 0 / float64 at levels >= 1) or slic_nn_exact_top1 (small n)
     a4  components         slic_finch_components (union-find on nn[], optional min_sim cut)
     a5/a6 merge + means    slic_compose_labels, slic_segmented_mean (float64)

@@ -56,8 +56,8 @@ def pdist_v2(vector1, vector2, eps=1e-6, dist_metric='cosine', backend=None):
     a, b = _f32_on_device(be, vector1), _f32_on_device(be, vector2)
     if dist_metric == 'euclidean':
         return be.distance_matrix(a, b, metric="euclidean")
-    ua, _ = be.normalize_rows(a, want_bf16=False)
-    ub, _ = be.normalize_rows(b, want_bf16=False)
+    ua, _ = be.normalize_rows(a, want_f16=False)
+    ub, _ = be.normalize_rows(b, want_f16=False)
     return be.distance_matrix(ua, ub, metric="cosine")
 
 

@@ -73,7 +73,7 @@ int exact_topk_cosine_rows(const void* q, const int* q_rows, int64_t nq, const v
 
 // nn_screen_tc.cu: level-0 first-neighbour search whose database is still being uploaded (finch_driver.cu).
 // gates[c] (device int32, zero-initialised) becomes non-zero once rows [c * chunk_rows, (c + 1) * chunk_rows) of the
-// bf16 matrix are in place; `after` runs on the host right after the screen kernel has been launched.
+// f16 matrix are in place; `after` runs on the host right after the screen kernel has been launched.
 struct GateSpec {
     const int* gates;
     int num_chunks;
@@ -89,8 +89,8 @@ bool screen_self_search_is_symmetric(int64_t n);
 // stats_ext (device, 8 ints, optional): asynchronous mode - the call never waits for the device and leaves
 // {[1] rows still to be finished exactly, [4] pipeline error, [5] candidate-log overflow} there; any non-zero value
 // means the result is incomplete and the search must be repeated through the synchronous path (slic_nn_top1).
-int nn_top1_f32_gated(const float* q_unit, const uint16_t* q_bf16, int64_t nq, const float* x_unit,
-                      const uint16_t* x_bf16, int64_t n, int d, int d_pad, int64_t self_offset, float eps, int* idx_out,
+int nn_top1_f32_gated(const float* q_unit, const uint16_t* q_f16, int64_t nq, const float* x_unit,
+                      const uint16_t* x_f16, int64_t n, int d, int d_pad, int64_t self_offset, float eps, int* idx_out,
                       float* dist_out, int* stats_out, const GateSpec* gate, AfterScreenFn after, void* after_ctx,
                       cudaStream_t st, int* stats_ext = nullptr);
 // self-search of all rows (first neighbour + distance in `dtype`), asynchronous as above
@@ -134,7 +134,9 @@ struct SmallLevelsArgs {
     int* parent;             // [rows]
     int use_filter;          // finch.py:51-52 applies (level 0 had dense distances and ensure_early_exit)
     const float* min_sim_dev;
+    unsigned long long* trace;   // optional [SMALL_TRACE_STAMPS] globaltimer stamps at the phase boundaries (diagnostic)
 };
+constexpr int SMALL_TRACE_STAMPS = 96;
 size_t small_levels_gram_elems(int64_t m);
 int launch_small_levels(const SmallLevelsArgs& args, cudaStream_t st);
 

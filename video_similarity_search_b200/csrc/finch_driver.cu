@@ -10,7 +10,7 @@
 // The level loop follows the reference line by line (exit rules finch.py:151-163, min_sim mode :142-144, the
 // "no dense distances above 70 000 rows" control flow :30-38); every numeric step is one of the kernels behind
 // include/slic_b200.h.  Host work per level: one 4-byte read-back of the cluster count.
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -286,7 +286,7 @@ static int finch_levels(const float* data, int64_t n, int d, const Level0& l0, b
     seed[1] = 0;
     for (size_t l = 0; l < num_clust.size(); ++l) seed[2 + l] = num_clust[l];
     SLIC_CUDA_OK(cudaMemcpyAsync(summary.ptr, seed, (2 + num_clust.size()) * sizeof(int), cudaMemcpyHostToDevice, st));
-    Scratch sl_sums, sl_counts, sl_means, sl_unit, sl_gram, sl_nn, sl_dist, sl_parent;
+    Scratch sl_sums, sl_counts, sl_means, sl_unit, sl_gram, sl_nn, sl_dist, sl_parent, sl_trace;
     const int64_t m_in = num_clust.back();
     if (loop_open && m_in > 1) {
         SLIC_CUDA_OK(sl_sums.alloc((size_t)m_in * d * sizeof(double), st));
@@ -316,7 +316,26 @@ static int finch_levels(const float* data, int64_t n, int d, const Level0& l0, b
         a.parent = sl_parent.as<int>();
         a.use_filter = (have_min_sim && m_in <= FLANN_THRESHOLD) ? 1 : 0;
         a.min_sim_dev = ms.as<float>();
+        a.trace = nullptr;
+        static int small_trace = -1;   // SLIC_SMALL_TRACE=1: print the phase timeline of the device-side level loop
+        if (small_trace < 0) {
+            const char* e = getenv("SLIC_SMALL_TRACE");
+            small_trace = e && atoi(e) == 1 ? 1 : 0;
+        }
+        if (small_trace) {
+            SLIC_CUDA_OK(sl_trace.alloc(SMALL_TRACE_STAMPS * sizeof(unsigned long long), st));
+            SLIC_CUDA_OK(cudaMemsetAsync(sl_trace.ptr, 0, SMALL_TRACE_STAMPS * sizeof(unsigned long long), st));
+            a.trace = sl_trace.as<unsigned long long>();
+        }
         SLIC_PROPAGATE(launch_small_levels(a, st));
+        if (small_trace) {
+            unsigned long long h[SMALL_TRACE_STAMPS];
+            SLIC_CUDA_OK(cudaMemcpyAsync(h, sl_trace.ptr, sizeof(h), cudaMemcpyDeviceToHost, st));
+            SLIC_CUDA_OK(cudaStreamSynchronize(st));
+            fprintf(stderr, "[slic] small levels from m=%lld: phase stamps (us since start):", (long long)m_in);
+            for (int i = 1; i < SMALL_TRACE_STAMPS && h[i]; ++i) fprintf(stderr, " %.1f", (double)(h[i] - h[0]) * 1e-3);
+            fprintf(stderr, "\n");
+        }
     }
     {
         const int64_t want = ceil_div(n * 8, 256);

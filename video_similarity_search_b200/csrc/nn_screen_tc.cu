@@ -5,7 +5,7 @@
 //
 // Work decomposition
 //   unit  = (128-row query block) x (one of `splits` contiguous column ranges)
-//   tile  = 128 x 256 scores of a unit, K = d_pad in 64-wide slabs (bf16, 128-byte swizzled rows)
+//   tile  = 128 x 256 scores of a unit, K = d_pad in 64-wide slabs (f16, 128-byte swizzled rows)
 //   CTA   = persistent, one per SM, walks units round-robin; 6 warps:
 //           warp 0  TMA producer   : cp.async.bulk.tensor of the A (16 KB) and B (32 KB) slab per stage
 //           warp 1  MMA issuer     : one thread issues tcgen05.mma (M128 N256 K16) x 4 per slab, commits to
@@ -22,11 +22,11 @@
 //   contains the exact first neighbour.  The common case costs one FMNMX3 per two scores plus one
 //   compare per 32; appends are rare (O(log n) per row).  A full list is first compacted against the
 //   current threshold; only if it is still full is the row flagged and later finished by the exact
-//   kernel - the result never depends on bf16 precision.
+//   kernel - the result never depends on f16 precision.
 //
 // Bound: tensor pipe.  Algorithmic work 2 * nq * n * d_pad flop; HBM traffic ~ (nq + n) * d_pad * 2 bytes.
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
@@ -47,10 +47,13 @@ constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
 // NCTA = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) works on a 256 x 256 tile; each CTA stages its own 128
 //           query rows of A and HALF of the B slab (16 KB) and the tensor cores of both SMs read both halves, so
 //           the L2 -> SM operand traffic per flop drops by a third and 6 stages fit instead of 4.
-// ARES (pairs only, d_pad <= 512): the unit's A rows (128 x d_pad bf16 <= 128 KB) are loaded ONCE per unit and stay
+// ARES (pairs only, d_pad <= 512): the unit's A rows (128 x d_pad f16 <= 128 KB) are loaded ONCE per unit and stay
 //           resident; only B slabs stream through the ring.  A is the one operand no other SM shares, so this removes
 //           most of the L2 -> SM traffic that bounds the streaming variants.
 constexpr int TC_ARES_MAX_SLABS = 8;
+// barrier block behind the operands: 38 eight-byte slots (pipeline barriers, TMEM slot, log counters, unit ring)
+constexpr uint32_t TC_BAR_BYTES = 320;
+constexpr int TC_UQ_DEPTH = 4;   // unit ring: ids of the units the scheduler has handed out, consumed in order by every role
 template <int NCTA, bool ARES, bool TOPK> struct TcCfg {
     static constexpr uint32_t B_ROWS = TC_BN / NCTA;
     static constexpr uint32_t B_BYTES = B_ROWS * TC_BK * 2;
@@ -62,14 +65,14 @@ template <int NCTA, bool ARES, bool TOPK> struct TcCfg {
     static constexpr uint32_t STAGE_BYTES = SPS * SLAB_BYTES;
     static constexpr int STAGES = ARES ? (TOPK ? 2 : 3) : (NCTA == 1 ? 4 : 3);
     static constexpr uint32_t OPERAND_BYTES = A_RES_BYTES + STAGES * STAGE_BYTES;            // 192 KB, ARES: 192 / 224 KB
-    static constexpr uint32_t SMEM_BYTES = OPERAND_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/ +
+    static constexpr uint32_t SMEM_BYTES = OPERAND_BYTES + TC_BAR_BYTES /*barriers, unit ring*/ + 960 /*alignment slack*/ +
                                            (TOPK ? 32768u : 0u) /*histograms*/;
     // symmetric variant: + 1 KB of column thresholds (float16, rounded down); the A-resident layout then leaves 768
     // bytes of alignment slack.  An SM has 228 KB of shared memory and every resident CTA reserves 1 KB of it: a
     // window above 226 KB would own the SM outright, and the kernels that feed a gated launch from another stream
     // (normalise, gate memset) could never become resident next to it - the launch would wait for itself.
     static constexpr uint32_t SYM_THR_BYTES = 2 * 2 * 128 * 2;   // [2 parities][2 halves][128 columns] float16
-    static constexpr uint32_t SYM_SMEM_BYTES = OPERAND_BYTES + 256 + SYM_THR_BYTES + (ARES ? 768u : 1024u);
+    static constexpr uint32_t SYM_SMEM_BYTES = OPERAND_BYTES + TC_BAR_BYTES + SYM_THR_BYTES + (ARES ? 704u : 960u);
     static constexpr uint32_t CORESIDENT_MAX_BYTES = 233472 - 2 * 1024;
     static_assert(TOPK || SYM_SMEM_BYTES <= CORESIDENT_MAX_BYTES,
                   "symmetric variant leaves no shared memory for a co-resident CTA of the upload stream");
@@ -87,10 +90,14 @@ constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 // measured at 22 % of the epilogue's stall samples, profiles/r1_sym_screen_kernel_ncu_full.txt.)
 constexpr int TC_THREADS_SYM = TC_THREADS + 32;
 constexpr int TC_TMEM_COLS = 512;
-// Screen error allowance: a bf16-rounded operand carries relative error <= 2^-9, a product of two <= 2^-8 (+2^-18),
-// so for unit rows |screened - exact| <= 2^-8 * sum|a_k b_k| <= 2^-8, plus fp32 accumulation (<= d * 2^-24 relative to
-// the same sum).  eps must be >= twice that: 2^-7 + 2^-11 covers d up to 4096.
-constexpr float TC_DEFAULT_EPS = 0.0078125f + 0.00048828125f;
+// Screen operands are IEEE half precision (float16: 11 significant bits; kind::f16 runs float16 and bfloat16 at the same
+// rate, and unit-vector components never leave float16's range).  Error allowance for unit rows: a component >= 2^-14
+// carries relative rounding error <= 2^-11, a product of two <= 2^-10 (+ 2^-22), so the sum over k is off by
+// <= 2^-10 * sum|a_k b_k| <= 2^-10; components in the subnormal range add <= 2^-25 each, <= 2^-18 in total for
+// d <= 4096; the tensor core's float32 accumulation (products exact, additions possibly truncated) adds <= d * 2^-23
+// <= 2^-11.  eps must be >= twice the worst-case |screened - exact|: 2 * (2^-10 + 2^-11 + 2^-18) < 2^-9 + 2^-10 + 2^-16.
+// (The first version screened in bfloat16 with eps = 2^-7 + 2^-11: 2.8 x as wide a band, several times the candidates.)
+constexpr float TC_DEFAULT_EPS = 0.001953125f + 0.0009765625f + 0.0000152587890625f;
 constexpr int TC_TOPK_MAX = 64;  // the top-k variant's per-row score histogram has saturating 8-bit counts: k must stay well below 255
 constexpr int TC_HIST_BINS = 128;
 constexpr int TC_HIST_STRIDE = 2 * TC_BM;   // one histogram per (row, column half)
@@ -132,6 +139,9 @@ struct ScreenParams {
     // chunks it touches), so that the column thresholds it reads are in place.  Affects speed only, never results.
     int* sync_counter;
     const int* sync_targets;
+    // Dynamic scheduling: units are handed out in list order from this global counter (zeroed before the launch) to
+    // whichever CTA pair becomes free - no pair idles while another still holds a queue of long units.
+    int* queue;
 };
 
 struct UnitInfo {
@@ -302,6 +312,64 @@ __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & TC_PEER_BIT_MASK) : "memory");
 }
+// cluster-scope forms for the unit ring: the scheduler writes the peer CTA's ring slot, then arrives on the peer's barrier
+__device__ __forceinline__ uint32_t peer_smem_addr(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t cluster_addr, uint32_t v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int* error_flag) {
+    uint32_t done = 0;
+    long long t0 = 0;
+    uint32_t polls = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if ((++polls & 0x3ff) == 0) {
+            long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 40000000000ll) {   // (a waiting role may legitimately sit behind a gated upload)
+                if (error_flag) atomicExch(error_flag, 1);
+                record_timeout(4, (int)bar, (int)parity);
+                __trap();
+            }
+        }
+    }
+}
+// Unit ring, consumer side.  Every role of a CTA pair (producers, MMA issuer, epilogue warps, threshold warp) walks the
+// SAME sequence of unit ids: the scheduler (the leader CTA's producer thread) draws them from the global queue and
+// writes them into slot k % TC_UQ_DEPTH of both CTAs' rings; a slot is reused once every reader of the pair has
+// arrived on the leader's "empty" barrier.  Called by one thread, or by all lanes of a warp together.
+struct UnitRing {
+    uint32_t full, val;        // own CTA's barriers / values
+    uint32_t empty_leader;     // shared::cluster address of the leader's "empty" barriers
+    int slot;
+    uint32_t phase;
+};
+__device__ __forceinline__ int ring_take(UnitRing& r, bool whole_warp, int* error_flag) {
+    mbar_wait_cluster(r.full + 8u * r.slot, r.phase, error_flag);
+    int u;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(u) : "r"(r.val + 4u * r.slot) : "memory");
+    if (whole_warp) __syncwarp();   // every lane holds the id before the slot is released
+    if (!whole_warp || (threadIdx.x & 31) == 0) mbar_arrive_release_cluster(r.empty_leader + 8u * r.slot);
+    if (++r.slot == TC_UQ_DEPTH) {
+        r.slot = 0;
+        r.phase ^= 1u;
+    }
+    return u;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -313,7 +381,7 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                           uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -325,7 +393,7 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                                uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -367,7 +435,7 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" : SLIC_V32_INOUT(v)::"memory");
 }
 
-// K-major, 128-byte-swizzled operand tile (rows of 64 bf16 = 128 B, 8-row groups 1024 B apart):
+// K-major, 128-byte-swizzled operand tile (rows of 64 f16 = 128 B, 8-row groups 1024 B apart):
 //   bits [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for swizzled K-major, 1),
 //   [32,46) stride byte offset >> 4 (1024 B), [46,48) descriptor version 1 (sm_100), [61,64) layout 2 = SWIZZLE_128B
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
@@ -379,14 +447,12 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
-// kind::f16 instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), both K-major,
-// N >> 3 at bits 17-22, M >> 4 at bits 24-28.
-constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
-                              ((uint32_t)(TC_BM >> 4) << 24);
+// kind::f16 instruction descriptor: D=f32 (bits 4-5 = 1), A=B=float16 (format fields at bits 7-9 and 10-12 = 0; 1 would
+// be bfloat16), both K-major, N >> 3 at bits 17-22, M >> 4 at bits 24-28.
+constexpr uint32_t TC_IDESC = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 
 // cta_group::2: the instruction spans both CTAs, M = 256
-constexpr uint32_t TC_IDESC_PAIR = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
-                                   ((uint32_t)((2 * TC_BM) >> 4) << 24);
+constexpr uint32_t TC_IDESC_PAIR = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)((2 * TC_BM) >> 4) << 24);
 
 // ---- candidate list maintenance (slow path, rare) -------------------------------------------
 struct RowState {
@@ -739,9 +805,13 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
     extern __shared__ uint8_t smem_raw[];
     // (the dynamic smem window starts at the same offset in both CTAs of a pair, so the aligned offsets agree)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    if constexpr (SYM) {
-        // the layout below needs OPERAND + 256 + 2048 bytes behind the aligned base (uniform across the grid)
-        if ((uint32_t)(smem - smem_raw) + Cfg::OPERAND_BYTES + 256 + Cfg::SYM_THR_BYTES > Cfg::SYM_SMEM_BYTES) {
+    {
+        // the layout needs OPERAND + barrier block (+ thresholds / histograms) behind the 1 KB-aligned base; the window
+        // is sized with less than 1 KB of slack, so check (uniform across the grid) instead of assuming
+        uint32_t dyn_bytes;
+        asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_bytes));
+        const uint32_t need = Cfg::OPERAND_BYTES + TC_BAR_BYTES + (SYM ? Cfg::SYM_THR_BYTES : 0u) + (TOPK ? TC_TOPK_SMEM : 0u);
+        if ((uint32_t)(smem - smem_raw) + need > dyn_bytes) {
             if (threadIdx.x == 0 && p.error_flag) atomicExch(p.error_flag, 2);
             return;
         }
@@ -756,13 +826,15 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 6);
     const uint32_t bar_thr_full = smem_u32(bars + 24);    // SYM [2]: thresholds of a tile are in place (threshold warp)
     const uint32_t bar_thr_empty = smem_u32(bars + 26);   // SYM [2]: the CTA's epilogue warps are done with them
+    const uint32_t bar_uq_full = smem_u32(bars + 28);     // [TC_UQ_DEPTH]: ring slot holds a unit id (own CTA's copy)
+    const uint32_t bar_uq_empty = smem_u32(bars + 32);    // [TC_UQ_DEPTH]: every role of the pair has read it (leader's used)
+    const uint32_t uq_val = smem_u32(bars + 36);          // [TC_UQ_DEPTH] int32 unit ids, -1 = no more units
     const uint32_t smem_base = smem_u32(smem);                 // ARES: resident A, slab ks at + ks * 16 KB
     const uint32_t ring_base = smem_base + Cfg::A_RES_BYTES;   // operand ring
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool tracing = p.trace != nullptr;
     const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0u;   // 0 = leader: issues the MMAs of the pair
-    const int64_t group = blockIdx.x / NCTA, num_groups = gridDim.x / NCTA;
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
@@ -777,6 +849,11 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
         }
         mbar_init(bar_a_full, 1);
         mbar_init(bar_a_empty, 1);
+        for (int s = 0; s < TC_UQ_DEPTH; ++s) {
+            mbar_init(bar_uq_full + 8 * s, 1);   // the scheduler's arrive
+            // readers of a slot, pair-wide: 8 epilogue warps (+ threshold warp) per CTA, the leader's MMA issuer, the peer's producer
+            mbar_init(bar_uq_empty + 8 * s, NCTA * (TC_EPI_WARPS + (SYM ? 1 : 0)) + 1 + (NCTA - 1));
+        }
         if constexpr (SYM) {
             for (int b = 0; b < 2; ++b) {
                 mbar_init(bar_thr_full + 8 * b, 1);
@@ -805,6 +882,12 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
     const int64_t n_col_tiles = (p.n + TC_BN - 1) / TC_BN;
+    UnitRing ring;
+    ring.full = bar_uq_full;
+    ring.val = uq_val;
+    ring.empty_leader = peer_smem_addr(bar_uq_empty, 0u);
+    ring.slot = 0;
+    ring.phase = 0u;
 
     if (warp == 0) {
         // ===================== TMA producer (every CTA: its own A rows, its share of the B slab) =====================
@@ -812,7 +895,30 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
             int stage = 0;
             uint32_t phase = 0, a_phase = 0;
             unsigned long long t_wait = 0;
-            for (int64_t u = group; u < p.num_units; u += num_groups) {
+            const bool scheduler = cta_rank == 0;
+            // (p.queue == nullptr: static striding over the CTA pairs - kept for A/B measurements, SLIC_SCREEN_STATIC=1)
+            const int stride_groups = (int)(gridDim.x / NCTA);
+            int u_next = scheduler ? (p.queue ? atomicAdd(p.queue, 1) : (int)(blockIdx.x / NCTA)) : 0;
+            while (true) {
+                int u;
+                if (scheduler) {
+                    // hand the next unit to every role of the pair (-1: the queue is exhausted)
+                    u = u_next < p.num_units ? u_next : -1;
+                    mbar_wait_cluster(bar_uq_empty + 8u * ring.slot, ring.phase ^ 1u, p.error_flag);
+#pragma unroll
+                    for (uint32_t r = 0; r < (uint32_t)NCTA; ++r) {
+                        st_cluster_u32(peer_smem_addr(uq_val + 4u * ring.slot, r), (uint32_t)u);
+                        mbar_arrive_release_cluster(peer_smem_addr(bar_uq_full + 8u * ring.slot, r));
+                    }
+                    if (++ring.slot == TC_UQ_DEPTH) {
+                        ring.slot = 0;
+                        ring.phase ^= 1u;
+                    }
+                    if (u >= 0) u_next = p.queue ? atomicAdd(p.queue, 1) : u_next + stride_groups;   // (the round trip overlaps this unit's loads)
+                } else {
+                    u = ring_take(ring, false, p.error_flag);
+                }
+                if (u < 0) break;
                 const UnitInfo ui = unit_info(p, u, n_col_tiles);
                 const int64_t row_block = ui.row_unit * NCTA + cta_rank;
                 if (ui.gate >= 0) gate_wait(p.gates + ui.gate, p.error_flag);
@@ -874,7 +980,13 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
             uint32_t acc_phase = 0, a_phase = 0;
             unsigned long long t_acc = 0, t_smem = 0;
             const long long t_begin = tracing ? clock64() : 0;
-            for (int64_t u = group; u < p.num_units; u += num_groups) {
+            unsigned long long t_ring = 0, n_units = 0;
+            while (true) {
+                const long long tr0 = tracing ? clock64() : 0;
+                const int u = ring_take(ring, false, p.error_flag);
+                if (tracing) t_ring += (unsigned long long)(clock64() - tr0);
+                if (u < 0) break;
+                ++n_units;
                 const int n_tiles = unit_info(p, u, n_col_tiles).count;
                 if constexpr (ARES) {
                     mbar_wait_traced(bar_a_full, a_phase, p.error_flag, t_smem, tracing);
@@ -897,12 +1009,12 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
                                 const uint64_t db = umma_smem_desc(ARES ? sl_addr : sl_addr + TC_A_BYTES);
 #pragma unroll
                                 for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
-                                    // advancing 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the address field
+                                    // advancing 16 f16 = 32 bytes along K inside the swizzle atom: +2 in the address field
                                     if constexpr (NCTA == 2)
-                                        umma_bf16_pair(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), TC_IDESC_PAIR,
+                                        umma_f16_pair(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), TC_IDESC_PAIR,
                                                        (uint32_t)((ks | j | k) != 0));
                                     else
-                                        umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), TC_IDESC,
+                                        umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), TC_IDESC,
                                                   (uint32_t)((ks | j | k) != 0));
                                 }
                             }
@@ -927,6 +1039,8 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
                 atomicAdd(p.trace + 1, t_acc);    // MMA issuer stalled on a free accumulator (epilogue too slow)
                 atomicAdd(p.trace + 2, t_smem);   // MMA issuer stalled on operands (TMA / L2 too slow)
                 atomicAdd(p.trace + 3, (unsigned long long)(clock64() - t_begin));   // MMA issuer total
+                atomicAdd(p.trace + 8, t_ring);    // MMA issuer waited for the next unit id (scheduler / pre-pass hand-over)
+                atomicAdd(p.trace + 10, n_units);
             }
         }
     } else if (SYM && warp == 2 + TC_EPI_WARPS) {
@@ -934,10 +1048,10 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
         // For every tile strictly right of the diagonal (the epilogue's "column role"): threshold of column c =
         // best score published for row c so far - eps, as float16 rounded DOWN (a lower threshold only adds candidates;
         // 2^-11 against eps = 2^-7), with a finite lower bound (threshold - masked score = +inf, never NaN).
-        uint16_t* thr_buf = reinterpret_cast<uint16_t*>(smem + Cfg::OPERAND_BYTES + 256);   // [2 buffers][2 halves][128]
+        uint16_t* thr_buf = reinterpret_cast<uint16_t*>(smem + Cfg::OPERAND_BYTES + TC_BAR_BYTES);   // [2 buffers][2 halves][128]
         constexpr unsigned ENC_POS_INF = 0xff800000u;
         unsigned seq = 0;
-        for (int64_t u = group; u < p.num_units; u += num_groups) {
+        for (int u; (u = ring_take(ring, true, p.error_flag)) >= 0;) {
             const UnitInfo ui = unit_info(p, u, n_col_tiles);
             if (!ui.coldir) continue;
             if (p.sync_counter) {   // published bests of the pre-pass are in place (speed only, as for the epilogue)
@@ -982,9 +1096,9 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
         cx.tracing = tracing;
         cx.n_trig = 0;
         cx.n_chunks = 0;
-        if constexpr (TOPK) cx.hist = smem + Cfg::OPERAND_BYTES + 256 + half * TC_BM + row_in_tile;
+        if constexpr (TOPK) cx.hist = smem + Cfg::OPERAND_BYTES + TC_BAR_BYTES + half * TC_BM + row_in_tile;
         unsigned int* s_logcnt = reinterpret_cast<unsigned int*>(bars + 20) + (warp - 2);   // spare bytes of the barrier block
-        uint16_t* thr_buf = reinterpret_cast<uint16_t*>(smem + Cfg::OPERAND_BYTES + 256);   // SYM: float16 [2 parities][2 halves][128]
+        uint16_t* thr_buf = reinterpret_cast<uint16_t*>(smem + Cfg::OPERAND_BYTES + TC_BAR_BYTES);   // SYM: float16 [2 parities][2 halves][128]
         unsigned tile_seq = 0;
         const int64_t log_region_id = (int64_t)blockIdx.x * TC_EPI_WARPS + (warp - 2);
         if constexpr (SYM) {
@@ -997,8 +1111,21 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
             cx.lg.region = p.log_region;
             cx.lg.overflow = p.cand_flags;
         }
-        for (int64_t u = group; u < p.num_units; u += num_groups) {
+        unsigned long long t_unit = 0;
+        while (true) {
+            const long long tr0 = tracing ? clock64() : 0;
+            const int u = ring_take(ring, true, p.error_flag);
+            if (u < 0) break;
             const UnitInfo ui = unit_info(p, u, n_col_tiles);
+            if constexpr (SYM) {
+                // a triangle unit reads published thresholds: not before every pre-pass unit it depends on has finished
+                // (the producer waits for the same counter, but this warp runs ahead of the first accumulator)
+                if (ui.coldir && p.sync_counter) {
+                    if (lane == 0) counter_wait(p.sync_counter, __ldg(p.sync_targets + ui.gate + 1), p.error_flag);
+                    __syncwarp();
+                }
+            }
+            if (tracing) t_unit += (unsigned long long)(clock64() - tr0);
             const int64_t row_block = ui.row_unit * NCTA + cta_rank;
             cx.row = row_block * TC_BM + row_in_tile;
             cx.row_ok = cx.row < p.nq;
@@ -1014,12 +1141,6 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
                 cx.st.thr = bin_edge(0) - p.eps;
                 cx.pd.n = 0;
             } else if constexpr (SYM) {
-                // a triangle unit reads published thresholds: not before every pre-pass unit it depends on has finished
-                // (the producer waits for the same counter, but this warp runs ahead of the first accumulator)
-                if (ui.coldir && p.sync_counter) {
-                    if (lane == 0) counter_wait(p.sync_counter, __ldg(p.sync_targets + ui.gate + 1), p.error_flag);
-                    __syncwarp();
-                }
                 // start from the best score any CTA has published for this row (pre-pass, earlier units, column roles)
                 cx.st.best = cx.row_ok ? dec_score(__ldcg(p.best_enc + cx.row)) : -CUDART_INF_F;
                 cx.st.thr = cx.st.best - p.eps;
@@ -1159,6 +1280,7 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
             atomicAdd(p.trace + 5, (unsigned long long)(clock64() - t_begin));   // epilogue warp 0 total
             atomicAdd(p.trace + 6, cx.n_trig);    // 32-column chunks in which some row had a candidate
             atomicAdd(p.trace + 7, cx.n_chunks);
+            atomicAdd(p.trace + 9, t_unit);    // epilogue warp 0 waited for a unit id / the pre-pass hand-over
         }
     }
 
@@ -1406,7 +1528,7 @@ static int get_encode_fn(EncodeTiledFn* out) {
     return SLIC_OK;
 }
 
-// rows x d_pad bf16, row-major; box = 64 (K) x box_rows, 128-byte swizzle, out-of-bounds rows read as zero
+// rows x d_pad f16, row-major; box = 64 (K) x box_rows, 128-byte swizzle, out-of-bounds rows read as zero
 static int make_tmap(CUtensorMap* map, const uint16_t* base, int64_t rows, int d_pad, int box_rows) {
     EncodeTiledFn enc;
     SLIC_PROPAGATE(get_encode_fn(&enc));
@@ -1414,7 +1536,7 @@ static int make_tmap(CUtensorMap* map, const uint16_t* base, int64_t rows, int d
     cuuint64_t gstride[1] = {(cuuint64_t)d_pad * 2};
     cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<uint16_t*>(base), gdim, gstride, box, estr,
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<uint16_t*>(base), gdim, gstride, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -1426,7 +1548,7 @@ static int make_tmap(CUtensorMap* map, const uint16_t* base, int64_t rows, int d
 
 // optional CUDA-event timing of the screen kernel on its own stream (bench.py's roofline leg)
 static bool g_profile = false, g_have_sample = false;
-static unsigned long long* g_trace = nullptr;   // device [8], allocated by slic_screen_trace(1)
+static unsigned long long* g_trace = nullptr;   // device [12], allocated by slic_screen_trace(1)
 static cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
 static double g_last_flop = 0.0, g_last_exec_flop = 0.0;
 
@@ -1551,7 +1673,7 @@ const char* timeout_record_text() {
     return buf;
 }
 
-static int launch_screen(const uint16_t* q_bf16, int64_t nq, const uint16_t* x_bf16, int64_t n, int d_pad,
+static int launch_screen(const uint16_t* q_f16, int64_t nq, const uint16_t* x_f16, int64_t n, int d_pad,
                          int64_t self_offset, float eps, int cap, const ScreenPlan& pl, int* cand_idx, float* cand_score,
                          int* cand_cnt, int* cand_flags, float* dump, int* error_flag, cudaStream_t st, int topk = 0,
                          float* cand_kth = nullptr, const int4* unit_table = nullptr, const int* gates = nullptr,
@@ -1560,8 +1682,8 @@ static int launch_screen(const uint16_t* q_bf16, int64_t nq, const uint16_t* x_b
     const int ncta = screen_ncta();
     if (gates) SLIC_PROPAGATE(arm_timeout_record());
     CUtensorMap tq, tx;
-    SLIC_PROPAGATE(make_tmap(&tq, q_bf16, nq, d_pad, TC_BM));
-    SLIC_PROPAGATE(make_tmap(&tx, x_bf16, n, d_pad, TC_BN / ncta));
+    SLIC_PROPAGATE(make_tmap(&tq, q_f16, nq, d_pad, TC_BM));
+    SLIC_PROPAGATE(make_tmap(&tx, x_f16, n, d_pad, TC_BN / ncta));
     ScreenParams p;
     p.nq = nq;
     p.n = n;
@@ -1588,6 +1710,18 @@ static int launch_screen(const uint16_t* q_bf16, int64_t nq, const uint16_t* x_b
     p.log_region = log_region;
     p.sync_counter = sync_counter;
     p.sync_targets = sync_targets;
+    Scratch queue;   // (freed in stream order, i.e. after the kernel)
+    SLIC_CUDA_OK(queue.alloc(sizeof(int), st));
+    SLIC_CUDA_OK(cudaMemsetAsync(queue.ptr, 0, sizeof(int), st));
+    p.queue = queue.as<int>();
+    {
+        static int static_sched = -1;
+        if (static_sched < 0) {
+            const char* e = getenv("SLIC_SCREEN_STATIC");
+            static_sched = e && atoi(e) == 1 ? 1 : 0;
+        }
+        if (static_sched) p.queue = nullptr;
+    }
     const bool sym = best_enc != nullptr;
     const bool is_topk = topk > 0;
     const bool ares = ncta == 2 && p.num_k_slabs <= TC_ARES_MAX_SLABS && screen_ares_allowed();
@@ -1657,8 +1791,10 @@ static int stage_to_device(void* dst_dev, const void* src, size_t bytes, cudaStr
     next = (next + 1) % SLOTS;
     if (s.used) SLIC_CUDA_OK(cudaEventSynchronize(s.done));
     if (s.cap < bytes) {
+        // (rare: a slot starts at 1 MB - the unit table of a 240 000-row search is 140 KB - because cudaFreeHost /
+        // cudaHostAlloc synchronise the device and take milliseconds)
         if (s.host) SLIC_CUDA_OK(cudaFreeHost(s.host));
-        s.cap = bytes < 4096 ? 4096 : bytes + bytes / 2;
+        s.cap = bytes < ((size_t)1 << 20) ? ((size_t)1 << 20) : bytes + bytes / 2;
         SLIC_CUDA_OK(cudaHostAlloc(&s.host, s.cap, cudaHostAllocDefault));
     }
     if (!s.done) SLIC_CUDA_OK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
@@ -1727,6 +1863,9 @@ static int plan_screen_sym(int64_t n, int part, int parts, const GateSpec* g, Sc
     // the triangle share against +0.1 ms per 16 tiles here)
     int samples = mode == SYM_BESTS ? (parts >= 4 ? 4 * SYM_SAMPLE_TILES : SYM_SAMPLE_TILES) : SYM_SAMPLE_TILES / parts;
     if (mode == SYM_BESTS && samples > span / 4) samples = (int)(span / 4);   // small inputs: a sample, not the whole square
+    // small inputs (a hierarchy's level 1): the pre-pass must stay a sample - measured at 21 436 x 512 float64 centroids:
+    // 16 / 10 / 4 sample tiles -> 0.88 / 0.79 / 0.72 ms for the whole search
+    if (mode == SYM_FULL && T < 128 && samples > T / 16) samples = (int)(T / 16);
     if (samples < 4) samples = 4;
     if (const char* e = getenv("SLIC_SYM_SAMPLES")) {   // experiments only
         const int v = atoi(e);
@@ -1747,16 +1886,28 @@ static int plan_screen_sym(int64_t n, int part, int parts, const GateSpec* g, Sc
         const int64_t c1 = c0 + SYM_CHUNK_TILES < T ? c0 + SYM_CHUNK_TILES : T;
         for (int64_t r = 0; r < c1; ++r) total_tiles += c1 - (r > c0 ? r : c0);
     }
+    // Unit length: units are handed out dynamically (p.queue), so the last ones to finish leave at most one unit of
+    // idle time per CTA pair - keep a unit well below a pair's share of the work (level 1 of a hierarchy has ~60 tiles per
+    // pair in total), but long enough to amortise the reload of the resident A rows (one tile's worth of traffic).
+    const int64_t pairs = num_sms() / 2 > 0 ? num_sms() / 2 : 1;
+    int64_t unit_len = total_tiles / parts / (pairs * 12);
+    unit_len = unit_len < 8 ? 8 : (unit_len > SYM_CHUNK_TILES ? SYM_CHUNK_TILES : unit_len);
+    if (const char* e = getenv("SLIC_SYM_UNIT_TILES")) {   // experiments only
+        const int v = atoi(e);
+        if (v >= 1 && v <= SYM_CHUNK_TILES) unit_len = v;
+    }
     int64_t seen_tiles = 0;
     for (int64_t c0 = 0; c0 < T && mode != SYM_BESTS; c0 += SYM_CHUNK_TILES) {
         const int64_t c1 = c0 + SYM_CHUNK_TILES < T ? c0 + SYM_CHUNK_TILES : T;
         for (int64_t r = 0; r < c1; ++r) {
-            const int64_t ct0 = r > c0 ? r : c0;
-            const int64_t owner = seen_tiles * parts / total_tiles;   // < parts: seen_tiles < total_tiles here
-            seen_tiles += c1 - ct0;
-            if (owner != part) continue;
             const int gate = g ? (int)((c1 - 1) / chunk_tiles_gate) : -1;   // column chunk >= row chunk
-            table->push_back(unit_entry(r, ct0, (int)(c1 - ct0), 1, gate, 0, nocol == 0));
+            for (int64_t ct0 = r > c0 ? r : c0; ct0 < c1; ct0 += unit_len) {
+                const int64_t cnt = c1 - ct0 < unit_len ? c1 - ct0 : unit_len;
+                const int64_t owner = seen_tiles * parts / total_tiles;   // < parts: seen_tiles < total_tiles here
+                seen_tiles += cnt;
+                if (owner != part) continue;
+                table->push_back(unit_entry(r, ct0, (int)cnt, 1, gate, 0, nocol == 0));
+            }
         }
     }
     if (g)   // consume the upload in arrival order: (pre-pass, triangle) of gate 0, then of gate 1, ...
@@ -1807,14 +1958,14 @@ static bool screen_sym_allowed();
 constexpr int64_t SYM_MIN_ROWS_FWD = 16384;   // below: too few tiles to fill the machine with half of them
 
 template <typename T>
-static int nn_top1_impl(const T* q_unit, const uint16_t* q_bf16, int64_t nq, const T* x_unit, const uint16_t* x_bf16,
+static int nn_top1_impl(const T* q_unit, const uint16_t* q_f16, int64_t nq, const T* x_unit, const uint16_t* x_f16,
                         int64_t n, int d, int d_pad, int64_t self_offset, float eps, int* idx_out, T* dist_out,
                         int* stats_out, cudaStream_t st, const GateSpec* gate = nullptr, AfterScreenFn after = nullptr,
                         void* after_ctx = nullptr, int* stats_ext = nullptr) {
     // stats_ext: asynchronous mode, see nn_top1_sym_impl ([1] rows to finish exactly, [4] pipeline error, [5] log overflow)
-    if (q_bf16 == x_bf16 && q_unit == x_unit && nq == n && self_offset == 0 && n >= SYM_MIN_ROWS_FWD && screen_sym_allowed()) {
+    if (q_f16 == x_f16 && q_unit == x_unit && nq == n && self_offset == 0 && n >= SYM_MIN_ROWS_FWD && screen_sym_allowed()) {
         bool overflowed = false;
-        SLIC_PROPAGATE(nn_top1_sym_impl<T>(x_unit, x_bf16, n, d, d_pad, eps, idx_out, dist_out, stats_out, st, 0, 1, gate,
+        SLIC_PROPAGATE(nn_top1_sym_impl<T>(x_unit, x_f16, n, d, d_pad, eps, idx_out, dist_out, stats_out, st, 0, 1, gate,
                                            after, after_ctx, &overflowed, 0, nullptr, nullptr, stats_ext));
         if (stats_ext || !overflowed) return SLIC_OK;
         // (degenerate input: almost every pair within eps of the best) - the full square with per-row lists and the
@@ -1843,7 +1994,7 @@ static int nn_top1_impl(const T* q_unit, const uint16_t* q_bf16, int64_t nq, con
         stats_dev = stats.as<int>();
     }
     SLIC_CUDA_OK(cudaMemsetAsync(stats_dev, 0, 8 * sizeof(int), st));
-    SLIC_PROPAGATE(launch_screen(q_bf16, nq, x_bf16, n, d_pad, self_offset, eps, TC_CAP, pl, ci.as<int>(), cs.as<float>(),
+    SLIC_PROPAGATE(launch_screen(q_f16, nq, x_f16, n, d_pad, self_offset, eps, TC_CAP, pl, ci.as<int>(), cs.as<float>(),
                                  cc.as<int>(), cf.as<int>(), nullptr, stats_dev + 4, st, 0, nullptr,
                                  gate ? table_dev.as<int4>() : nullptr, gate ? gate->gates : nullptr));
     // gated: the caller now enqueues the upload that feeds the running kernel and makes `st` wait for its end
@@ -1877,7 +2028,7 @@ static int nn_top1_impl(const T* q_unit, const uint16_t* q_bf16, int64_t nq, con
 }
 
 template <typename T>
-static int topk_tc_impl(const T* q_unit, const uint16_t* q_bf16, int64_t nq, const T* x_unit, const uint16_t* x_bf16,
+static int topk_tc_impl(const T* q_unit, const uint16_t* q_f16, int64_t nq, const T* x_unit, const uint16_t* x_f16,
                         int64_t n, int d, int d_pad, int k, int64_t self_offset, float eps, int* idx_out, T* dist_out,
                         int* stats_out, cudaStream_t st) {
     const ScreenPlan pl = plan_screen_topk(nq, n, k);
@@ -1892,7 +2043,7 @@ static int topk_tc_impl(const T* q_unit, const uint16_t* q_bf16, int64_t nq, con
     SLIC_CUDA_OK(ovr.alloc(nq * sizeof(int), st));
     SLIC_CUDA_OK(stats.alloc(8 * sizeof(int), st));
     SLIC_CUDA_OK(cudaMemsetAsync(stats.ptr, 0, 8 * sizeof(int), st));
-    SLIC_PROPAGATE(launch_screen(q_bf16, nq, x_bf16, n, d_pad, self_offset, eps, TC_CAP_TOPK, pl, ci.as<int>(),
+    SLIC_PROPAGATE(launch_screen(q_f16, nq, x_f16, n, d_pad, self_offset, eps, TC_CAP_TOPK, pl, ci.as<int>(),
                                  cs.as<float>(), cc.as<int>(), cf.as<int>(), nullptr, stats.as<int>() + 4, st, k,
                                  ck.as<float>()));
     rerank_topk_kernel<T><<<(unsigned)nq, RK_THREADS, 0, st>>>(q_unit, x_unit, nq, d, eps, TC_CAP_TOPK, 2 * pl.splits, k,
@@ -1943,6 +2094,26 @@ static bool screen_sym_allowed() {
 __global__ void flip_sign_bit_kernel(const unsigned int* __restrict__ in, int64_t n, unsigned int* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i] ^ 0x80000000u;
+}
+
+// all the per-launch state of a symmetric search in ONE launch: counters, log counts, row minima, row bests, outputs
+__global__ void sym_init_kernel(int* __restrict__ stats8, int* __restrict__ lcnt, int64_t regions,
+                                unsigned char* __restrict__ rmin_bytes, int64_t rmin_n_bytes, int* __restrict__ sync_counter,
+                                unsigned int* __restrict__ best, const unsigned int* __restrict__ bests_in, int64_t n,
+                                unsigned int* __restrict__ idx_out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 8) stats8[i] = 0;
+    if (i == 0) *sync_counter = 0;
+    if (i < regions) lcnt[i] = 0;
+    if (i < n) {
+        best[i] = bests_in ? (bests_in[i] ^ 0x80000000u) : ENC_NEG_INF;   // exchanged bests arrive in signed-comparable form
+        if (idx_out) idx_out[i] = 0x7fffffffu;
+    }
+    // row minima: all-ones (above every distance's bit pattern), 16 bytes per thread
+    const int64_t b = i * 16;
+    if (b + 16 <= rmin_n_bytes) *reinterpret_cast<uint4*>(rmin_bytes + b) = make_uint4(~0u, ~0u, ~0u, ~0u);
+    else
+        for (int64_t k = b; k < rmin_n_bytes; ++k) rmin_bytes[k] = 0xff;
 }
 
 __global__ void fill_u32_kernel(unsigned int* out, int64_t n, unsigned int v) {
@@ -2066,12 +2237,19 @@ static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d,
     if (mode == SYM_BESTS) capacity = SYM_LOG_MIN;   // the records of phase 1 are discarded (an overflow is harmless)
     const int64_t region = ceil_div(capacity, regions);
     SLIC_REQUIRE(region < ((int64_t)1 << 31), "symmetric screen: log region too large");
-    Scratch table_dev, lq, lnb, ls, lcnt, best, rmin, edist, ovr, stats, sync;
-    SLIC_CUDA_OK(table_dev.alloc(table.size() * sizeof(int4), st));
-    SLIC_PROPAGATE(stage_to_device(table_dev.ptr, table.data(), table.size() * sizeof(int4), st));
-    SLIC_CUDA_OK(sync.alloc((targets.size() + 1) * sizeof(int), st));   // [0] counter, [1..] targets
-    SLIC_CUDA_OK(cudaMemsetAsync(sync.ptr, 0, sizeof(int), st));
-    SLIC_PROPAGATE(stage_to_device(sync.as<int>() + 1, targets.data(), targets.size() * sizeof(int), st));
+    Scratch table_dev, lq, lnb, ls, lcnt, best, rmin, edist, ovr, stats;
+    // unit table followed by the barrier targets: one transfer.  sync: [0] counter, then the targets (device view)
+    const size_t table_bytes = table.size() * sizeof(int4);
+    SLIC_CUDA_OK(table_dev.alloc(table_bytes + (targets.size() + 4) * sizeof(int), st));
+    {
+        std::vector<unsigned char> blob(table_bytes + (targets.size() + 1) * sizeof(int));
+        memcpy(blob.data(), table.data(), table_bytes);
+        const int zero = 0;
+        memcpy(blob.data() + table_bytes, &zero, sizeof(int));
+        memcpy(blob.data() + table_bytes + sizeof(int), targets.data(), targets.size() * sizeof(int));
+        SLIC_PROPAGATE(stage_to_device(table_dev.ptr, blob.data(), blob.size(), st));
+    }
+    int* sync_dev = reinterpret_cast<int*>(static_cast<unsigned char*>(table_dev.ptr) + table_bytes);
     SLIC_CUDA_OK(lq.alloc(regions * region * sizeof(int), st));
     SLIC_CUDA_OK(lnb.alloc(regions * region * sizeof(int), st));
     SLIC_CUDA_OK(ls.alloc(regions * region * sizeof(float), st));
@@ -2086,22 +2264,26 @@ static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d,
         stats_dev = stats.as<int>();
     }
     int* flag_dev = stats_dev + 5;   // the log-overflow flag lives in the same block: one read-back fetches everything
-    SLIC_CUDA_OK(cudaMemsetAsync(stats_dev, 0, 8 * sizeof(int), st));
-    SLIC_CUDA_OK(cudaMemsetAsync(lcnt.ptr, 0, regions * sizeof(int), st));
-    SLIC_CUDA_OK(cudaMemsetAsync(rmin.ptr, 0xff, n * sizeof(Bits), st));   // all-ones: above every distance's bits
-    if (bests_in)   // exchanged row bests (signed-comparable form) seed the thresholds
-        flip_sign_bit_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>((const unsigned int*)bests_in, n, best.as<unsigned int>());
-    else
-        fill_u32_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(best.as<unsigned int>(), n, ENC_NEG_INF);
-    SLIC_LAUNCH_OK();
-    if (idx_out) {
-        fill_u32_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>((unsigned int*)idx_out, n, 0x7fffffffu);
+    {
+        const int64_t rmin_bytes = n * (int64_t)sizeof(Bits);
+        int64_t threads = n > regions ? n : regions;
+        if (ceil_div(rmin_bytes, 16) > threads) threads = ceil_div(rmin_bytes, 16);
+        if (threads < 8) threads = 8;
+        sym_init_kernel<<<(unsigned)ceil_div(threads, 256), 256, 0, st>>>(stats_dev, lcnt.as<int>(), regions,
+                                                                         static_cast<unsigned char*>(rmin.ptr), rmin_bytes, sync_dev,
+                                                                         best.as<unsigned int>(), (const unsigned int*)bests_in, n,
+                                                                         (unsigned int*)idx_out);
         SLIC_LAUNCH_OK();
+    }
+    static int nowait = -1;   // experiments: SLIC_SYM_NOWAIT=1 lets triangle units start before the pre-pass has finished
+    if (nowait < 0) {
+        const char* e = getenv("SLIC_SYM_NOWAIT");
+        nowait = e && atoi(e) == 1 ? 1 : 0;
     }
     SLIC_PROPAGATE(launch_screen(ub, n, ub, n, d_pad, 0, eps, 0, pl, lnb.as<int>(), ls.as<float>(), lcnt.as<int>(),
                                  flag_dev, nullptr, stats_dev + 4, st, 0, nullptr, table_dev.as<int4>(),
                                  gate ? gate->gates : nullptr, best.as<unsigned int>(), exec_tiles, lq.as<int>(),
-                                 (int)region, sync.as<int>(), sync.as<int>() + 1));
+                                 (int)region, nowait ? nullptr : sync_dev, sync_dev + 1));
     if (g_profile && parts > 1) g_last_flop /= (double)parts;   // this process's share of the algorithmic 2 n^2 d
     if (after) SLIC_PROPAGATE(after(after_ctx));
     if (mode == SYM_BESTS) {   // phase 1 of the multi-GPU search: the row bests are the result, the log is discarded
@@ -2235,12 +2417,12 @@ bool screen_can_overlap_upload(int64_t n, int d_pad, int guest_threads, int gues
     return regs_ok && smem_ok && threads_ok;
 }
 
-int nn_top1_f32_gated(const float* q_unit, const uint16_t* q_bf16, int64_t nq, const float* x_unit,
-                      const uint16_t* x_bf16, int64_t n, int d, int d_pad, int64_t self_offset, float eps, int* idx_out,
+int nn_top1_f32_gated(const float* q_unit, const uint16_t* q_f16, int64_t nq, const float* x_unit,
+                      const uint16_t* x_f16, int64_t n, int d, int d_pad, int64_t self_offset, float eps, int* idx_out,
                       float* dist_out, int* stats_out, const GateSpec* gate, AfterScreenFn after, void* after_ctx,
                       cudaStream_t st, int* stats_ext) {
     if (eps <= 0.f) eps = TC_DEFAULT_EPS;
-    return nn_top1_impl<float>(q_unit, q_bf16, nq, x_unit, x_bf16, n, d, d_pad, self_offset, eps, idx_out, dist_out,
+    return nn_top1_impl<float>(q_unit, q_f16, nq, x_unit, x_f16, n, d, d_pad, self_offset, eps, idx_out, dist_out,
                                stats_out, st, gate, after, after_ctx, stats_ext);
 }
 
@@ -2257,55 +2439,55 @@ int nn_top1_self_async(const void* unit, const uint16_t* ub, int64_t n, int d, i
 
 extern "C" {
 
-int slic_nn_top1(const void* q_unit_dev, const uint16_t* q_bf16_dev, int64_t nq, const void* x_unit_dev,
-                 const uint16_t* x_bf16_dev, int64_t n, int32_t d, int32_t d_pad, int32_t dtype, int64_t self_offset,
+int slic_nn_top1(const void* q_unit_dev, const uint16_t* q_f16_dev, int64_t nq, const void* x_unit_dev,
+                 const uint16_t* x_f16_dev, int64_t n, int32_t d, int32_t d_pad, int32_t dtype, int64_t self_offset,
                  float eps, int32_t* idx_out_dev, void* dist_out_dev, int32_t* stats_out_dev, slic_stream_t stream) {
     SLIC_REQUIRE(nq > 0 && n > 1 && n < ((int64_t)1 << 31) && nq < ((int64_t)1 << 31), "nn_top1: bad shape");
     SLIC_REQUIRE(d > 0 && d_pad >= d && d_pad % 64 == 0, "nn_top1: d_pad must be a multiple of 64 >= d");
-    SLIC_REQUIRE(q_unit_dev && q_bf16_dev && x_unit_dev && x_bf16_dev && idx_out_dev, "nn_top1: null pointer");
+    SLIC_REQUIRE(q_unit_dev && q_f16_dev && x_unit_dev && x_f16_dev && idx_out_dev, "nn_top1: null pointer");
     SLIC_REQUIRE(dtype == SLIC_F32 || dtype == SLIC_F64, "nn_top1: bad dtype");
-    SLIC_REQUIRE((reinterpret_cast<uintptr_t>(q_bf16_dev) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_bf16_dev) & 15) == 0,
-                 "nn_top1: bf16 matrices must be 16-byte aligned");
+    SLIC_REQUIRE((reinterpret_cast<uintptr_t>(q_f16_dev) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_f16_dev) & 15) == 0,
+                 "nn_top1: f16 matrices must be 16-byte aligned");
     SLIC_PROPAGATE(slic_require_device());
     if (eps <= 0.f) eps = slic::TC_DEFAULT_EPS;
     cudaStream_t st = slic::as_stream(stream);
     if (dtype == SLIC_F32)
-        return slic::nn_top1_impl<float>((const float*)q_unit_dev, q_bf16_dev, nq, (const float*)x_unit_dev, x_bf16_dev,
+        return slic::nn_top1_impl<float>((const float*)q_unit_dev, q_f16_dev, nq, (const float*)x_unit_dev, x_f16_dev,
                                          n, d, d_pad, self_offset, eps, idx_out_dev, (float*)dist_out_dev,
                                          stats_out_dev, st);
-    return slic::nn_top1_impl<double>((const double*)q_unit_dev, q_bf16_dev, nq, (const double*)x_unit_dev, x_bf16_dev, n,
+    return slic::nn_top1_impl<double>((const double*)q_unit_dev, q_f16_dev, nq, (const double*)x_unit_dev, x_f16_dev, n,
                                       d, d_pad, self_offset, eps, idx_out_dev, (double*)dist_out_dev, stats_out_dev,
                                       st);
 }
 
-int slic_sym_row_bests(const float* unit_dev, const uint16_t* bf16_dev, int64_t n, int32_t d, int32_t d_pad, int32_t part,
+int slic_sym_row_bests(const float* unit_dev, const uint16_t* f16_dev, int64_t n, int32_t d, int32_t d_pad, int32_t part,
                        int32_t parts, int32_t* bests_out_dev, slic_stream_t stream) {
     using namespace slic;
     SLIC_REQUIRE(n > 1 && n < ((int64_t)1 << 31), "sym_row_bests: bad shape");
     SLIC_REQUIRE(d > 0 && d_pad >= d && d_pad % 64 == 0, "sym_row_bests: d_pad must be a multiple of 64 >= d");
-    SLIC_REQUIRE(unit_dev && bf16_dev && bests_out_dev, "sym_row_bests: null pointer");
+    SLIC_REQUIRE(unit_dev && f16_dev && bests_out_dev, "sym_row_bests: null pointer");
     SLIC_REQUIRE(parts >= 1 && part >= 0 && part < parts, "sym_row_bests: part must be in [0, parts)");
-    SLIC_REQUIRE((reinterpret_cast<uintptr_t>(bf16_dev) & 15) == 0, "sym_row_bests: bf16 matrix must be 16-byte aligned");
+    SLIC_REQUIRE((reinterpret_cast<uintptr_t>(f16_dev) & 15) == 0, "sym_row_bests: f16 matrix must be 16-byte aligned");
     SLIC_PROPAGATE(slic_require_device());
     if (!screen_self_search_is_symmetric(n)) {
         set_error("sym_row_bests: the symmetric screen needs n >= %lld rows (and SLIC_SCREEN_SYM != 0)", (long long)SYM_MIN_ROWS_FWD);
         return SLIC_ERR_UNSUPPORTED;
     }
     bool overflowed = false;
-    return nn_top1_sym_impl<float>(unit_dev, bf16_dev, n, d, d_pad, TC_DEFAULT_EPS, nullptr, nullptr, nullptr,
+    return nn_top1_sym_impl<float>(unit_dev, f16_dev, n, d, d_pad, TC_DEFAULT_EPS, nullptr, nullptr, nullptr,
                                    as_stream(stream), part, parts, nullptr, nullptr, nullptr, &overflowed, SYM_BESTS, nullptr,
                                    bests_out_dev);
 }
 
-int slic_nn_top1_sym_part(const float* unit_dev, const uint16_t* bf16_dev, int64_t n, int32_t d, int32_t d_pad,
+int slic_nn_top1_sym_part(const float* unit_dev, const uint16_t* f16_dev, int64_t n, int32_t d, int32_t d_pad,
                           int32_t part, int32_t parts, const int32_t* row_bests_dev, float eps, uint64_t* keys_out_dev,
                           int32_t* stats_out_dev, slic_stream_t stream) {
     using namespace slic;
     SLIC_REQUIRE(n > 1 && n < ((int64_t)1 << 31), "nn_top1_sym_part: bad shape");
     SLIC_REQUIRE(d > 0 && d_pad >= d && d_pad % 64 == 0, "nn_top1_sym_part: d_pad must be a multiple of 64 >= d");
-    SLIC_REQUIRE(unit_dev && bf16_dev && keys_out_dev, "nn_top1_sym_part: null pointer");
+    SLIC_REQUIRE(unit_dev && f16_dev && keys_out_dev, "nn_top1_sym_part: null pointer");
     SLIC_REQUIRE(parts >= 1 && part >= 0 && part < parts, "nn_top1_sym_part: part must be in [0, parts)");
-    SLIC_REQUIRE((reinterpret_cast<uintptr_t>(bf16_dev) & 15) == 0, "nn_top1_sym_part: bf16 matrix must be 16-byte aligned");
+    SLIC_REQUIRE((reinterpret_cast<uintptr_t>(f16_dev) & 15) == 0, "nn_top1_sym_part: f16 matrix must be 16-byte aligned");
     SLIC_PROPAGATE(slic_require_device());
     if (!screen_self_search_is_symmetric(n)) {
         set_error("nn_top1_sym_part: the symmetric screen needs n >= %lld rows (and SLIC_SCREEN_SYM != 0)",
@@ -2318,7 +2500,7 @@ int slic_nn_top1_sym_part(const float* unit_dev, const uint16_t* bf16_dev, int64
     SLIC_CUDA_OK(idx.alloc((size_t)n * sizeof(int), st));
     SLIC_CUDA_OK(dist.alloc((size_t)n * sizeof(float), st));
     bool overflowed = false;
-    SLIC_PROPAGATE(nn_top1_sym_impl<float>(unit_dev, bf16_dev, n, d, d_pad, eps, idx.as<int>(), dist.as<float>(),
+    SLIC_PROPAGATE(nn_top1_sym_impl<float>(unit_dev, f16_dev, n, d, d_pad, eps, idx.as<int>(), dist.as<float>(),
                                            stats_out_dev, st, part, parts, nullptr, nullptr, nullptr, &overflowed,
                                            row_bests_dev ? SYM_TRIANGLE : SYM_FULL, row_bests_dev, nullptr));
     sym_pack_keys_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(idx.as<int>(), dist.as<float>(), n,
@@ -2376,27 +2558,27 @@ int slic_unpack_neighbor_keys(const uint64_t* keys_dev, int64_t n, int32_t* idx_
     return SLIC_OK;
 }
 
-int slic_topk_cosine_tc(const void* q_unit_dev, const uint16_t* q_bf16_dev, int64_t nq, const void* x_unit_dev,
-                        const uint16_t* x_bf16_dev, int64_t n, int32_t d, int32_t d_pad, int32_t dtype, int32_t k,
+int slic_topk_cosine_tc(const void* q_unit_dev, const uint16_t* q_f16_dev, int64_t nq, const void* x_unit_dev,
+                        const uint16_t* x_f16_dev, int64_t n, int32_t d, int32_t d_pad, int32_t dtype, int32_t k,
                         int64_t self_offset, float eps, int32_t* idx_out_dev, void* dist_out_dev, int32_t* stats_out_dev,
                         slic_stream_t stream) {
     SLIC_REQUIRE(nq >= 0 && n > 0 && n < ((int64_t)1 << 31) && nq < ((int64_t)1 << 31), "topk_cosine_tc: bad shape");
     SLIC_REQUIRE(d > 0 && d_pad >= d && d_pad % 64 == 0, "topk_cosine_tc: d_pad must be a multiple of 64 >= d");
     SLIC_REQUIRE(k > 0 && k <= slic::TC_TOPK_MAX && k <= n - (self_offset >= 0 ? 1 : 0),
                  "topk_cosine_tc: k must satisfy 1 <= k <= min(64, columns available)");
-    SLIC_REQUIRE(q_unit_dev && q_bf16_dev && x_unit_dev && x_bf16_dev && idx_out_dev, "topk_cosine_tc: null pointer");
+    SLIC_REQUIRE(q_unit_dev && q_f16_dev && x_unit_dev && x_f16_dev && idx_out_dev, "topk_cosine_tc: null pointer");
     SLIC_REQUIRE(dtype == SLIC_F32 || dtype == SLIC_F64, "topk_cosine_tc: bad dtype");
-    SLIC_REQUIRE((reinterpret_cast<uintptr_t>(q_bf16_dev) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_bf16_dev) & 15) == 0,
-                 "topk_cosine_tc: bf16 matrices must be 16-byte aligned");
+    SLIC_REQUIRE((reinterpret_cast<uintptr_t>(q_f16_dev) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_f16_dev) & 15) == 0,
+                 "topk_cosine_tc: f16 matrices must be 16-byte aligned");
     if (nq == 0) return SLIC_OK;
     SLIC_PROPAGATE(slic_require_device());
     if (eps <= 0.f) eps = slic::TC_DEFAULT_EPS;
     cudaStream_t st = slic::as_stream(stream);
     if (dtype == SLIC_F32)
-        return slic::topk_tc_impl<float>((const float*)q_unit_dev, q_bf16_dev, nq, (const float*)x_unit_dev, x_bf16_dev,
+        return slic::topk_tc_impl<float>((const float*)q_unit_dev, q_f16_dev, nq, (const float*)x_unit_dev, x_f16_dev,
                                          n, d, d_pad, k, self_offset, eps, idx_out_dev, (float*)dist_out_dev,
                                          stats_out_dev, st);
-    return slic::topk_tc_impl<double>((const double*)q_unit_dev, q_bf16_dev, nq, (const double*)x_unit_dev, x_bf16_dev, n,
+    return slic::topk_tc_impl<double>((const double*)q_unit_dev, q_f16_dev, nq, (const double*)x_unit_dev, x_f16_dev, n,
                                       d, d_pad, k, self_offset, eps, idx_out_dev, (double*)dist_out_dev, stats_out_dev,
                                       st);
 }
@@ -2411,16 +2593,16 @@ int slic_screen_trace(int32_t enable, uint64_t* counters_out_host) {
     using namespace slic;
     if (counters_out_host && g_trace) {
         SLIC_CUDA_OK(cudaDeviceSynchronize());
-        SLIC_CUDA_OK(cudaMemcpy(counters_out_host, g_trace, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        SLIC_CUDA_OK(cudaMemcpy(counters_out_host, g_trace, 12 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     }
     if (enable && !g_trace) {
-        SLIC_CUDA_OK(cudaMalloc(&g_trace, 8 * sizeof(uint64_t)));
+        SLIC_CUDA_OK(cudaMalloc(&g_trace, 12 * sizeof(uint64_t)));
     } else if (!enable && g_trace) {
         SLIC_CUDA_OK(cudaDeviceSynchronize());
         SLIC_CUDA_OK(cudaFree(g_trace));
         g_trace = nullptr;
     }
-    if (g_trace) SLIC_CUDA_OK(cudaMemset(g_trace, 0, 8 * sizeof(uint64_t)));
+    if (g_trace) SLIC_CUDA_OK(cudaMemset(g_trace, 0, 12 * sizeof(uint64_t)));
     return SLIC_OK;
 }
 
@@ -2442,11 +2624,11 @@ int slic_last_screen_exec_flop(double* flop_out) {
     return SLIC_OK;
 }
 
-int slic_screen_scores_debug(const uint16_t* q_bf16_dev, int64_t nq, const uint16_t* x_bf16_dev, int64_t n,
+int slic_screen_scores_debug(const uint16_t* q_f16_dev, int64_t nq, const uint16_t* x_f16_dev, int64_t n,
                              int32_t d_pad, float* out_dev, slic_stream_t stream) {
     using namespace slic;
     SLIC_REQUIRE(nq > 0 && n > 0 && d_pad > 0 && d_pad % 64 == 0, "screen_scores_debug: bad shape");
-    SLIC_REQUIRE(q_bf16_dev && x_bf16_dev && out_dev, "screen_scores_debug: null pointer");
+    SLIC_REQUIRE(q_f16_dev && x_f16_dev && out_dev, "screen_scores_debug: null pointer");
     SLIC_PROPAGATE(slic_require_device());
     cudaStream_t st = as_stream(stream);
     const ScreenPlan pl = plan_screen(nq, n);
@@ -2458,7 +2640,7 @@ int slic_screen_scores_debug(const uint16_t* q_bf16_dev, int64_t nq, const uint1
     SLIC_CUDA_OK(cf.alloc(slots * sizeof(int), st));
     SLIC_CUDA_OK(err.alloc(sizeof(int), st));
     SLIC_CUDA_OK(cudaMemsetAsync(err.ptr, 0, sizeof(int), st));
-    SLIC_PROPAGATE(launch_screen(q_bf16_dev, nq, x_bf16_dev, n, d_pad, -1, TC_DEFAULT_EPS, TC_CAP, pl, ci.as<int>(),
+    SLIC_PROPAGATE(launch_screen(q_f16_dev, nq, x_f16_dev, n, d_pad, -1, TC_DEFAULT_EPS, TC_CAP, pl, ci.as<int>(),
                                  cs.as<float>(), cc.as<int>(), cf.as<int>(), out_dev, err.as<int>(), st));
     int host_err = 0;
     SLIC_CUDA_OK(cudaMemcpyAsync(&host_err, err.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));

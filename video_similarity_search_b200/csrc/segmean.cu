@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(SM_THREADS) segsum_chunk_kernel(const T* __res
 // clusters that span several chunks: add the partial sums.  One CTA per such cluster (grid-stride); for every tile of
 // FIN_COLS columns its FIN_LANES thread rows each add every FIN_LANES-th chunk (fixed order), then the lanes are
 // combined by a fixed-order shared-memory tree - deterministic whatever the grid.
-constexpr int FIN_COLS = 32, FIN_LANES = 8;
+constexpr int FIN_COLS = 32, FIN_LANES = 8, FIN_DIRECT_MAX = 32;
 
 __global__ void __launch_bounds__(FIN_COLS * FIN_LANES) segsum_finalize_kernel(const int* __restrict__ multi,
                                                                                const int* __restrict__ totals,
@@ -172,6 +172,16 @@ __global__ void __launch_bounds__(FIN_COLS * FIN_LANES) segsum_finalize_kernel(c
         }
         __syncthreads();
         const double rows = (double)s_cnt;
+        if (n_chunks <= FIN_DIRECT_MAX) {
+            // few chunks (the usual case: a cluster of a few dozen rows): every thread owns columns and adds the chunks
+            // in order - coalesced, no barriers.  (Which path runs depends on n_chunks only: deterministic.)
+            for (int k = threadIdx.x; k < d; k += FIN_COLS * FIN_LANES) {
+                double a = 0;
+                for (int j = 0; j < n_chunks; ++j) a += partial[(first + j) * d + k];
+                sums[(int64_t)c * d + k] = a;
+                if (means) means[(int64_t)c * d + k] = a / rows;
+            }
+        } else
         for (int k0 = 0; k0 < d; k0 += FIN_COLS) {
             const int k = k0 + cx;
             double a = 0;

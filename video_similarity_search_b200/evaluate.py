@@ -41,11 +41,11 @@ class DistanceMatrix:
     def _units(self):
         if self._unit_x is None:
             screen = self._x.shape[0] >= _backend.SCREEN_MIN_ROWS
-            self._unit_x, self._bf_x = self._be.normalize_rows(self._x, want_bf16=screen)
+            self._unit_x, self._bf_x = self._be.normalize_rows(self._x, want_f16=screen)
             if self.same:
                 self._unit_q, self._bf_q = self._unit_x, self._bf_x
             else:
-                self._unit_q, self._bf_q = self._be.normalize_rows(self._q, want_bf16=screen)
+                self._unit_q, self._bf_q = self._be.normalize_rows(self._q, want_f16=screen)
         return self._unit_q, self._unit_x
 
     def device_matrix(self):
@@ -78,8 +78,8 @@ class DistanceMatrix:
         """(idx int32 [Q,k], dist [Q,k]) on the device, ascending distance, ties -> lowest column."""
         if self.metric == 'cosine':
             uq, ux = self._units()
-            return self._be.topk_cosine(uq, ux, k, self_offset=0 if self.same else -1, q_bf16=self._bf_q,
-                                        x_bf16=self._bf_x)
+            return self._be.topk_cosine(uq, ux, k, self_offset=0 if self.same else -1, q_f16=self._bf_q,
+                                        x_f16=self._bf_x)
         return self._be.rows_topk(self.device_matrix(), k)
 
 

@@ -116,12 +116,12 @@ def topk_neighbors_sharded(q, x, k, same=False, group=None, backend=None):
     d_pad = torch.zeros((per, k), dtype=x.dtype, device=x.device)
     if r1 > r0:
         use_screen = x.shape[0] >= _backend.SCREEN_MIN_ROWS and k <= _backend.TOPK_SCREEN_MAX_K
-        ux, xb = be.normalize_rows(x, want_bf16=use_screen)
+        ux, xb = be.normalize_rows(x, want_f16=use_screen)
         if same:
             uq, qb = ux[r0:r1], (xb[r0:r1] if xb is not None else None)
         else:
-            uq, qb = be.normalize_rows(q[r0:r1].contiguous(), want_bf16=use_screen)
-        idx, d = be.topk_cosine(uq, ux, k, self_offset=r0 if same else -1, q_bf16=qb, x_bf16=xb)
+            uq, qb = be.normalize_rows(q[r0:r1].contiguous(), want_f16=use_screen)
+        idx, d = be.topk_cosine(uq, ux, k, self_offset=r0 if same else -1, q_f16=qb, x_f16=xb)
         idx_pad[: r1 - r0] = idx
         d_pad[: r1 - r0] = d
     idx_all = torch.empty((per * world, k), dtype=torch.int32, device=x.device)
