@@ -275,8 +275,9 @@ int slic_dense_labels(const int32_t* labels_dev, int64_t n, int32_t* dense_out_d
  * (metrics/cluster/_supervised.py mutual_info_score + entropy, _expected_mutual_info_fast.pyx):
  *   out_dev[0] mutual information (nats)   [1] entropy of labels_true   [2] entropy of labels_pred
  *   out_dev[3] expected mutual information (0 unless want_emi)   [4], [5] number of non-empty classes / clusters
- * Labels must lie in [0, num_true) / [0, num_pred) (empty classes are allowed); num_true * num_pred <= 2^28 cells
- * (SLIC_ERR_UNSUPPORTED above).  The final ratios (and sklearn's special cases) are host arithmetic on these six numbers. */
+ * Labels must lie in [0, num_true) / [0, num_pred) (empty classes are allowed); a label outside is never counted
+ * (no out-of-bounds write): all six outputs become NaN except out_dev[4] = -(number of such labels).
+ * num_true * num_pred <= 2^28 cells (SLIC_ERR_UNSUPPORTED above).  The final ratios (and sklearn's special cases) are host arithmetic on these six numbers. */
 int slic_cluster_metrics(const int32_t* labels_true_dev, const int32_t* labels_pred_dev, int64_t n,
                          int32_t num_true, int32_t num_pred, int32_t want_emi, double* out_dev,
                          slic_stream_t stream);
@@ -327,6 +328,15 @@ int slic_finch_host(const float* x_host, int64_t n, int32_t d, const int64_t* in
                     int32_t ensure_early_exit, int32_t capacity, int32_t* labels_out_host,
                     int32_t* num_clust_out_host, int32_t* num_levels_out_host,
                     float* min_sim_out_host /* or NULL */, int32_t* has_min_sim_out_host /* or NULL */);
+
+/* Upload / search overlap of slic_finch_host.  The pipelined path launches the persistent screen kernel BEFORE the
+ * embeddings have arrived and needs the upload stream's small kernels to become resident next to it - true on an
+ * otherwise idle B200, not promised by CUDA in general.  enable = 0: always upload first, then search (use this under
+ * MPS / time slicing or when other work shares the device); 1: overlap whenever the resource check passes;
+ * -1 (default): overlap unless the environment shows serialised launches (CUDA_LAUNCH_BLOCKING, compute-sanitizer,
+ * Nsight tools) or SLIC_UPLOAD_OVERLAP=0.  A gate that stays shut for ~3 s makes the kernel give up without trapping;
+ * the call then repeats the search after the upload (same result) and keeps the overlap off for the process. */
+int slic_set_upload_overlap(int32_t enable);
 
 /* Diagnostic timeline of slic_finch_host (CUDA events): enable, run a call, then read ms_out_host[4] =
  * {start -> first copy begins, upload duration, start -> level-0 search done, start -> labels copied back}. */

@@ -164,6 +164,45 @@ def test_host_entry_pipelined_upload_matches_resident_path(be):
     assert no == num_pinned and np.array_equal(co, c_pinned)
 
 
+_SERIALISED_SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+from video_similarity_search_b200 import _lib, synth
+from video_similarity_search_b200.backend import CudaBackend
+be = CudaBackend()
+x = synth.gaussian_mixture(40000, 64, 60, 5)
+c_ref, num_ref, _ = be.finch_native(be.to_device(x))
+_lib.call("slic_set_upload_overlap", 1)                  # force the gated launch although launches are serialised
+c1, num1, _ = be.finch_host(x)                           # gates stay shut -> kernel gives up, search repeated after the upload
+c2, num2, _ = be.finch_host(x)                           # overlap now off for the process: plain upload-then-search
+ok = num1 == num_ref == num2 and np.array_equal(c1, c_ref.cpu().numpy()) and np.array_equal(c2, c1)
+_lib.call("slic_set_upload_overlap", -1)
+c3, num3, _ = be.finch_host(x)                           # default policy sees CUDA_LAUNCH_BLOCKING and never tries
+print("RESULT", int(ok and num3 == num_ref and np.array_equal(c3, c1)), num1)
+"""
+
+
+def test_gated_upload_survives_serialised_launches(tmp_path):
+    """with CUDA_LAUNCH_BLOCKING=1 (or a tool that serialises kernels) the upload can never run next to the
+    gated screen kernel.  The kernel must not trap (that would destroy the caller's CUDA context): the gate wait gives up
+    after ~2 s, the driver repeats the search after the upload, the partition is the resident path's, and the context
+    stays usable for further calls."""
+    import os
+    import subprocess
+    import sys
+    import time
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "serialised.py"
+    script.write_text(_SERIALISED_SCRIPT % root)
+    env = dict(os.environ, CUDA_LAUNCH_BLOCKING="1")
+    env.pop("SLIC_UPLOAD_OVERLAP", None)
+    t0 = time.time()
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "RESULT 1" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
+    assert time.time() - t0 < 120
+
+
 def test_host_entry_initial_rank_and_overflow_path(be, monkeypatch):
     """initial_rank through the host entry; and a label buffer that is too small (SLIC_ERR_OVERFLOW) makes FINCH
     continue with the Python-orchestrated loop instead of failing."""

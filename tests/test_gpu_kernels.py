@@ -96,6 +96,22 @@ def test_compose_and_segmented_mean(be):
                                fo.cluster_means(xo, lab), rtol=0, atol=1e-11)
 
 
+def test_direct_callers_with_sloppy_labels_get_defined_results(be):
+    """the C ABI is public.  Empty clusters of slic_cluster_sums get sum 0 / count 0 / mean NaN instead of
+    uninitialised rows; labels outside [0, num) in slic_cluster_metrics are refused (no out-of-bounds write)."""
+    x = synth.gaussian_mixture(500, 64, 5, 2)
+    lab = (np.arange(500) % 3 * 2).astype(np.int32)                     # clusters 1, 3, 5, 6 are empty
+    sums, counts, means = be.cluster_sums(dev(be, x), dev(be, lab), 7)
+    assert counts.cpu().numpy().tolist() == [167, 0, 167, 0, 166, 0, 0]
+    m = means.cpu().numpy()
+    assert np.isnan(m[[1, 3, 5, 6]]).all() and np.all(sums.cpu().numpy()[[1, 3, 5, 6]] == 0)
+    np.testing.assert_allclose(m[[0, 2, 4]], fo.cluster_means(x, lab // 2), rtol=0, atol=1e-11)
+    t = torch.tensor([0, 1, 2, 3], dtype=torch.int32, device=be.device)
+    with pytest.raises(ValueError, match="outside"):
+        be.cluster_metrics(t, t, 3, 4)                                    # label 3 >= num_true 3
+    assert be.cluster_metrics(t, t, 4, 4)[0] > 0
+
+
 def test_cluster_sums_and_hierarchical_merge(be):
     """slic_cluster_sums / slic_merge_cluster_sums: the level l+1 means formed from the level-l float64 sums equal
     cool_mean over the original rows (finch.py:58-71) to float64 rounding, at every size of cluster."""

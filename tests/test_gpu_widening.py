@@ -129,6 +129,40 @@ def test_pdist_matches_torch_restatement(be):
                                    rtol=0, atol=tol if metric == "cosine" else 4e-3)   # euclidean self-distances: eps * sqrt(d) in the reference
 
 
+def test_pdist_backward_matches_torch_autograd(be):
+    """pdist feeds the loss in 'noise_contrastive' / 'all_semi_hard' (loss/triplet_loss.py:100, :122): the kernel-backed
+    matrix must carry a gradient equal to autograd through the reference's row-by-row formula (:429-447)."""
+    import torch.nn.functional as F
+    from video_similarity_search_b200 import coclr_retrieval as cr
+    g = torch.Generator().manual_seed(5)
+    a0, b0 = torch.randn(48, 128, generator=g), torch.randn(33, 128, generator=g)
+    w = torch.randn(48, 33, generator=g).cuda()
+    for metric in ("cosine", "euclidean"):
+        a, b = a0.cuda().requires_grad_(True), b0.cuda().requires_grad_(True)
+        out = cr.pdist_v2(a, b, 1e-6, metric, backend=be)
+        assert out.requires_grad
+        (out * w).sum().backward()
+        ar, br = a0.cuda().requires_grad_(True), b0.cuda().requires_grad_(True)
+        if metric == "cosine":
+            ref = torch.stack([1 - F.cosine_similarity(ar[i].unsqueeze(0), br, dim=1) for i in range(len(ar))])
+        else:
+            ref = torch.stack([F.pairwise_distance(ar[i].unsqueeze(0), br, eps=0.0) for i in range(len(ar))])
+        (ref * w).sum().backward()
+        torch.testing.assert_close(a.grad, ar.grad, rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(b.grad, br.grad, rtol=1e-4, atol=1e-5)
+        # the same tensor on both sides (pdist): the two gradient paths add up
+        v = a0.cuda().requires_grad_(True)
+        cr.pdist(v, 1e-6, "cosine", backend=be).pow(2).sum().backward()
+        vr = a0.cuda().requires_grad_(True)
+        vn = F.normalize(vr, dim=1)
+        (1 - vn @ vn.t()).pow(2).sum().backward()
+        torch.testing.assert_close(v.grad, vr.grad, rtol=1e-3, atol=1e-5)
+    with torch.no_grad():      # the mining call sites (:54, :279): no graph, plain path
+        assert not cr.pdist(a0.cuda().requires_grad_(True), backend=be).requires_grad
+    with pytest.raises(ValueError):
+        cr.pdist_v2(a0.requires_grad_(True), b0, backend=be)     # CPU tensor that needs grad: refuse instead of cutting the graph
+
+
 @pytest.mark.parametrize("n,lo,hi,seed", [(1, 5, 6, 0), (1000, -50, 50, 1), (240000, 0, 21436, 2), (100000, -2**31, 2**31 - 1, 3),
                                           (5000, 7, 8, 4)])
 def test_dense_labels_equal_numpy_unique(be, n, lo, hi, seed):

@@ -52,6 +52,7 @@ SIGNATURES = {
     "slic_first_neighbors_host": [_ptr, _i64, _i32, _i32, _ptr, _ptr],
     "slic_set_flann_threshold": [_i64],
     "slic_host_trace": [_i32, _ptr],
+    "slic_set_upload_overlap": [_i32],
     "slic_finch": [_ptr, _i64, _i32, _ptr, _ptr, _ptr, _i32, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
     "slic_finch_host": [_ptr, _i64, _i32, _ptr, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr],
 }

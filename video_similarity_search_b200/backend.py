@@ -357,7 +357,10 @@ class CudaBackend:
         out = torch.empty(6, dtype=torch.float64, device=labels_true.device)
         _lib.call("slic_cluster_metrics", _p(labels_true), _p(labels_pred), labels_true.shape[0], int(num_true),
                   int(num_pred), int(bool(want_emi)), _p(out), self._stream())
-        return out.tolist()
+        vals = out.tolist()
+        if vals[0] != vals[0]:      # NaN: the kernel met labels outside [0, num) and refused to count them
+            raise ValueError("cluster_metrics: %d labels lie outside [0, num_true) x [0, num_pred)" % int(-vals[4]))
+        return vals
 
     def group_by_label(self, labels, num_labels):
         n = labels.shape[0]

@@ -47,18 +47,62 @@ def nn_retrieval_accuracy(test_feature, test_label, train_feature, train_label, 
     return accs
 
 
-def pdist_v2(vector1, vector2, eps=1e-6, dist_metric='cosine', backend=None):
-    """loss/triplet_loss.py:438-447: [len(vector1), len(vector2)] distance matrix, cosine (1 - cosine similarity) or
-    euclidean, in one launch instead of a Python loop over rows.  Differences from the reference, both below 1e-6:
-    cosine distances are clipped to [0, 2] (F.cosine_similarity can return 1 + 1e-8); euclidean does not add `eps` to
-    every coordinate difference as F.pairwise_distance does."""
-    be = backend or _backend.default_backend()
-    a, b = _f32_on_device(be, vector1), _f32_on_device(be, vector2)
+def _pdist_forward(be, a, b, dist_metric):
     if dist_metric == 'euclidean':
         return be.distance_matrix(a, b, metric="euclidean")
     ua, _ = be.normalize_rows(a, want_f16=False)
     ub, _ = be.normalize_rows(b, want_f16=False)
     return be.distance_matrix(ua, ub, metric="cosine")
+
+
+class _PdistFn(torch.autograd.Function):
+    """Forward through the C ABI (no [A, B, D] intermediate); backward in closed form with torch ops - the loss
+    strategies 'noise_contrastive' / 'all_semi_hard' differentiate through the matrix (triplet_loss.py:100, :122)."""
+
+    @staticmethod
+    def forward(ctx, a, b, dist_metric, be):
+        out = _pdist_forward(be, a.detach(), b.detach(), dist_metric)
+        ctx.metric = dist_metric
+        ctx.save_for_backward(a.detach(), b.detach(), out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, out = ctx.saved_tensors
+        g = g.to(torch.float32)
+        if ctx.metric == 'euclidean':
+            # d|a_i - b_j| / da_i = (a_i - b_j) / |a_i - b_j|   (0 where the rows coincide)
+            w = torch.where(out > 0, g / out.clamp_min(1e-30), torch.zeros_like(g))
+            ga = a * w.sum(1, keepdim=True) - w @ b
+            gb = b * w.sum(0).unsqueeze(1) - w.t() @ a
+        else:
+            # D = 1 - ua ub^T with u = x / max(|x|, tiny); the clip to [0, 2] only acts within rounding of its bounds
+            na = a.norm(dim=1, keepdim=True).clamp_min(1e-30)
+            nb = b.norm(dim=1, keepdim=True).clamp_min(1e-30)
+            ua, ub = a / na, b / nb
+            gua, gub = -(g @ ub), -(g.t() @ ua)
+            ga = (gua - (gua * ua).sum(1, keepdim=True) * ua) / na
+            gb = (gub - (gub * ub).sum(1, keepdim=True) * ub) / nb
+        return ga, gb, None, None
+
+
+def pdist_v2(vector1, vector2, eps=1e-6, dist_metric='cosine', backend=None):
+    """loss/triplet_loss.py:438-447: [len(vector1), len(vector2)] distance matrix, cosine (1 - cosine similarity) or
+    euclidean, in one launch instead of a Python loop over rows.  Differences from the reference, both below 1e-6:
+    cosine distances are clipped to [0, 2] (F.cosine_similarity can return 1 + 1e-8); euclidean does not add `eps` to
+    every coordinate difference as F.pairwise_distance does.
+    Inputs that require grad (the matrix feeds the loss in 'noise_contrastive' / 'all_semi_hard',
+    triplet_loss.py:100, :122) get an autograd node: forward through the kernel, analytic backward.  The mining uses
+    (triplet_loss.py:54, :279) run under no_grad and take the plain path."""
+    be = backend or _backend.default_backend()
+    needs_grad = torch.is_grad_enabled() and any(isinstance(v, torch.Tensor) and v.requires_grad
+                                                 for v in (vector1, vector2))
+    if needs_grad:
+        if not all(isinstance(v, torch.Tensor) and v.is_cuda and v.dtype == torch.float32 for v in (vector1, vector2)):
+            raise ValueError("pdist: differentiable inputs must be float32 CUDA tensors (a device / dtype copy would cut "
+                             "the autograd graph)")
+        return _PdistFn.apply(vector1.contiguous(), vector2.contiguous(), dist_metric, be)
+    return _pdist_forward(be, _f32_on_device(be, vector1), _f32_on_device(be, vector2), dist_metric)
 
 
 def pdist(vectors, eps=1e-6, dist_metric='cosine', backend=None):

@@ -41,6 +41,35 @@ static int gated_chunks() {
     return cached;
 }
 
+// Pipelined upload policy.  The gated launch relies on the upload stream's kernels becoming resident NEXT TO the
+// persistent screen kernel, which CUDA does not promise: serialised launches (CUDA_LAUNCH_BLOCKING, compute-sanitizer,
+// Nsight's kernel replay), MPS / time slicing or an oversubscribed device keep the gates shut.  So:
+//   * slic_set_upload_overlap(0) / SLIC_UPLOAD_OVERLAP=0 switch it off explicitly;
+//   * it is off by itself when the environment shows a serialising tool;
+//   * a gate that stays shut for ~3 s makes the kernel give up WITHOUT trapping (nn_screen_tc.cu, gate_wait): the driver
+//     repeats the search after the upload and keeps the overlap off for the rest of the process.
+static int g_overlap_user = -1;          // -1: not set by the caller, 0 / 1: slic_set_upload_overlap
+static bool g_overlap_failed = false;    // a gated launch timed out in this process
+static bool env_set(const char* name) {
+    const char* e = getenv(name);
+    return e && *e && strcmp(e, "0") != 0;
+}
+static bool upload_overlap_allowed() {
+    if (g_overlap_failed) return false;
+    if (g_overlap_user >= 0) return g_overlap_user != 0;
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("SLIC_UPLOAD_OVERLAP");
+        if (e && *e) cached = atoi(e) != 0 ? 1 : 0;
+        else
+            cached = !(env_set("CUDA_LAUNCH_BLOCKING") || getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") ||
+                       getenv("NV_SANITIZER_INJECTION_PORT_BASE") || getenv("NV_SANITIZER_INJECTION_PORT_RANGE_BEGIN") ||
+                       getenv("SANITIZER_INJECTION_PATH") || getenv("NSYS_PROFILING_SESSION_ID") || getenv("CUDA_MPS_PIPE_DIRECTORY"))
+                         ? 1 : 0;
+    }
+    return cached != 0;
+}
+
 // diagnostic timeline of the last slic_finch_host call (slic_host_trace): CUDA events, read after the call
 static bool g_host_trace = false;
 static cudaEvent_t g_up0 = nullptr, g_up1 = nullptr, g_t0 = nullptr, g_t_search = nullptr, g_t_end = nullptr;
@@ -177,7 +206,9 @@ static int finch_levels(const float* data, int64_t n, int d, const Level0& l0, b
             return SLIC_ERR_INVALID_ARG;
         }
         if (l0.retry_nn && attempt == 0 && (s[1] | s[4] | s[5])) {
-            if (s[4] != 0 && s[4] != 2) {
+            if (s[4] == 3) {
+                g_overlap_failed = true;   // the upload did not run next to the gated kernel: search again, now that it has landed
+            } else if (s[4] != 0 && s[4] != 2) {
                 set_error("nn_screen_kernel: pipeline barrier timed out");
                 return SLIC_ERR_CUDA;
             }
@@ -433,6 +464,16 @@ static int finch_host_impl(const float* x_host, int64_t n, int d, const int64_t*
     const int dp = d_pad_of(d);
     cudaStream_t st = hs.main;
     Scratch data, unit, ub, nn, dist, gates, labels, rank64, blk;
+    // Declared AFTER the buffers, hence destroyed BEFORE them: on every return path (errors included) both streams are
+    // drained before a buffer goes back to the pool - the copy stream may still be writing chunks that `st` never
+    // waited for when an error cut the call short.
+    struct Drain {
+        HostStreams& h;
+        ~Drain() {
+            cudaStreamSynchronize(h.copy);
+            cudaStreamSynchronize(h.main);
+        }
+    } drain{hs};
     SLIC_CUDA_OK(data.alloc((size_t)n * d * sizeof(float), st));
     SLIC_CUDA_OK(nn.alloc((size_t)n * sizeof(int), st));
     SLIC_CUDA_OK(labels.alloc((size_t)n * capacity * sizeof(int), st));
@@ -467,7 +508,7 @@ static int finch_host_impl(const float* x_host, int64_t n, int d, const int64_t*
         if (g_host_trace) SLIC_CUDA_OK(cudaEventRecord(g_t0, st));
         int guest_threads = 0, guest_regs = 0;
         SLIC_PROPAGATE(normalize_kernel_shape(&guest_threads, &guest_regs));
-        if (screen && n >= GATED_MIN_ROWS && gated_chunks() > 1 &&
+        if (screen && n >= GATED_MIN_ROWS && gated_chunks() > 1 && upload_overlap_allowed() &&
             screen_can_overlap_upload(n, dp, guest_threads, guest_regs)) {
             // pipelined: screen first, upload behind it
             up.num_chunks = gated_chunks();
@@ -545,6 +586,12 @@ int slic_host_trace(int32_t enable, float* ms_out_host) {
         SLIC_CUDA_OK(cudaEventElapsedTime(ms_out_host + 3, g_t0, g_t_end));      // start -> labels copied back
     }
     g_host_trace = enable != 0;
+    return SLIC_OK;
+}
+
+int slic_set_upload_overlap(int32_t enable) {
+    slic::g_overlap_user = enable < 0 ? -1 : (enable != 0 ? 1 : 0);
+    if (enable > 0) slic::g_overlap_failed = false;
     return SLIC_OK;
 }
 

@@ -22,14 +22,27 @@ namespace slic {
 constexpr int MT_THREADS = 256;
 
 __global__ void __launch_bounds__(MT_THREADS) contingency_count_kernel(const int* __restrict__ lt, const int* __restrict__ lp,
-                                                                      int64_t n, int num_pred, int* __restrict__ cells,
-                                                                      int* __restrict__ a, int* __restrict__ b) {
+                                                                      int64_t n, int num_true, int num_pred,
+                                                                      int* __restrict__ cells, int* __restrict__ a,
+                                                                      int* __restrict__ b, int* __restrict__ bad) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int t = lt[i], p = lp[i];
+    if (t < 0 || t >= num_true || p < 0 || p >= num_pred) {   // labels are documented dense; a direct C caller may not comply
+        atomicAdd(bad, 1);
+        return;
+    }
     atomicAdd(cells + (int64_t)t * num_pred + p, 1);
     atomicAdd(a + t, 1);
     atomicAdd(b + p, 1);
+}
+
+// labels outside [0, num) were met: every output becomes NaN (the scores are undefined), [4] carries the count negated
+__global__ void poison_scores_kernel(const int* __restrict__ bad, double* __restrict__ out) {
+    if (*bad > 0) {
+        for (int i = 0; i < 6; ++i) out[i] = nan("");
+        out[4] = -(double)*bad;
+    }
 }
 
 // fixed-order block sum: warp shuffles, then warp 0 over the warp totals
@@ -171,7 +184,9 @@ extern "C" int slic_cluster_metrics(const int32_t* labels_true_dev, const int32_
     }
     SLIC_PROPAGATE(slic_require_device());
     cudaStream_t st = as_stream(stream);
-    Scratch hist, a, b, partial;
+    Scratch hist, a, b, partial, bad;
+    SLIC_CUDA_OK(bad.alloc(sizeof(int), st));
+    SLIC_CUDA_OK(cudaMemsetAsync(bad.ptr, 0, sizeof(int), st));
     SLIC_CUDA_OK(hist.alloc(cells * sizeof(int), st));
     SLIC_CUDA_OK(a.alloc((size_t)num_true * sizeof(int), st));
     SLIC_CUDA_OK(b.alloc((size_t)num_pred * sizeof(int), st));
@@ -180,8 +195,8 @@ extern "C" int slic_cluster_metrics(const int32_t* labels_true_dev, const int32_
     SLIC_CUDA_OK(cudaMemsetAsync(b.ptr, 0, (size_t)num_pred * sizeof(int), st));
     SLIC_CUDA_OK(cudaMemsetAsync(out_dev, 0, 6 * sizeof(double), st));
     contingency_count_kernel<<<(unsigned)ceil_div(n, MT_THREADS), MT_THREADS, 0, st>>>(labels_true_dev, labels_pred_dev, n,
-                                                                                      num_pred, hist.as<int>(),
-                                                                                      a.as<int>(), b.as<int>());
+                                                                                      num_true, num_pred, hist.as<int>(),
+                                                                                      a.as<int>(), b.as<int>(), bad.as<int>());
     SLIC_LAUNCH_OK();
     // out: [0] mi  [1] h_true  [2] h_pred  [3] emi  [4] non-empty true classes  [5] non-empty predicted clusters
     Scratch ent;
@@ -239,5 +254,7 @@ extern "C" int slic_cluster_metrics(const int32_t* labels_true_dev, const int32_
         sum_partials_kernel<<<1, MT_THREADS, 0, st>>>(partial.as<double>(), (int)emi_warps, out_dev + 3, 0);
         SLIC_LAUNCH_OK();
     }
+    poison_scores_kernel<<<1, 1, 0, st>>>(bad.as<int>(), out_dev);
+    SLIC_LAUNCH_OK();
     return SLIC_OK;
 }

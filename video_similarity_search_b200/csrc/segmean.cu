@@ -35,6 +35,12 @@ struct ChunkScanOp {
     int* pbase;                 // [C]
     int* multi;                 // [<= n / 33]
     int* totals;
+    // outputs, touched here only for EMPTY clusters (no chunk will ever write their rows): sum 0, count 0, mean NaN (0 / 0,
+    // what the reference's division gives) - FINCH labels are dense so this is for direct callers of the C ABI
+    double* sums;
+    double* means;
+    int* counts;
+    int d;
     // (a device count above the host bound means the caller's bound was wrong: clamp - nothing is written out of
     // bounds - and the caller, who reads the count back, repeats the call with a larger bound)
     __device__ int64_t size() const {
@@ -53,6 +59,13 @@ struct ChunkScanOp {
         pbase[c] = lb_b(excl);
         for (int j = 0; j < nc && first + j < max_chunks; ++j) chunk_cluster[first + j] = (int)c;
         if (lb_b(item)) multi[atomicAdd(totals + 1, 1)] = (int)c;
+        if (nc == 0) {
+            for (int k = 0; k < d; ++k) {
+                if (sums) sums[c * d + k] = 0.0;
+                if (means) means[c * d + k] = nan("");
+            }
+            if (counts) counts[c] = 0;
+        }
     }
     __device__ void finish(unsigned long long t) const {
         const int64_t c = size();
@@ -230,7 +243,7 @@ int cluster_sums_csr(const T* data, const int* weights, const int* order, const 
     int* tot = state.as<int>();
     unsigned long long* scan_state = reinterpret_cast<unsigned long long*>(state.as<int>() + 8);
     ChunkScanOp op = {offsets, num_clust_dev, num_clust, chunk_base.as<int>(), chunk_cluster.as<int>(), (int)max_chunks,
-                      pbase.as<int>(), multi.as<int>(), tot};
+                      pbase.as<int>(), multi.as<int>(), tot, sums_out, means_out, counts_out, d};
     lookback_scan_kernel<ChunkScanOp><<<lookback_grid(num_clust), LB_THREADS, 0, st>>>(op, scan_state);
     SLIC_LAUNCH_OK();
     const bool vec4 = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(data) & 15) == 0) &&
