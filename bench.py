@@ -482,6 +482,9 @@ def run_b200(args):
                 del xq
                 torch.cuda.empty_cache()
 
+    if world > 1:
+        from video_similarity_search_b200.sharded import close_peer_groups
+        close_peer_groups()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -494,9 +497,11 @@ def run_b200(args):
     if world == 1:
         par = "1 GPU"
     else:
-        par = ("level-0 NN: the %d ranks share the tiles of the symmetric screen's triangle; on the critical path: one NCCL "
-               "all-reduce MAX of 4N bytes (row bests) and one all-reduce MIN of 8(N+1) bytes ((distance, neighbour) keys); "
-               "levels >= 1 replicated" % world)
+        par = ("level-0 NN: the %d ranks share the tiles of the symmetric screen's triangle through NVLink peer windows "
+               "(csrc/comm.cu): ONE screen kernel per rank publishes its pre-pass row bests into every rank's memory (red.max) "
+               "and ONE merge kernel reads the ranks' (distance, neighbour) keys in place - no collective call on the critical "
+               "path of the resident step (two flag barriers in device memory); levels >= 1 replicated on every rank; e2e adds "
+               "one NCCL all-gather of the rows each rank uploaded (1/%d of the matrix per rank over PCIe)" % (world, world))
     line = {
         "metric": METRIC, "value": n / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",

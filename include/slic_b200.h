@@ -338,6 +338,44 @@ int slic_finch_host(const float* x_host, int64_t n, int32_t d, const int64_t* in
  * the call then repeats the search after the upload (same result) and keeps the overlap off for the process. */
 int slic_set_upload_overlap(int32_t enable);
 
+/* ---- multi-GPU (one box, NVLink peer memory; csrc/comm.cu) ---------------------------------------------
+ * The reference clusters on rank 0 only while the other DDP ranks wait at a barrier (online_train.py:619-627, 660-662).
+ * Here the level-0 first-neighbour stage (clustering/finch.py:27-29) is shared by up to 8 GPUs of the box, every GPU
+ * holding the full matrix; no collective library is on the data path - the ranks publish row bests into each other's
+ * memory from inside the screen kernel and merge their (distance, neighbour) keys with one kernel reading peer memory. */
+typedef struct slic_comm slic_comm_t;
+#define SLIC_COMM_HANDLE_BYTES 64
+
+/* (a) ONE PROCESS FOR ALL GPUS - the drop-in for the unmodified call site `c, num_clust, req_c = FINCH(data)` on rank 0:
+ * slic_comm_create enables peer access among `devices` (device 0 of the list runs levels >= 1) and starts one worker
+ * thread per device; max_rows bounds N of later calls (12 bytes of device memory per row and device).
+ * slic_finch_multi = slic_finch_host on the group: every device uploads 1 / G of the rows and forwards them to its peers
+ * over NVLink (copy engines), all devices share the level-0 search, labels come back from device 0.  Inputs the group
+ * cannot share (initial_rank_host given, N < 16384, N > max_rows, one device) run on device 0 alone - same results.
+ * slic_comm_last_timeline: ms_out_host[3] = {upload + forward, normalise + search, whole call} of the last call (CUDA
+ * events on device 0). */
+int slic_comm_create(const int32_t* devices, int32_t num_devices, int64_t max_rows, slic_comm_t** comm_out);
+int slic_finch_multi(slic_comm_t* comm, const float* x_host, int64_t n, int32_t d, const int64_t* initial_rank_host,
+                     int32_t ensure_early_exit, int32_t capacity, int32_t* labels_out_host,
+                     int32_t* num_clust_out_host, int32_t* num_levels_out_host,
+                     float* min_sim_out_host /* or NULL */, int32_t* has_min_sim_out_host /* or NULL */);
+int slic_comm_last_timeline(slic_comm_t* comm, float* ms_out_host);
+int slic_comm_destroy(slic_comm_t* comm);
+
+/* (b) ONE PROCESS PER GPU (torch.distributed jobs): every rank creates its window on its current device and receives a
+ * 64-byte CUDA IPC handle; the host side exchanges the handles (any transport) and every rank maps its peers' windows
+ * with slic_comm_connect(all_handles = world x 64 bytes, in rank order).  slic_comm_nn_top1 is then called by EVERY rank
+ * with the same normalised matrix (slic_normalize_rows: unit_dev [n, d] float32, f16_dev [n, d_pad]), n >= 16384: on
+ * return (stream-ordered, no host synchronisation) idx_out_dev / dist_out_dev [n] hold the first neighbour and float32
+ * cosine distance of every row - identical on every rank and to slic_nn_top1 on one GPU - and status_out_dev[2] =
+ * {rows left without a neighbour, 1 if some rank's search was incomplete}; if either is non-zero the caller repeats the
+ * search another way (degenerate inputs only). */
+int slic_comm_window_create(int64_t max_rows, slic_comm_t** comm_out, void* ipc_handle_out /* 64 bytes */);
+int slic_comm_connect(slic_comm_t* comm, int32_t rank, int32_t world, const void* all_handles);
+int slic_comm_nn_top1(slic_comm_t* comm, const float* unit_dev, const uint16_t* f16_dev, int64_t n, int32_t d,
+                      int32_t d_pad, int32_t* idx_out_dev, float* dist_out_dev, int32_t* status_out_dev,
+                      slic_stream_t stream);
+
 /* Diagnostic timeline of slic_finch_host (CUDA events): enable, run a call, then read ms_out_host[4] =
  * {start -> first copy begins, upload duration, start -> level-0 search done, start -> labels copied back}. */
 int slic_host_trace(int32_t enable, float* ms_out_host);

@@ -41,6 +41,7 @@ class CudaBackend:
             _lib.check(self.lib.slic_require_device(), "slic_require_device")
         self.last_stats = None
         self._stage = None
+        self._multi = None
 
     # -- plumbing ------------------------------------------------------------------------------
     def _stream(self):
@@ -151,6 +152,63 @@ class CudaBackend:
                   _p(keys), _p(stats), self._stream())
         self.last_stats = stats
         return keys, unit
+
+    # -- peer windows (csrc/comm.cu): one process per GPU -----------------------------------------------
+    def comm_window_create(self, max_rows):
+        """-> (comm handle, 64-byte IPC handle of this rank's window as bytes)."""
+        comm = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        with torch.cuda.device(self.device):
+            _lib.call("slic_comm_window_create", int(max_rows), ctypes.addressof(comm), ctypes.addressof(handle))
+        return comm, bytes(handle)
+
+    def comm_connect(self, comm, rank, world, all_handles):
+        buf = (ctypes.c_ubyte * (64 * world)).from_buffer_copy(all_handles)
+        with torch.cuda.device(self.device):
+            _lib.call("slic_comm_connect", comm, int(rank), int(world), ctypes.addressof(buf))
+
+    def comm_destroy(self, comm):
+        _lib.call("slic_comm_destroy", comm)
+
+    def comm_first_neighbors(self, comm, x):
+        """Level-0 first neighbours of all rows of x, the O(N^2 D) stage shared by the ranks connected through `comm`
+        (slic_comm_nn_top1: every rank calls it with the same matrix).  -> (nn, dist, unit, status) with status a
+        device int32[2] = {rows without a neighbour, incomplete flag}; nothing here waits for the device."""
+        n, d = x.shape
+        unit, ub = self.normalize_rows(x, want_f16=True)
+        nn = torch.empty(n, dtype=torch.int32, device=x.device)
+        dist = torch.empty(n, dtype=torch.float32, device=x.device)
+        status = torch.empty(2, dtype=torch.int32, device=x.device)
+        _lib.call("slic_comm_nn_top1", comm, _p(unit), _p(ub), n, d, ub.shape[1], _p(nn), _p(dist), _p(status), self._stream())
+        return nn, dist, unit, status
+
+    # -- rank-0-driven multi-GPU FINCH (csrc/comm.cu): one process, all GPUs of the box -------------------
+    def enable_multi_gpu(self, devices=None, max_rows=1 << 21):
+        """From now on finch_host() - i.e. FINCH(host matrix) - shares the level-0 search among `devices` (default:
+        every visible GPU) through slic_finch_multi; the first device of the list runs levels >= 1.  The call site
+        (online_train.py:619-627: rank 0 clusters, the other ranks wait) stays as it is."""
+        if devices is None:
+            devices = list(range(torch.cuda.device_count()))
+        devices = [int(torch.device(v).index) if not isinstance(v, int) else v for v in devices]
+        self.disable_multi_gpu()
+        if len(devices) < 2:
+            return
+        arr = (ctypes.c_int32 * len(devices))(*devices)
+        comm = ctypes.c_void_p()
+        _lib.call("slic_comm_create", ctypes.addressof(arr), len(devices), int(max_rows), ctypes.addressof(comm))
+        self._multi = (comm, devices, int(max_rows))
+
+    def disable_multi_gpu(self):
+        multi = getattr(self, "_multi", None)
+        if multi is not None:
+            _lib.call("slic_comm_destroy", multi[0])
+        self._multi = None
+
+    def multi_gpu_timeline(self):
+        """ms of the last multi-GPU finch_host call: (upload + forward, normalise + search, whole call)."""
+        out = (ctypes.c_float * 3)()
+        _lib.call("slic_comm_last_timeline", self._multi[0], ctypes.addressof(out))
+        return tuple(out)
 
     def unpack_neighbor_keys(self, keys):
         """Merged keys [n + 1] -> (nn int32 [n], dist float32 [n], complete bool).  One host read-back."""
@@ -313,10 +371,16 @@ class CudaBackend:
             rank = np.ascontiguousarray(np.asarray(initial_rank), dtype=np.int64)
             if rank.shape != (n,):
                 raise ValueError("initial_rank must have one entry per row of data")
+        multi = getattr(self, "_multi", None)
         with torch.cuda.device(self.device):
-            _lib.call("slic_finch_host", x.ctypes.data, n, d, None if rank is None else rank.ctypes.data,
-                      int(bool(ensure_early_exit)), cap, out.ctypes.data, ctypes.addressof(num), ctypes.addressof(levels),
-                      ctypes.addressof(ms), ctypes.addressof(has))
+            if multi is not None:
+                _lib.call("slic_finch_multi", multi[0], x.ctypes.data, n, d, None if rank is None else rank.ctypes.data,
+                          int(bool(ensure_early_exit)), cap, out.ctypes.data, ctypes.addressof(num),
+                          ctypes.addressof(levels), ctypes.addressof(ms), ctypes.addressof(has))
+            else:
+                _lib.call("slic_finch_host", x.ctypes.data, n, d, None if rank is None else rank.ctypes.data,
+                          int(bool(ensure_early_exit)), cap, out.ctypes.data, ctypes.addressof(num), ctypes.addressof(levels),
+                          ctypes.addressof(ms), ctypes.addressof(has))
         p = levels.value
         return out[: n * p].reshape(n, p).copy(), [int(v) for v in num[:p]], (np.float32(ms.value) if has.value else None)
 

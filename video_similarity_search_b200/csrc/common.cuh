@@ -80,6 +80,16 @@ struct GateSpec {
     int64_t chunk_rows;   // multiple of 256
 };
 typedef int (*AfterScreenFn)(void* ctx);
+// Multi-GPU fused search: where this rank's screen kernel publishes pre-pass results (comm.cu owns the memory: every
+// pointer lies in a peer-mapped window of one of the ranks of the box).
+constexpr int SLIC_MAX_PEERS = 7;   // ranks of one box - 1
+struct ScreenPeers {
+    int num_peers;
+    unsigned int* own_best;                    // [n] this rank's row bests (its window; the peers write into it)
+    int* own_sync;                             // this rank's pre-pass arrival counter (its window)
+    unsigned int* peer_best[SLIC_MAX_PEERS];   // the same two of every other rank
+    int* peer_sync[SLIC_MAX_PEERS];
+};
 // can CTAs of the given shape co-reside with the persistent screen kernel of a gated self-search (see nn_screen_tc.cu)
 bool screen_can_overlap_upload(int64_t n, int d_pad, int guest_threads, int guest_regs);
 // prep.cu: CTA shape of the float32 normalise kernel (the guest of a gated launch)
@@ -96,6 +106,23 @@ int nn_top1_f32_gated(const float* q_unit, const uint16_t* q_f16, int64_t nq, co
 // self-search of all rows (first neighbour + distance in `dtype`), asynchronous as above
 int nn_top1_self_async(const void* unit, const uint16_t* ub, int64_t n, int d, int d_pad, int dtype, int* idx_out,
                        void* dist_out, int* stats_ext, cudaStream_t st);
+
+// This rank's part of the fused multi-GPU self-search (comm.cu): pre-pass over its 1 / parts of the row units, published
+// to every rank from inside the kernel, then its 1 / parts of the symmetric screen's triangle and the exact re-rank.
+// idx_out / dist_out [n]: the best pair this rank saw for EVERY row (idx 0x7fffffff: none).  Asynchronous: stats_dev
+// (8 ints) receives {[1] rows without a record, [4] pipeline error, [5] log overflow}.
+int nn_top1_sym_fused(const float* unit, const uint16_t* ub, int64_t n, int d, int d_pad, int part, int parts,
+                      const ScreenPeers* peers, AfterScreenFn before_screen, void* before_ctx, int* idx_out,
+                      float* dist_out, int* stats_dev, cudaStream_t st);
+// finch_driver.cu: the hierarchy after a level-0 search done elsewhere (comm.cu), labels to the host; see there
+int finch_tail_to_host(const float* data, int64_t n, int d, int* nn, float* dist, const float* unit, const uint16_t* ub,
+                       int* blk16, bool ensure_early_exit, int capacity, int* labels_out_host, int* num_clust_host,
+                       int* num_levels_host, float* min_sim_host, int* has_min_sim_host, cudaStream_t st);
+int finch_host_single(const float* x_host, int64_t n, int d, const int64_t* initial_rank_host, bool ensure_early_exit,
+                      int capacity, int* labels_out_host, int* num_clust_host, int* num_levels_host, float* min_sim_host,
+                      int* has_min_sim_host);
+// per-row key of the multi-GPU merge: (float32 distance bits << 32) | neighbour; MIN over the ranks = np.argmin's rule
+constexpr unsigned long long SYM_KEY_NONE = 0x7fffffff7fffffffull;
 
 __host__ __device__ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -566,6 +566,45 @@ static int finch_host_impl(const float* x_host, int64_t n, int d, const int64_t*
     return SLIC_OK;
 }
 
+// comm.cu (single-process multi-GPU FINCH): everything after a level-0 search that was carried out elsewhere, on the
+// device whose stream this is; labels go straight to the host.  blk16: the search's asynchronous status block
+// ([1] rows without a neighbour, [4] pipeline error, [5] incomplete) - when set, the search is repeated here on this
+// one device through the synchronous path before the hierarchy is built (nn / dist are then overwritten).
+int finch_tail_to_host(const float* data, int64_t n, int d, int* nn, float* dist, const float* unit, const uint16_t* ub,
+                       int* blk16, bool ensure_early_exit, int capacity, int* labels_out_host, int* num_clust_host,
+                       int* num_levels_host, float* min_sim_host, int* has_min_sim_host, cudaStream_t st) {
+    Scratch labels;
+    SLIC_CUDA_OK(labels.alloc((size_t)n * capacity * sizeof(int), st));
+    Level0 l0;
+    l0.nn = nn;
+    l0.dist = dist;
+    l0.unit = unit;
+    l0.dense = n <= FLANN_THRESHOLD;
+    l0.async_stats = blk16;
+    l0.retry_ub = ub;
+    l0.retry_nn = nn;
+    l0.retry_dist = dist;
+    l0.no_self_links = true;
+    int levels = 0;
+    SLIC_PROPAGATE(finch_levels(data, n, d, l0, ensure_early_exit, capacity, labels.as<int>(), num_clust_host, &levels,
+                                min_sim_host, has_min_sim_host, st));
+    *num_levels_host = levels;
+    SLIC_CUDA_OK(cudaMemcpyAsync(labels_out_host, labels.ptr, (size_t)n * levels * sizeof(int), cudaMemcpyDeviceToHost, st));
+    SLIC_CUDA_OK(cudaStreamSynchronize(st));
+    return SLIC_OK;
+}
+
+// the host-matrix entry on the CURRENT device with its own streams (comm.cu falls back to it for inputs the multi-GPU
+// search does not take: caller-supplied neighbours, fewer rows than the symmetric screen needs)
+int finch_host_single(const float* x_host, int64_t n, int d, const int64_t* initial_rank_host, bool ensure_early_exit,
+                      int capacity, int* labels_out_host, int* num_clust_host, int* num_levels_host, float* min_sim_host,
+                      int* has_min_sim_host) {
+    HostStreams hs;
+    SLIC_PROPAGATE(hs.init());
+    return finch_host_impl(x_host, n, d, initial_rank_host, ensure_early_exit, capacity, labels_out_host, num_clust_host,
+                           num_levels_host, min_sim_host, has_min_sim_host, hs);
+}
+
 }  // namespace slic
 
 extern "C" {

@@ -142,6 +142,13 @@ struct ScreenParams {
     // Dynamic scheduling: units are handed out in list order from this global counter (zeroed before the launch) to
     // whichever CTA pair becomes free - no pair idles while another still holds a queue of long units.
     int* queue;
+    // Multi-GPU fused search (comm.cu): the pre-pass units of this rank publish their rows' bests into the best arrays
+    // of the OTHER ranks as well (red.max over NVLink peer mappings) and count their arrivals on every rank's
+    // sync_counter, so the triangle units of every rank start from thresholds for ALL rows - the exchange that used to
+    // be a separate launch + all-reduce happens inside the one kernel.
+    int num_peers;
+    unsigned int* peer_best[SLIC_MAX_PEERS];
+    int* peer_sync[SLIC_MAX_PEERS];
 };
 
 struct UnitInfo {
@@ -283,21 +290,25 @@ __device__ __forceinline__ void gate_wait(const int* gate, int* error_flag) {
     }
     asm volatile("fence.proxy.async.global;" ::: "memory");
 }
+// Pre-pass hand-over.  In a multi-GPU fused search the counter also collects the arrivals of the OTHER ranks' kernels,
+// so - like a gate - it depends on work this kernel does not control: bounded, never traps.  (Thresholds read too early
+// only cost speed, never results; the flag makes the host repeat the search anyway, since a rank may be missing.)
 __device__ __forceinline__ void counter_wait(const int* counter, int target, int* error_flag) {
     long long t0 = 0;
     uint32_t polls = 0;
     while (true) {
         int v;
-        asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        asm volatile("ld.acquire.sys.global.b32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");   // (peers add over NVLink)
         if (v >= target) break;
         __nanosleep(128);
         if ((++polls & 0xff) == 0) {
+            if (error_flag && *reinterpret_cast<volatile int*>(error_flag) == SCREEN_ERR_GATE) break;
             long long now = clock64();
             if (t0 == 0) t0 = now;
-            else if (now - t0 > 20000000000ll) {
-                if (error_flag) atomicExch(error_flag, 1);
+            else if (now - t0 > 4000000000ll) {
+                if (error_flag) atomicCAS(error_flag, 0, SCREEN_ERR_GATE);
                 record_timeout(3, v, target);
-                __trap();
+                break;
             }
         }
     }
@@ -1266,11 +1277,20 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
             if constexpr (TOPK) pend_flush(cx.pd, cx.st, p.eps, p.cap, p.topk, true, cx.hist, cx.li, cx.ls);
             if constexpr (SYM) {
                 // publish this unit's best for the row; the shared list is already in place
-                if (cx.row_ok && cx.st.best > -CUDART_INF_F) atomicMax(p.best_enc + cx.row, enc_score(cx.st.best));
+                if (cx.row_ok && cx.st.best > -CUDART_INF_F) {
+                    const unsigned e = enc_score(cx.st.best);
+                    atomicMax(p.best_enc + cx.row, e);
+                    if (!ui.coldir)   // pre-pass: every other rank learns this row's first threshold too
+                        for (int g = 0; g < p.num_peers; ++g) atomicMax(p.peer_best[g] + cx.row, e);
+                }
                 if (!ui.coldir && p.sync_counter) {   // pre-pass unit done: its rows' thresholds are published
-                    __threadfence();
+                    if (p.num_peers) __threadfence_system();
+                    else __threadfence();
                     __syncwarp();
-                    if (lane == 0) atomicAdd(p.sync_counter, 1);
+                    if (lane == 0) {
+                        atomicAdd(p.sync_counter, 1);
+                        for (int g = 0; g < p.num_peers; ++g) atomicAdd(p.peer_sync[g], 1);
+                    }
                 }
             } else if (cx.row_ok) {
                 p.cand_cnt[slot] = cx.st.cnt;
@@ -1685,7 +1705,8 @@ static int launch_screen(const uint16_t* q_f16, int64_t nq, const uint16_t* x_f1
                          int* cand_cnt, int* cand_flags, float* dump, int* error_flag, cudaStream_t st, int topk = 0,
                          float* cand_kth = nullptr, const int4* unit_table = nullptr, const int* gates = nullptr,
                          unsigned int* best_enc = nullptr, int64_t exec_tiles = 0, int* log_q = nullptr,
-                         int log_region = 0, int* sync_counter = nullptr, const int* sync_targets = nullptr) {
+                         int log_region = 0, int* sync_counter = nullptr, const int* sync_targets = nullptr,
+                         const ScreenPeers* peers = nullptr) {
     const int ncta = screen_ncta();
     if (gates) SLIC_PROPAGATE(arm_timeout_record());
     CUtensorMap tq, tx;
@@ -1717,6 +1738,18 @@ static int launch_screen(const uint16_t* q_f16, int64_t nq, const uint16_t* x_f1
     p.log_region = log_region;
     p.sync_counter = sync_counter;
     p.sync_targets = sync_targets;
+    p.num_peers = 0;
+    for (int g = 0; g < SLIC_MAX_PEERS; ++g) {
+        p.peer_best[g] = nullptr;
+        p.peer_sync[g] = nullptr;
+    }
+    if (peers) {
+        p.num_peers = peers->num_peers;
+        for (int g = 0; g < peers->num_peers; ++g) {
+            p.peer_best[g] = peers->peer_best[g];
+            p.peer_sync[g] = peers->peer_sync[g];
+        }
+    }
     Scratch queue;   // (freed in stream order, i.e. after the kernel)
     SLIC_CUDA_OK(queue.alloc(sizeof(int), st));
     SLIC_CUDA_OK(cudaMemsetAsync(queue.ptr, 0, sizeof(int), st));
@@ -1844,9 +1877,14 @@ constexpr int SYM_SAMPLE_TILES = 16;
 //       SYM_BESTS     ONLY a pre-pass, over this part's 1 / parts of the row units (multi-GPU phase 1: the parts then
 //                     exchange the row bests, so that every part starts the triangle with thresholds for ALL rows)
 //       SYM_TRIANGLE  ONLY this part's share of the triangle (row bests were seeded by the caller)
-enum SymMode { SYM_FULL = 0, SYM_BESTS = 1, SYM_TRIANGLE = 2 };
+//       SYM_FUSED     SYM_BESTS followed by SYM_TRIANGLE in ONE unit list (multi-GPU, comm.cu): the pre-pass units publish
+//                     to every rank's best array from inside the kernel and the triangle units wait for the pre-pass
+//                     arrivals of ALL ranks (*prepass_units_all = their number over all parts)
+enum SymMode { SYM_FULL = 0, SYM_BESTS = 1, SYM_TRIANGLE = 2, SYM_FUSED = 3 };
+constexpr int SYM_FUSED_PRE_TILES = 16;   // fused pre-pass: a row unit's sample is cut into units of this many tiles (balance)
 static int plan_screen_sym(int64_t n, int part, int parts, const GateSpec* g, ScreenPlan* pl, std::vector<int4>* table,
-                           SymMode mode = SYM_FULL) {
+                           SymMode mode = SYM_FULL, int64_t* prepass_units_all = nullptr) {
+    const bool own_rows_prepass = mode == SYM_BESTS || mode == SYM_FUSED;
     const int64_t T = ceil_div(n, TC_BN);
     SLIC_REQUIRE(T < 65536, "symmetric screen: more than 16.7 M rows");
     SLIC_REQUIRE(parts >= 1 && part >= 0 && part < parts, "symmetric screen: bad partition");
@@ -1868,8 +1906,8 @@ static int plan_screen_sym(int64_t n, int part, int parts, const GateSpec* g, Sc
     // SYM_BESTS: every part pays a warm-up of loose thresholds at the start of its (short) share of the triangle, so a
     // stronger sample pays off from 4 parts on (measured at 8 parts, C3: 16 / 32 / 64 tiles -> 3.96 / 3.64 / 3.30 ms for
     // the triangle share against +0.1 ms per 16 tiles here)
-    int samples = mode == SYM_BESTS ? (parts >= 4 ? 4 * SYM_SAMPLE_TILES : SYM_SAMPLE_TILES) : SYM_SAMPLE_TILES / parts;
-    if (mode == SYM_BESTS && samples > span / 4) samples = (int)(span / 4);   // small inputs: a sample, not the whole square
+    int samples = own_rows_prepass ? (parts >= 4 ? 4 * SYM_SAMPLE_TILES : SYM_SAMPLE_TILES) : SYM_SAMPLE_TILES / parts;
+    if (own_rows_prepass && samples > span / 4) samples = (int)(span / 4);   // small inputs: a sample, not the whole square
     // small inputs (a hierarchy's level 1): the pre-pass must stay a sample - measured at 21 436 x 512 float64 centroids:
     // 16 / 10 / 4 sample tiles -> 0.88 / 0.79 / 0.72 ms for the whole search
     if (mode == SYM_FULL && T < 128 && samples > T / 16) samples = (int)(T / 16);
@@ -1880,10 +1918,14 @@ static int plan_screen_sym(int64_t n, int part, int parts, const GateSpec* g, Sc
     }
     if (samples > span) samples = (int)span;
     const int stride = (int)(span / samples);
-    const int64_t pre0 = mode == SYM_BESTS ? T * part / parts : 0, pre1 = mode == SYM_BESTS ? T * (part + 1) / parts : T;
+    const int64_t pre0 = own_rows_prepass ? T * part / parts : 0, pre1 = own_rows_prepass ? T * (part + 1) / parts : T;
+    const int pre_len = mode == SYM_FUSED ? SYM_FUSED_PRE_TILES : samples;
+    if (prepass_units_all) *prepass_units_all = T * ceil_div(samples, pre_len);
     for (int64_t r = pre0; r < pre1 && mode != SYM_TRIANGLE; ++r) {
         const int gate = g ? (int)(r / chunk_tiles_gate) : -1;
-        table->push_back(unit_entry(r, 0, samples, stride, gate, 0, false));
+        for (int s0 = 0; s0 < samples; s0 += pre_len)
+            table->push_back(unit_entry(r, (int64_t)s0 * stride, samples - s0 < pre_len ? samples - s0 : pre_len, stride, gate, 0,
+                                        false));
     }
     // part / parts: a CONTIGUOUS range of the chunk-major unit list holding 1 / parts of the triangle's tiles.  (Dealing
     // the units round-robin was measured at 8 ranks: a rank's 74 concurrent CTA pairs then span ~9 column chunks, the B
@@ -1960,7 +2002,9 @@ template <typename T>
 static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d, int d_pad, float eps, int* idx_out,
                             T* dist_out, int* stats_out, cudaStream_t st, int part, int parts, const GateSpec* gate,
                             AfterScreenFn after, void* after_ctx, bool* overflowed, int mode = 0,
-                            const int* bests_in = nullptr, int* bests_out = nullptr, int* stats_ext = nullptr);
+                            const int* bests_in = nullptr, int* bests_out = nullptr, int* stats_ext = nullptr,
+                            const ScreenPeers* peers = nullptr, AfterScreenFn before_screen = nullptr,
+                            void* before_ctx = nullptr);
 static bool screen_sym_allowed();
 constexpr int64_t SYM_MIN_ROWS_FWD = 16384;   // below: too few tiles to fill the machine with half of them
 
@@ -2217,7 +2261,11 @@ template <typename T>
 static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d, int d_pad, float eps, int* idx_out,
                             T* dist_out, int* stats_out, cudaStream_t st, int part, int parts, const GateSpec* gate,
                             AfterScreenFn after, void* after_ctx, bool* overflowed, int mode, const int* bests_in,
-                            int* bests_out, int* stats_ext) {
+                            int* bests_out, int* stats_ext, const ScreenPeers* peers, AfterScreenFn before_screen,
+                            void* before_ctx) {
+    // peers (SYM_FUSED only): the row bests and the pre-pass counter live in this rank's peer-mapped window; before_screen
+    // runs on the host between the initialisation kernel and the screen launch (comm.cu enqueues the cross-rank barrier
+    // there: no rank may publish into a window that has not been reset yet).
     // stats_ext (device, 8 ints, optional): ASYNCHRONOUS mode - nothing here waits for the device.  The counters
     // {[1] rows without a neighbour, [4] pipeline error, [5] log overflow} land in stats_ext; if any is non-zero the
     // result is incomplete and the caller repeats the search through the synchronous path (which has the fallbacks).
@@ -2225,7 +2273,10 @@ static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d,
     *overflowed = false;
     ScreenPlan pl;
     std::vector<int4> table;
-    SLIC_PROPAGATE(plan_screen_sym(n, part, parts, gate, &pl, &table, (SymMode)mode));
+    int64_t prepass_units_all = 0;
+    SLIC_PROPAGATE(plan_screen_sym(n, part, parts, gate, &pl, &table, (SymMode)mode, &prepass_units_all));
+    SLIC_REQUIRE((mode == SYM_FUSED) == (peers != nullptr), "symmetric screen: the fused mode needs peer windows (and only it)");
+    SLIC_REQUIRE(mode != SYM_FUSED || (stats_ext && !gate), "symmetric screen: the fused mode is asynchronous and ungated");
     int64_t exec_tiles = 0;
     for (const int4& e : table) exec_tiles += e.z & 0xffff;
     // sync_targets[g + 1] = epilogue-warp arrivals of all pre-pass units with gate <= g (index 0: ungated)
@@ -2236,6 +2287,7 @@ static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d,
         const int g = (e.w & 0xfff) - 1;
         for (int k = g + 1; k <= num_gates; ++k) targets[k] += 2 * TC_EPI_WARPS;   // g = -1 (ungated): index 0
     }
+    if (mode == SYM_FUSED) targets[0] = (int)(prepass_units_all * 2 * TC_EPI_WARPS);   // the pre-pass units of ALL ranks
     const int64_t groups = num_sms() / 2;
     const int64_t grid = (pl.units < groups ? pl.units : groups) * 2;
     const int64_t regions = grid * TC_EPI_WARPS;
@@ -2262,7 +2314,9 @@ static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d,
     SLIC_CUDA_OK(ls.alloc(regions * region * sizeof(float), st));
     SLIC_CUDA_OK(edist.alloc(regions * region * sizeof(T), st));
     SLIC_CUDA_OK(lcnt.alloc(regions * sizeof(int), st));
-    SLIC_CUDA_OK(best.alloc(n * sizeof(unsigned int), st));
+    if (!peers) SLIC_CUDA_OK(best.alloc(n * sizeof(unsigned int), st));
+    unsigned int* best_dev = peers ? peers->own_best : best.as<unsigned int>();
+    int* sync_counter_dev = peers ? peers->own_sync : sync_dev;
     SLIC_CUDA_OK(rmin.alloc(n * sizeof(Bits), st));
     SLIC_CUDA_OK(ovr.alloc(n * sizeof(int), st));
     int* stats_dev = stats_ext;
@@ -2277,11 +2331,12 @@ static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d,
         if (ceil_div(rmin_bytes, 16) > threads) threads = ceil_div(rmin_bytes, 16);
         if (threads < 8) threads = 8;
         sym_init_kernel<<<(unsigned)ceil_div(threads, 256), 256, 0, st>>>(stats_dev, lcnt.as<int>(), regions,
-                                                                         static_cast<unsigned char*>(rmin.ptr), rmin_bytes, sync_dev,
-                                                                         best.as<unsigned int>(), (const unsigned int*)bests_in, n,
-                                                                         (unsigned int*)idx_out);
+                                                                         static_cast<unsigned char*>(rmin.ptr), rmin_bytes,
+                                                                         sync_counter_dev, best_dev,
+                                                                         (const unsigned int*)bests_in, n, (unsigned int*)idx_out);
         SLIC_LAUNCH_OK();
     }
+    if (before_screen) SLIC_PROPAGATE(before_screen(before_ctx));
     static int nowait = -1;   // experiments: SLIC_SYM_NOWAIT=1 lets triangle units start before the pre-pass has finished
     if (nowait < 0) {
         const char* e = getenv("SLIC_SYM_NOWAIT");
@@ -2289,12 +2344,12 @@ static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d,
     }
     SLIC_PROPAGATE(launch_screen(ub, n, ub, n, d_pad, 0, eps, 0, pl, lnb.as<int>(), ls.as<float>(), lcnt.as<int>(),
                                  flag_dev, nullptr, stats_dev + 4, st, 0, nullptr, table_dev.as<int4>(),
-                                 gate ? gate->gates : nullptr, best.as<unsigned int>(), exec_tiles, lq.as<int>(),
-                                 (int)region, nowait ? nullptr : sync_dev, sync_dev + 1));
+                                 gate ? gate->gates : nullptr, best_dev, exec_tiles, lq.as<int>(),
+                                 (int)region, nowait ? nullptr : sync_counter_dev, sync_dev + 1, peers));
     if (g_profile && parts > 1) g_last_flop /= (double)parts;   // this process's share of the algorithmic 2 n^2 d
     if (after) SLIC_PROPAGATE(after(after_ctx));
     if (mode == SYM_BESTS) {   // phase 1 of the multi-GPU search: the row bests are the result, the log is discarded
-        flip_sign_bit_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(best.as<unsigned int>(), n, (unsigned int*)bests_out);
+        flip_sign_bit_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(best_dev, n, (unsigned int*)bests_out);
         SLIC_LAUNCH_OK();
         int host_err = 0;
         SLIC_CUDA_OK(cudaMemcpyAsync(&host_err, stats_dev + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -2307,7 +2362,7 @@ static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d,
         return SLIC_OK;
     }
     sym_rerank_dist_kernel<T><<<(unsigned)regions, 256, 0, st>>>(unit, d, eps, (int)region, lq.as<int>(), lnb.as<int>(),
-                                                                 ls.as<float>(), lcnt.as<int>(), best.as<unsigned int>(),
+                                                                 ls.as<float>(), lcnt.as<int>(), best_dev,
                                                                  rmin.as<Bits>(), edist.as<T>(), stats_dev);
     SLIC_LAUNCH_OK();
     sym_rerank_pick_kernel<T><<<(unsigned)regions, 256, 0, st>>>((int)region, lq.as<int>(), lnb.as<int>(), lcnt.as<int>(),
@@ -2376,8 +2431,6 @@ static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d,
 // key = (float32 distance bits << 32) | neighbour: distances are >= 0, so their bit patterns order like the values and
 // an element-wise MIN over the processes' key arrays (one all-reduce) picks the smallest distance and, among equal
 // distances, the lowest neighbour index - np.argmin's rule.  A row without a record keeps the largest key.
-constexpr unsigned long long SYM_KEY_NONE = 0x7fffffff7fffffffull;
-
 __global__ void sym_pack_keys_kernel(const int* __restrict__ idx, const float* __restrict__ dist, int64_t n,
                                      unsigned long long* __restrict__ keys) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -2440,6 +2493,19 @@ int nn_top1_self_async(const void* unit, const uint16_t* ub, int64_t n, int d, i
                                    idx_out, (float*)dist_out, nullptr, st, nullptr, nullptr, nullptr, stats_ext);
     return nn_top1_impl<double>((const double*)unit, ub, n, (const double*)unit, ub, n, d, d_pad, 0, TC_DEFAULT_EPS, idx_out,
                                 (double*)dist_out, nullptr, st, nullptr, nullptr, nullptr, stats_ext);
+}
+
+int nn_top1_sym_fused(const float* unit, const uint16_t* ub, int64_t n, int d, int d_pad, int part, int parts,
+                      const ScreenPeers* peers, AfterScreenFn before_screen, void* before_ctx, int* idx_out,
+                      float* dist_out, int* stats_dev, cudaStream_t st) {
+    if (!screen_self_search_is_symmetric(n)) {
+        set_error("fused multi-GPU search: the symmetric screen needs n >= %lld rows", (long long)SYM_MIN_ROWS_FWD);
+        return SLIC_ERR_UNSUPPORTED;
+    }
+    bool overflowed = false;
+    return nn_top1_sym_impl<float>(unit, ub, n, d, d_pad, TC_DEFAULT_EPS, idx_out, dist_out, nullptr, st, part, parts, nullptr,
+                                   nullptr, nullptr, &overflowed, SYM_FUSED, nullptr, nullptr, stats_dev, peers,
+                                   before_screen, before_ctx);
 }
 
 }  // namespace slic

@@ -75,7 +75,9 @@ int exclusive_scan_i32(const int* in, int* out, int64_t n, int* total_out, cudaS
 // ------------------------------------------------------------------------------------------
 // Warp-aggregated: lanes holding the same key elect one leader that adds the group's size, so a label array
 // with few distinct values (the coarse FINCH levels) does not serialise on a handful of addresses.
-__global__ void histogram_kernel(const int* __restrict__ keys, int64_t n, int* __restrict__ counts) {
+// Keys outside [0, bins) are not counted (the asynchronous FINCH driver enqueues this on neighbour arrays whose
+// completeness it only learns later: a row the search left unsettled carries the index 0x7fffffff).
+__global__ void histogram_kernel(const int* __restrict__ keys, int64_t n, int* __restrict__ counts, int64_t bins) {
     const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t n_round = (n + 31) / 32 * 32;  // keep whole warps in the loop for the match
@@ -83,7 +85,7 @@ __global__ void histogram_kernel(const int* __restrict__ keys, int64_t n, int* _
         const bool valid = i < n;
         const int key = valid ? keys[i] : -1 - lane;
         const unsigned peers = __match_any_sync(0xffffffffu, key);
-        if (valid && (__ffs(peers) - 1) == lane) atomicAdd(&counts[key], __popc(peers));
+        if (valid && key >= 0 && key < bins && (__ffs(peers) - 1) == lane) atomicAdd(&counts[key], __popc(peers));
     }
 }
 
@@ -91,7 +93,7 @@ int histogram_i32(const int* keys, int64_t n, int* counts, int64_t bins, cudaStr
     SLIC_CUDA_OK(cudaMemsetAsync(counts, 0, bins * sizeof(int), st));
     if (n <= 0) return SLIC_OK;
     int blocks = (int)((n + 1023) / 1024 < (int64_t)num_sms() * 8 ? (n + 1023) / 1024 : (int64_t)num_sms() * 8);
-    histogram_kernel<<<blocks, 256, 0, st>>>(keys, n, counts);
+    histogram_kernel<<<blocks, 256, 0, st>>>(keys, n, counts, bins);
     SLIC_LAUNCH_OK();
     return SLIC_OK;
 }

@@ -19,22 +19,68 @@ from . import backend as _backend
 from .clustering.finch import FINCH
 
 
+class PeerGroup:
+    """NVLink peer windows of the ranks of a process group (one process per GPU; csrc/comm.cu).  The 64-byte CUDA IPC
+    handles travel through the process group once, at construction; after that the level-0 search of the group needs
+    no collective call at all - the ranks publish into and read from each other's windows from inside their kernels."""
+
+    def __init__(self, be, group=None, max_rows=1 << 20):
+        self.be, self.group, self.max_rows = be, group, int(max_rows)
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.comm, handle = be.comm_window_create(self.max_rows)
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=be.device)
+        everyone = torch.empty(64 * self.world, dtype=torch.uint8, device=be.device)
+        dist.all_gather_into_tensor(everyone, mine, group=group)
+        be.comm_connect(self.comm, self.rank, self.world, bytes(everyone.cpu().tolist()))
+        dist.barrier(group=group)          # every rank has mapped every window before anyone publishes into one
+
+    def first_neighbors(self, mat):
+        """-> (nn, dist, unit, status): status is a device int32[2], non-zero = repeat the search another way."""
+        return self.be.comm_first_neighbors(self.comm, mat)
+
+    def close(self):
+        if self.comm is not None:
+            torch.cuda.synchronize(self.be.device)
+            dist.barrier(group=self.group)  # nobody unmaps a window a peer's kernel may still be touching
+            self.be.comm_destroy(self.comm)
+            self.comm = None
+
+
 def shard_range(n, rank, world):
     per = (n + world - 1) // world
     r0 = min(rank * per, n)
     return r0, min(r0 + per, n), per
 
 
-def sharded_first_neighbors(be, group=None, timings=None, triangle=True):
+def sharded_first_neighbors(be, group=None, timings=None, triangle=True, peer=True):
     """Returns a callable mat -> (nn, dist, unit) for FINCH(first_neighbors=...).
-    triangle=True (default): large float32 self-searches are shared as parts of the symmetric screen's triangle and
-    merged by one all-reduce; otherwise (and for small inputs) query rows are sharded and the ids all-gathered."""
+    triangle=True (default): large float32 self-searches are shared as parts of the symmetric screen's triangle;
+      peer=True (default, up to 8 ranks of one box): through NVLink peer windows - one fused kernel per rank, no collective
+        call on the data path (PeerGroup); peer=False: two screen launches with an NCCL all-reduce MAX of the row bests
+        between them and an all-reduce MIN of the keys after (the round-1 scheme, also used by the CPU stand-in tests);
+    otherwise (and for small inputs) query rows are sharded and the ids all-gathered."""
+    def peer_group(n):
+        # one set of windows per (backend, process group), shared by every search built on them and grown on demand
+        key = (id(be), id(group))
+        pg = _PEER_GROUPS.get(key)
+        if pg is not None and pg.max_rows < n:
+            pg.close()
+            pg = None
+        if pg is None:
+            pg = _PEER_GROUPS[key] = PeerGroup(be, group, max_rows=max(n, 1 << 18))
+        return pg
 
     def search(mat):
         world = dist.get_world_size(group)
         rank = dist.get_rank(group)
         n = mat.shape[0]
-        if world > 1 and triangle and hasattr(be, "first_neighbors_part") and be.supports_triangle_parts(mat):
+        use_triangle = world > 1 and triangle and hasattr(be, "first_neighbors_part") and be.supports_triangle_parts(mat)
+        if use_triangle and peer and world <= 8 and hasattr(be, "comm_first_neighbors"):
+            nn, d, unit, status = peer_group(n).first_neighbors(mat)
+            if not status.any().item():      # (the one host read-back of the stage; identical on every rank)
+                return nn, d, unit
+            use_triangle = False             # degenerate input (candidate log overflow): row-sharded full square below
+        if use_triangle:
             # The score matrix of a self-search is symmetric: the ranks share the tiles on or right of its diagonal
             # (half the flops of the row-sharded full square) and every rank ends up with, for EVERY row, the best
             # neighbour among the pairs it saw, as (distance, neighbour) keys; every rank sees the same merged array,
@@ -65,6 +111,15 @@ def sharded_first_neighbors(be, group=None, timings=None, triangle=True):
         return nn_all[:n].contiguous(), d_all[:n].contiguous(), unit
 
     return search
+
+
+_PEER_GROUPS = {}
+
+
+def close_peer_groups():
+    """Unmap and free the NVLink peer windows (collective: every rank calls it; before destroy_process_group)."""
+    for key in list(_PEER_GROUPS):
+        _PEER_GROUPS.pop(key).close()
 
 
 def upload_replicated(data, group=None, backend=None):
