@@ -27,7 +27,7 @@ def screen_ms(fn):
         lib.slic_screen_trace(0, c)
         c = [v / 148.0 / 1e6 for v in c]
         print("    trace (Mcycles per CTA): producer-wait %.2f | mma: wait-acc %.2f wait-operands %.2f total %.2f | epi0: wait-mma %.2f total %.2f | chunks triggered %.3f of %.3f M"
-              % tuple(c))
+              % tuple(c[:8]))
     return ms.value, fl.value / ms.value / 1e9
 for shape in sys.argv[1:]:
     nq, n, d = [int(v) for v in shape.split("x")]
