@@ -376,6 +376,14 @@ int slic_comm_nn_top1(slic_comm_t* comm, const float* unit_dev, const uint16_t* 
                       int32_t d_pad, int32_t* idx_out_dev, float* dist_out_dev, int32_t* status_out_dev,
                       slic_stream_t stream);
 
+/* slic_finch on the group: the whole hierarchy of the device-resident [n, d] float32 matrix, called by EVERY rank with
+ * the same matrix; level 0 through slic_comm_nn_top1's data path, everything after it replicated on every rank, one
+ * host synchronisation at the end.  Outputs as slic_finch (labels_out_dev: [n, capacity] on this rank's device). */
+int slic_comm_finch(slic_comm_t* comm, const float* data_dev, int64_t n, int32_t d, int32_t ensure_early_exit,
+                    int32_t capacity, int32_t* labels_out_dev, int32_t* num_clust_out_host,
+                    int32_t* num_levels_out_host, float* min_sim_out_host /* or NULL */,
+                    int32_t* has_min_sim_out_host /* or NULL */, slic_stream_t stream);
+
 /* Diagnostic timeline of slic_finch_host (CUDA events): enable, run a call, then read ms_out_host[4] =
  * {start -> first copy begins, upload duration, start -> level-0 search done, start -> labels copied back}. */
 int slic_host_trace(int32_t enable, float* ms_out_host);

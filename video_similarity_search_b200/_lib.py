@@ -60,6 +60,7 @@ SIGNATURES = {
     "slic_comm_window_create": [_i64, _ptr, _ptr],
     "slic_comm_connect": [_ptr, _i32, _i32, _ptr],
     "slic_comm_nn_top1": [_ptr, _ptr, _ptr, _i64, _i32, _i32, _ptr, _ptr, _ptr, _ptr],
+    "slic_comm_finch": [_ptr, _ptr, _i64, _i32, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
     "slic_finch": [_ptr, _i64, _i32, _ptr, _ptr, _ptr, _i32, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
     "slic_finch_host": [_ptr, _i64, _i32, _ptr, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr],
 }

@@ -182,6 +182,20 @@ class CudaBackend:
         _lib.call("slic_comm_nn_top1", comm, _p(unit), _p(ub), n, d, ub.shape[1], _p(nn), _p(dist), _p(status), self._stream())
         return nn, dist, unit, status
 
+    def finch_native_comm(self, comm, data, ensure_early_exit=True):
+        """slic_comm_finch: the whole hierarchy with the level-0 search shared by the ranks connected through `comm`
+        (every rank calls it with the same device matrix).  -> as finch_native."""
+        n, d = data.shape
+        cap = self.FINCH_CAPACITY
+        labels = torch.empty(n * cap, dtype=torch.int32, device=data.device)
+        num = (ctypes.c_int32 * cap)()
+        levels, has = ctypes.c_int32(0), ctypes.c_int32(0)
+        ms = ctypes.c_float(0)
+        _lib.call("slic_comm_finch", comm, _p(data), n, d, int(bool(ensure_early_exit)), cap, _p(labels),
+                  ctypes.addressof(num), ctypes.addressof(levels), ctypes.addressof(ms), ctypes.addressof(has), self._stream())
+        p = levels.value
+        return labels[: n * p].view(n, p), [int(v) for v in num[:p]], (np.float32(ms.value) if has.value else None)
+
     # -- rank-0-driven multi-GPU FINCH (csrc/comm.cu): one process, all GPUs of the box -------------------
     def enable_multi_gpu(self, devices=None, max_rows=1 << 21):
         """From now on finch_host() - i.e. FINCH(host matrix) - shares the level-0 search among `devices` (default:

@@ -160,6 +160,12 @@ def _finch_native(be, data, initial_rank, ensure_early_exit, first_neighbors):
         if nn0.shape[0] != n:
             raise ValueError("initial_rank must have one entry per row of data")
     elif first_neighbors is not None and n > 1:
+        comm = first_neighbors.native_comm(dev) if hasattr(first_neighbors, "native_comm") else None
+        if comm is not None:
+            # multi-GPU, one process per GPU: normalise + shared level-0 search + the rest of the hierarchy behind ONE
+            # call on every rank (csrc/comm.cu), no host synchronisation between the stages
+            c_dev, num_clust, _ = be.finch_native_comm(comm, dev, ensure_early_exit)
+            return be.to_host(c_dev), num_clust, dev
         nn0, dist0, unit0 = first_neighbors(dev)
         dense0 = n <= FLANN_THRESHOLD
     c_dev, num_clust, _ = be.finch_native(dev, nn0, dist0, unit0, dense0, ensure_early_exit)

@@ -447,6 +447,41 @@ int slic_comm_nn_top1(slic_comm_t* comm, const float* unit_dev, const uint16_t* 
                              status_out_dev + 1, st);
 }
 
+int slic_comm_finch(slic_comm_t* comm, const float* data_dev, int64_t n, int32_t d, int32_t ensure_early_exit,
+                    int32_t capacity, int32_t* labels_out_dev, int32_t* num_clust_out_host, int32_t* num_levels_out_host,
+                    float* min_sim_out_host, int32_t* has_min_sim_out_host, slic_stream_t stream) {
+    using namespace slic;
+    Comm* c = static_cast<Comm*>(comm);
+    SLIC_REQUIRE(c && !c->single && c->connected, "comm_finch: the group is not connected (slic_comm_connect)");
+    SLIC_REQUIRE(n > 1 && n < ((int64_t)1 << 31) && d > 0, "comm_finch: bad shape");
+    SLIC_REQUIRE(data_dev && labels_out_dev && num_clust_out_host && num_levels_out_host, "comm_finch: null pointer");
+    SLIC_REQUIRE(capacity >= 1, "comm_finch: the label buffer needs at least one column");
+    SLIC_PROPAGATE(slic_require_device());
+    int dev = -1;
+    SLIC_CUDA_OK(cudaGetDevice(&dev));
+    SLIC_REQUIRE(dev == c->device, "comm_finch: called on another device than the window lives on");
+    if (!screen_self_search_is_symmetric(n) || n > c->max_rows) {
+        set_error("comm_finch: the shared search takes 16384 <= n <= max_rows (%lld) rows", (long long)c->max_rows);
+        return SLIC_ERR_UNSUPPORTED;
+    }
+    cudaStream_t st = as_stream(stream);
+    const int dp = d_pad_of(d);
+    Scratch unit, ub, nn, dist, blk;
+    SLIC_CUDA_OK(unit.alloc((size_t)n * d * sizeof(float), st));
+    SLIC_CUDA_OK(ub.alloc((size_t)n * dp * 2, st));
+    SLIC_CUDA_OK(nn.alloc((size_t)n * sizeof(int), st));
+    SLIC_CUDA_OK(dist.alloc((size_t)n * sizeof(float), st));
+    SLIC_CUDA_OK(blk.alloc(16 * sizeof(int), st));
+    SLIC_CUDA_OK(cudaMemsetAsync(blk.ptr, 0, 16 * sizeof(int), st));
+    SLIC_PROPAGATE(slic_normalize_rows(data_dev, n, d, SLIC_F32, unit.ptr, nullptr, ub.as<uint16_t>(), dp, stream));
+    SLIC_PROPAGATE(comm_nn_top1_rank(c, c->rank, ++c->epoch, unit.as<float>(), ub.as<uint16_t>(), n, d, dp, nn.as<int>(),
+                                     dist.as<float>(), blk.as<int>() + 1, blk.as<int>() + 5, st));
+    // levels >= 1, components and means: replicated on every rank (milliseconds), so that every rank holds the labels
+    return finch_tail_device(data_dev, n, d, nn.as<int>(), dist.as<float>(), unit.as<float>(), ub.as<uint16_t>(),
+                             blk.as<int>(), ensure_early_exit != 0, capacity, labels_out_dev, num_clust_out_host,
+                             num_levels_out_host, min_sim_out_host, has_min_sim_out_host, st);
+}
+
 int slic_comm_create(const int32_t* devices, int32_t num_devices, int64_t max_rows, slic_comm_t** comm_out) {
     using namespace slic;
     SLIC_REQUIRE(devices && comm_out && num_devices >= 1 && num_devices <= COMM_MAX_RANKS,

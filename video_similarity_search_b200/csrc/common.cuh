@@ -118,6 +118,10 @@ int nn_top1_sym_fused(const float* unit, const uint16_t* ub, int64_t n, int d, i
 int finch_tail_to_host(const float* data, int64_t n, int d, int* nn, float* dist, const float* unit, const uint16_t* ub,
                        int* blk16, bool ensure_early_exit, int capacity, int* labels_out_host, int* num_clust_host,
                        int* num_levels_host, float* min_sim_host, int* has_min_sim_host, cudaStream_t st);
+// the same with the [n, capacity] label buffer on the device (every rank of a per-process group keeps its own copy)
+int finch_tail_device(const float* data, int64_t n, int d, int* nn, float* dist, const float* unit, const uint16_t* ub,
+                      int* blk16, bool ensure_early_exit, int capacity, int* labels_out_dev, int* num_clust_host,
+                      int* num_levels_host, float* min_sim_host, int* has_min_sim_host, cudaStream_t st);
 int finch_host_single(const float* x_host, int64_t n, int d, const int64_t* initial_rank_host, bool ensure_early_exit,
                       int capacity, int* labels_out_host, int* num_clust_host, int* num_levels_host, float* min_sim_host,
                       int* has_min_sim_host);

@@ -570,6 +570,23 @@ static int finch_host_impl(const float* x_host, int64_t n, int d, const int64_t*
 // device whose stream this is; labels go straight to the host.  blk16: the search's asynchronous status block
 // ([1] rows without a neighbour, [4] pipeline error, [5] incomplete) - when set, the search is repeated here on this
 // one device through the synchronous path before the hierarchy is built (nn / dist are then overwritten).
+int finch_tail_device(const float* data, int64_t n, int d, int* nn, float* dist, const float* unit, const uint16_t* ub,
+                      int* blk16, bool ensure_early_exit, int capacity, int* labels_out_dev, int* num_clust_host,
+                      int* num_levels_host, float* min_sim_host, int* has_min_sim_host, cudaStream_t st) {
+    Level0 l0;
+    l0.nn = nn;
+    l0.dist = dist;
+    l0.unit = unit;
+    l0.dense = n <= FLANN_THRESHOLD;
+    l0.async_stats = blk16;
+    l0.retry_ub = ub;
+    l0.retry_nn = nn;
+    l0.retry_dist = dist;
+    l0.no_self_links = true;
+    return finch_levels(data, n, d, l0, ensure_early_exit, capacity, labels_out_dev, num_clust_host, num_levels_host,
+                        min_sim_host, has_min_sim_host, st);
+}
+
 int finch_tail_to_host(const float* data, int64_t n, int d, int* nn, float* dist, const float* unit, const uint16_t* ub,
                        int* blk16, bool ensure_early_exit, int capacity, int* labels_out_host, int* num_clust_host,
                        int* num_levels_host, float* min_sim_host, int* has_min_sim_host, cudaStream_t st) {

@@ -110,6 +110,16 @@ def sharded_first_neighbors(be, group=None, timings=None, triangle=True, peer=Tr
         dist.all_gather_into_tensor(d_all, d_pad, group=group)
         return nn_all[:n].contiguous(), d_all[:n].contiguous(), unit
 
+    def native_comm(mat):
+        """The peer-window handle for a whole-hierarchy call (slic_comm_finch) on this matrix, or None when the shared
+        search does not apply (clustering/finch.py then falls back to search() + the single-GPU driver)."""
+        world = dist.get_world_size(group)
+        if (world > 1 and world <= 8 and triangle and peer and hasattr(be, "finch_native_comm")
+                and be.supports_triangle_parts(mat)):
+            return peer_group(mat.shape[0]).comm
+        return None
+
+    search.native_comm = native_comm
     return search
 
 
@@ -122,28 +132,71 @@ def close_peer_groups():
         _PEER_GROUPS.pop(key).close()
 
 
+UPLOAD_CHUNKS = 4   # host -> device copy of a rank's shard in this many pieces, each all-gathered while the next one is copied
+
+
 def upload_replicated(data, group=None, backend=None):
     """Host matrix held by EVERY rank -> full [N, D] float32 device matrix on every rank, with 1 / G of the PCIe
-    traffic per rank: rank r copies rows [r * ceil(N / G), ...) host -> device, then one all-gather over NVLink
-    assembles the matrix (the G ranks of a box share the host's memory and PCIe root, so G full uploads cost G times
-    the bytes over the same links).  Device-resident input is returned as it is."""
+    traffic per rank: rank r copies rows [r * ceil(N / G), ...) host -> device, and all-gathers over NVLink assemble the
+    matrix (the G ranks of a box share the host's memory and PCIe root, so G full uploads cost G times the bytes over
+    the same links).  The shard travels in UPLOAD_CHUNKS pieces: the all-gather of piece c runs while piece c + 1 is
+    still crossing PCIe (copy stream + current stream).  Device-resident input is returned as it is."""
     be = backend or _backend.default_backend()
     if isinstance(data, torch.Tensor) and data.device.type != "cpu":
         return be.to_device(data.detach(), torch.float32)
     host = data.detach() if isinstance(data, torch.Tensor) else torch.as_tensor(data)
     if not dist.is_initialized() or dist.get_world_size(group) == 1 or host.dim() != 2:
         return be.to_device(host, torch.float32)
+    if host.dtype != torch.float32:
+        host = host.to(torch.float32)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     n, d = host.shape
     r0, r1, per = shard_range(n, rank, world)
-    full = torch.empty((per * world, d), dtype=torch.float32, device=be.device)
-    mine = torch.empty((per, d), dtype=torch.float32, device=be.device)
-    if r1 > r0:
-        mine[: r1 - r0].copy_(host[r0:r1], non_blocking=True)
-    if r1 - r0 < per:
-        mine[r1 - r0:].zero_()                         # padding rows of the ragged last shards
-    dist.all_gather_into_tensor(full, mine, group=group)
-    return full[:n]
+    full = torch.empty((world, per, d), dtype=torch.float32, device=be.device)
+    on_gpu = full.device.type == "cuda"
+    chunks = UPLOAD_CHUNKS if (on_gpu and per >= 4096 * UPLOAD_CHUNKS) else 1
+    step = (per + chunks - 1) // chunks
+    main = torch.cuda.current_stream(be.device) if on_gpu else None
+    copier = _copy_stream(be.device) if on_gpu and chunks > 1 else None
+    if copier is not None:
+        copier.wait_stream(main)
+    for c in range(chunks):
+        c0, c1 = c * step, min(per, (c + 1) * step)
+        if c1 <= c0:
+            break
+        mine = full[rank, c0:c1]                          # this rank's piece lands in place
+        rows = max(0, min(r1 - r0, c1) - c0)              # real rows of the piece (the last shards may be ragged)
+        ctx = torch.cuda.stream(copier) if copier is not None else _nullcontext()
+        with ctx:
+            if rows > 0:
+                mine[:rows].copy_(host[r0 + c0:r0 + c0 + rows], non_blocking=True)
+            if rows < c1 - c0:
+                mine[rows:].zero_()                       # padding rows of the ragged last shards
+        if copier is not None:
+            main.wait_stream(copier)                      # (only the copies enqueued so far)
+        if chunks == 1:
+            dist.all_gather_into_tensor(full.view(world * per, d), mine.reshape(per, d), group=group)
+        else:
+            dist.all_gather([full[g, c0:c1] for g in range(world)], mine, group=group)
+    return full.view(world * per, d)[:n]
+
+
+_COPY_STREAMS = {}
+
+
+def _copy_stream(device):
+    key = str(device)
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _COPY_STREAMS[key]
+
+
+class _nullcontext:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
 
 
 def FINCH_sharded(data, group=None, backend=None, **kwargs):
