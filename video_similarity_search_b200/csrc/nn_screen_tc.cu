@@ -41,7 +41,24 @@
 
 namespace slic {
 
-constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_UMMA_K = 16;
+constexpr int TC_BM = 128, TC_BK = 64, TC_UMMA_K = 16;
+// Column-tile width.  WIDE (256, what every kernel runs): two 256-column accumulators in TMEM, every epilogue warp filters
+// one 128-column half of EVERY tile - the pair then advances at the pace of the slowest of its 16 epilogue warps on every
+// single tile (measured on the symmetric kernel at C3: MMA busy 66 %, epilogue warps busy 69 %, yet 6 019 cycles per tile
+// against 4 096 of MMA work).  NARROW (128; built, tested, NOT selected - SLIC_SCREEN_NARROW=1 builds a plan for it only in
+// the planner tests): FOUR 128-column accumulators, the epilogue warps in two groups that take ALTERNATE tiles, so that a
+// tile is released by the 8 warps of one group and the MMA issuer runs up to three tiles ahead.  Measured (round 2, C3):
+// the accumulator wait of the MMA issuer drops from 15 % to 5 % as intended, but the kernel takes 31.6 ms instead of 22.2:
+// with both operands in shared memory a tcgen05.mma M256 N128 K16 takes ~113 cycles against ~124 for N256 - the A
+// operand (4 KB per CTA and instruction) is re-read from shared memory by every instruction whatever N is, so halving N
+// halves the flops per instruction at the same cost.  A narrow tile needs A in TMEM, which the four accumulators fill.
+constexpr int TC_BN_WIDE = 256, TC_BN_NARROW = 128;
+// K slabs per ring stage of the A-resident kernels.  2 = three 32 KB stages, 8 MMAs per barrier round trip.  (1 = six 16 KB
+// stages was measured in round 2 at C3: operand wait of the MMA issuer 15 % -> 25 %, kernel 22.6 -> 24.1 ms: the finer
+// hand-over costs more in round trips than it gains in ring occupancy.)
+constexpr int TC_ARES_SPS = 2;
+constexpr bool TC_NARROW_ARES = false;   // (true: the A-resident kernels run on narrow tiles - the experiment above)
+constexpr int TC_ROW_UNIT = 256;   // rows of a CTA pair's unit (the symmetric planner counts row units and column tiles)
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
 // NCTA = 1: one CTA per 128 x 256 tile, it stages the whole 256-column B slab (32 KB).
 // NCTA = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) works on a 256 x 256 tile; each CTA stages its own 128
@@ -52,27 +69,33 @@ constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
 //           most of the L2 -> SM traffic that bounds the streaming variants.
 constexpr int TC_ARES_MAX_SLABS = 8;
 // barrier block behind the operands: 38 eight-byte slots (pipeline barriers, TMEM slot, log counters, unit ring)
-constexpr uint32_t TC_BAR_BYTES = 320;
+constexpr uint32_t TC_BAR_BYTES = 384;
 constexpr int TC_UQ_DEPTH = 4;   // unit ring: ids of the units the scheduler has handed out, consumed in order by every role
+constexpr int TC_TMEM_COLS = 512;
 template <int NCTA, bool ARES, bool TOPK> struct TcCfg {
-    static constexpr uint32_t B_ROWS = TC_BN / NCTA;
+    static constexpr int BN = (ARES && TC_NARROW_ARES) ? TC_BN_NARROW : TC_BN_WIDE;
+    static constexpr int ACCS = TC_TMEM_COLS / BN;          // accumulators in TMEM: 4 (narrow) or 2 (wide)
+    static constexpr bool GROUPED = BN == TC_BN_NARROW;     // epilogue warps in two groups that take alternate tiles
+    static constexpr uint32_t B_ROWS = BN / NCTA;
     static constexpr uint32_t B_BYTES = B_ROWS * TC_BK * 2;
     static constexpr uint32_t A_RES_BYTES = ARES ? TC_ARES_MAX_SLABS * TC_A_BYTES : 0;      // 128 KB
     // K slabs per ring stage: the A-resident top-1 kernel moves two (32 KB of B per CTA and barrier round trip,
     // 8 MMAs per wait / commit); the top-k variant has 32 KB less shared memory and keeps four single-slab stages
-    static constexpr int SPS = NCTA == 2 ? 2 : 1;
+    static constexpr int SPS = NCTA == 2 ? (ARES ? TC_ARES_SPS : 2) : 1;
     static constexpr uint32_t SLAB_BYTES = ARES ? B_BYTES : TC_A_BYTES + B_BYTES;   // one K slab of a stage
     static constexpr uint32_t STAGE_BYTES = SPS * SLAB_BYTES;
-    static constexpr int STAGES = ARES ? (TOPK ? 2 : 3) : (NCTA == 1 ? 4 : 3);
+    // A-resident: 96 KB (64 KB with the top-k histograms) of ring behind the 128 KB of A rows
+    static constexpr int STAGES = ARES ? (TOPK ? 64 : 96) * 1024 / (int)STAGE_BYTES : (NCTA == 1 ? 4 : 3);
+    static_assert(STAGES >= 2 && STAGES <= 6, "ring depth");
     static constexpr uint32_t OPERAND_BYTES = A_RES_BYTES + STAGES * STAGE_BYTES;            // 192 KB, ARES: 192 / 224 KB
     static constexpr uint32_t SMEM_BYTES = OPERAND_BYTES + TC_BAR_BYTES /*barriers, unit ring*/ + 960 /*alignment slack*/ +
                                            (TOPK ? 32768u : 0u) /*histograms*/;
-    // symmetric variant: + 1 KB of column thresholds (float16, rounded down); the A-resident layout then leaves 768
+    // symmetric variant: + 1 KB of column thresholds (float16, rounded down); the A-resident layout then leaves 640
     // bytes of alignment slack.  An SM has 228 KB of shared memory and every resident CTA reserves 1 KB of it: a
     // window above 226 KB would own the SM outright, and the kernels that feed a gated launch from another stream
     // (normalise, gate memset) could never become resident next to it - the launch would wait for itself.
     static constexpr uint32_t SYM_THR_BYTES = 2 * 2 * 128 * 2;   // [2 parities][2 halves][128 columns] float16
-    static constexpr uint32_t SYM_SMEM_BYTES = OPERAND_BYTES + TC_BAR_BYTES + SYM_THR_BYTES + (ARES ? 704u : 960u);
+    static constexpr uint32_t SYM_SMEM_BYTES = OPERAND_BYTES + TC_BAR_BYTES + SYM_THR_BYTES + (ARES ? 640u : 960u);
     static constexpr uint32_t CORESIDENT_MAX_BYTES = 233472 - 2 * 1024;
     static_assert(TOPK || SYM_SMEM_BYTES <= CORESIDENT_MAX_BYTES,
                   "symmetric variant leaves no shared memory for a co-resident CTA of the upload stream");
@@ -89,7 +112,6 @@ constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 // (Before: the first epilogue warp of each 128-column half wrote them and the half met at a named barrier per tile -
 // measured at 22 % of the epilogue's stall samples, profiles/r1_sym_screen_kernel_ncu_full.txt.)
 constexpr int TC_THREADS_SYM = TC_THREADS + 32;
-constexpr int TC_TMEM_COLS = 512;
 // Screen operands are IEEE half precision (float16: 11 significant bits; kind::f16 runs float16 and bfloat16 at the same
 // rate, and unit-vector components never leave float16's range).  Error allowance for unit rows: a component >= 2^-14
 // carries relative rounding error <= 2^-11, a product of two <= 2^-10 (+ 2^-22), so the sum over k is off by
@@ -479,10 +501,10 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
 }
 // kind::f16 instruction descriptor: D=f32 (bits 4-5 = 1), A=B=float16 (format fields at bits 7-9 and 10-12 = 0; 1 would
 // be bfloat16), both K-major, N >> 3 at bits 17-22, M >> 4 at bits 24-28.
-constexpr uint32_t TC_IDESC = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-
 // cta_group::2: the instruction spans both CTAs, M = 256
-constexpr uint32_t TC_IDESC_PAIR = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)((2 * TC_BM) >> 4) << 24);
+__host__ __device__ constexpr uint32_t tc_idesc(int bn, int ncta) {
+    return (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)((ncta * TC_BM) >> 4) << 24);
+}
 
 // ---- candidate list maintenance (slow path, rare) -------------------------------------------
 struct RowState {
@@ -849,16 +871,22 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OPERAND_BYTES);
     const uint32_t bar_full = smem_u32(bars);                              // [STAGES]  (pair: the leader's are used)
     const uint32_t bar_empty = smem_u32(bars + TC_MAX_STAGES);             // [STAGES]
-    const uint32_t bar_acc_full = smem_u32(bars + 2 * TC_MAX_STAGES);      // [2]
-    const uint32_t bar_acc_empty = smem_u32(bars + 2 * TC_MAX_STAGES + 2); // [2]      (pair: the leader's are used)
-    const uint32_t bar_a_full = smem_u32(bars + 2 * TC_MAX_STAGES + 4);    // ARES: resident A landed (leader's used)
-    const uint32_t bar_a_empty = smem_u32(bars + 2 * TC_MAX_STAGES + 5);   // ARES: the unit's MMAs retired
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 6);
-    const uint32_t bar_thr_full = smem_u32(bars + 24);    // SYM [2]: thresholds of a tile are in place (threshold warp)
-    const uint32_t bar_thr_empty = smem_u32(bars + 26);   // SYM [2]: the CTA's epilogue warps are done with them
-    const uint32_t bar_uq_full = smem_u32(bars + 28);     // [TC_UQ_DEPTH]: ring slot holds a unit id (own CTA's copy)
-    const uint32_t bar_uq_empty = smem_u32(bars + 32);    // [TC_UQ_DEPTH]: every role of the pair has read it (leader's used)
-    const uint32_t uq_val = smem_u32(bars + 36);          // [TC_UQ_DEPTH] int32 unit ids, -1 = no more units
+    constexpr int BN = Cfg::BN, ACCS = Cfg::ACCS;
+    constexpr bool GROUPED = Cfg::GROUPED;
+    // epilogue warps that read (and release) one tile: all eight (each a 128-column half), or the four of one group
+    constexpr int TILE_WARPS = GROUPED ? TC_EPI_WARPS / 2 : TC_EPI_WARPS;
+    const uint32_t bar_acc_full = smem_u32(bars + 12);    // [ACCS <= 4]
+    const uint32_t bar_acc_empty = smem_u32(bars + 16);   // [ACCS <= 4]  (pair: the leader's are used)
+    const uint32_t bar_a_full = smem_u32(bars + 20);      // ARES: resident A landed (leader's used)
+    const uint32_t bar_a_empty = smem_u32(bars + 21);     // ARES: the unit's MMAs retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+    // (slots 24-27: the epilogue warps' log counters, see s_logcnt)
+    const uint32_t bar_thr_full = smem_u32(bars + 28);    // SYM [4]: thresholds of a tile are in place (threshold warp)
+    const uint32_t bar_thr_empty = smem_u32(bars + 32);   // SYM [4]: the tile's epilogue warps of this CTA are done with them
+    const uint32_t bar_uq_full = smem_u32(bars + 36);     // [TC_UQ_DEPTH]: ring slot holds a unit id (own CTA's copy)
+    const uint32_t bar_uq_empty = smem_u32(bars + 40);    // [TC_UQ_DEPTH]: every role of the pair has read it (leader's used)
+    const uint32_t uq_val = smem_u32(bars + 44);          // [TC_UQ_DEPTH] int32 unit ids, -1 = no more units
+    static_assert(46 * 8 <= TC_BAR_BYTES && 2 * TC_MAX_STAGES <= 12, "barrier block layout");
     const uint32_t smem_base = smem_u32(smem);                 // ARES: resident A, slab ks at + ks * 16 KB
     const uint32_t ring_base = smem_base + Cfg::A_RES_BYTES;   // operand ring
 
@@ -873,9 +901,9 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
             mbar_init(bar_full + 8 * s, 1);    // the (leader's) producer's arrive.expect_tx
             mbar_init(bar_empty + 8 * s, 1);   // one tcgen05.commit
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < ACCS; ++a) {
             mbar_init(bar_acc_full + 8 * a, 1);
-            mbar_init(bar_acc_empty + 8 * a, TC_EPI_WARPS * NCTA);  // one arrive per epilogue warp of the pair
+            mbar_init(bar_acc_empty + 8 * a, TILE_WARPS * NCTA);  // one arrive per epilogue warp (of the pair) that reads the tile
         }
         mbar_init(bar_a_full, 1);
         mbar_init(bar_a_empty, 1);
@@ -885,9 +913,9 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
             mbar_init(bar_uq_empty + 8 * s, NCTA * (TC_EPI_WARPS + (SYM ? 1 : 0)) + 1 + (NCTA - 1));
         }
         if constexpr (SYM) {
-            for (int b = 0; b < 2; ++b) {
+            for (int b = 0; b < 4; ++b) {
                 mbar_init(bar_thr_full + 8 * b, 1);
-                mbar_init(bar_thr_empty + 8 * b, TC_EPI_WARPS);
+                mbar_init(bar_thr_empty + 8 * b, TILE_WARPS);
             }
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -911,7 +939,7 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
-    const int64_t n_col_tiles = (p.n + TC_BN - 1) / TC_BN;
+    const int64_t n_col_tiles = (p.n + BN - 1) / BN;
     UnitRing ring;
     ring.full = bar_uq_full;
     ring.val = uq_val;
@@ -976,7 +1004,7 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
                             if (cta_rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * (uint32_t)nsl * Cfg::B_BYTES);
                             for (int j = 0; j < nsl; ++j)
                                 tma_load_2d_pair(&tmap_x, b_dst + j * Cfg::SLAB_BYTES, bar_full + 8 * stage, (ks + j) * TC_BK,
-                                                 (int)(ct * TC_BN + cta_rank * Cfg::B_ROWS));
+                                                 (int)(ct * BN + cta_rank * Cfg::B_ROWS));
                         } else if constexpr (NCTA == 2) {
                             // both CTAs' bytes complete on the LEADER's full barrier
                             const int nsl = min(Cfg::SPS, p.num_k_slabs - ks);
@@ -985,12 +1013,12 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
                                 tma_load_2d_pair(&tmap_q, a_dst + j * Cfg::SLAB_BYTES, bar_full + 8 * stage, (ks + j) * TC_BK,
                                                  (int)(row_block * TC_BM));
                                 tma_load_2d_pair(&tmap_x, b_dst + j * Cfg::SLAB_BYTES, bar_full + 8 * stage, (ks + j) * TC_BK,
-                                                 (int)(ct * TC_BN + cta_rank * Cfg::B_ROWS));
+                                                 (int)(ct * BN + cta_rank * Cfg::B_ROWS));
                             }
                         } else {
                             mbar_expect_tx(bar_full + 8 * stage, Cfg::STAGE_BYTES);
                             tma_load_2d(&tmap_q, a_dst, bar_full + 8 * stage, ks * TC_BK, (int)(row_block * TC_BM));
-                            tma_load_2d(&tmap_x, b_dst, bar_full + 8 * stage, ks * TC_BK, (int)(ct * TC_BN));
+                            tma_load_2d(&tmap_x, b_dst, bar_full + 8 * stage, ks * TC_BK, (int)(ct * BN));
                         }
                         if (++stage == STAGES) {
                             stage = 0;
@@ -1026,7 +1054,7 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
                 for (int kt = 0; kt < n_tiles; ++kt) {
                     mbar_wait_traced(bar_acc_empty + 8 * acc, acc_phase ^ 1, p.error_flag, t_acc, tracing);
                     tc_fence_after();
-                    const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TC_BN);
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
                     for (int ks = 0; ks < p.num_k_slabs; ks += Cfg::SPS) {
                         mbar_wait_traced(bar_full + 8 * stage, phase, p.error_flag, t_smem, tracing);
                         tc_fence_after();
@@ -1041,10 +1069,10 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
                                 for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
                                     // advancing 16 f16 = 32 bytes along K inside the swizzle atom: +2 in the address field
                                     if constexpr (NCTA == 2)
-                                        umma_f16_pair(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), TC_IDESC_PAIR,
+                                        umma_f16_pair(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), tc_idesc(BN, 2),
                                                        (uint32_t)((ks | j | k) != 0));
                                     else
-                                        umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), TC_IDESC,
+                                        umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), tc_idesc(BN, 1),
                                                   (uint32_t)((ks | j | k) != 0));
                                 }
                             }
@@ -1060,8 +1088,10 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
                     // accumulator complete -> epilogue (of both CTAs)
                     if constexpr (NCTA == 2) umma_commit_pair(bar_acc_full + 8 * acc);
                     else umma_commit(bar_acc_full + 8 * acc);
-                    acc ^= 1;
-                    if (acc == 0) acc_phase ^= 1;
+                    if (++acc == ACCS) {
+                        acc = 0;
+                        acc_phase ^= 1;
+                    }
                 }
                 if constexpr (ARES) umma_commit_pair(bar_a_empty);   // the resident A rows may be replaced (both CTAs)
             }
@@ -1078,36 +1108,48 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
         // For every tile strictly right of the diagonal (the epilogue's "column role"): threshold of column c =
         // best score published for row c so far - eps, as float16 rounded DOWN (a lower threshold only adds candidates;
         // 2^-11 against eps = 2^-7), with a finite lower bound (threshold - masked score = +inf, never NaN).
-        uint16_t* thr_buf = reinterpret_cast<uint16_t*>(smem + Cfg::OPERAND_BYTES + TC_BAR_BYTES);   // [2 buffers][2 halves][128]
+        // Buffers (1 KB in all): wide tiles - 2 x [256 columns], consumed by all eight epilogue warps of the CTA; narrow
+        // tiles - per epilogue group 2 x [128 columns], consumed by the group's four warps.  `tile_seq` counts EVERY tile the
+        // pair processes (it decides which group takes a narrow tile), cseq[g] the column-role tiles of group g.
+        uint16_t* thr_buf = reinterpret_cast<uint16_t*>(smem + Cfg::OPERAND_BYTES + TC_BAR_BYTES);
         constexpr unsigned ENC_POS_INF = 0xff800000u;
-        unsigned seq = 0;
+        constexpr int PER_LANE = BN / 32;
+        constexpr int DIAG_TILES = TC_ROW_UNIT / BN;   // column tiles that make up a row unit's diagonal block
+        unsigned tile_seq = 0, cseq0 = 0u, cseq1 = 0u;   // (two scalars: an indexed array would live in local memory)
         for (int u; (u = ring_take(ring, true, p.error_flag)) >= 0;) {
             const UnitInfo ui = unit_info(p, u, n_col_tiles);
-            if (!ui.coldir) continue;
+            if (!ui.coldir) {
+                tile_seq += (unsigned)ui.count;
+                continue;
+            }
             if (p.sync_counter) {   // published bests of the pre-pass are in place (speed only, as for the epilogue)
                 if (lane == 0) counter_wait(p.sync_counter, __ldg(p.sync_targets + ui.gate + 1), p.error_flag);
                 __syncwarp();
             }
-            for (int kt = 0; kt < ui.count; ++kt) {
+            for (int kt = 0; kt < ui.count; ++kt, ++tile_seq) {
                 const int64_t ct = ui.ct0 + (int64_t)kt * ui.stride;
-                if (ct == ui.row_unit) continue;
-                const uint32_t buf = seq & 1u, ph = (seq >> 1) & 1u;
-                unsigned e[8];   // fetched first: the L2 round trip overlaps the wait for the buffer
+                if (ct / DIAG_TILES == ui.row_unit) continue;
+                const int grp = GROUPED ? (int)(tile_seq & 1u) : 0;
+                const unsigned cs = grp ? cseq1 : cseq0;
+                const uint32_t buf = cs & 1u, ph = (cs >> 1) & 1u;
+                const uint32_t bi = (uint32_t)grp * 2u + buf;   // barrier / buffer index
+                unsigned e[PER_LANE];   // fetched first: the L2 round trip overlaps the wait for the buffer
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int64_t c = ct * TC_BN + lane + 32 * j;
+                for (int j = 0; j < PER_LANE; ++j) {
+                    const int64_t c = ct * BN + lane + 32 * j;
                     e[j] = c < p.n ? __ldcg(p.best_enc + c) : ENC_POS_INF;
                 }
-                mbar_wait(bar_thr_empty + 8 * buf, ph ^ 1u, p.error_flag);
-                const uint32_t ta = smem_u32(thr_buf + buf * 256) + 2u * lane;
+                mbar_wait(bar_thr_empty + 8 * bi, ph ^ 1u, p.error_flag);
+                const uint32_t ta = smem_u32(thr_buf + (GROUPED ? bi * 128u : buf * 256u)) + 2u * lane;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < PER_LANE; ++j) {
                     const unsigned short t = __half_as_ushort(__float2half_rd(fmaxf(dec_score(e[j]) - p.eps, -60000.f)));
                     asm volatile("st.shared.b16 [%0], %1;" ::"r"(ta + 64u * j), "h"(t) : "memory");
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_thr_full + 8 * buf);
-                ++seq;
+                if (lane == 0) mbar_arrive(bar_thr_full + 8 * bi);
+                if (grp) ++cseq1;
+                else ++cseq0;
             }
         }
     } else {
@@ -1115,10 +1157,13 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
         // Warp w reads TMEM lanes [32 * (w % 4), +32) (the hardware's lane window of that warp) and the 128-column
         // half (w - 2) / 4 of every tile: one thread = one (query row, column half) stream with its own list.
         const int quad = warp & 3;
+        // wide tiles: the warp's 128-column half of EVERY tile; narrow tiles: the warp's GROUP - it takes the tiles whose
+        // sequence number (over everything the pair processes, all units) has this parity, all 128 columns of them.
+        // Either way one thread = one (query row, stream) with its own candidate list, 128 columns per tile it takes.
         const int half = (warp - 2) >> 2;
         const int row_in_tile = quad * 32 + lane;
-        int acc = 0;
-        uint32_t acc_phase = 0;
+        unsigned seq_all = 0;   // tiles the pair has been through; accumulator of tile s: s % ACCS, barrier phase (s / ACCS) & 1
+        constexpr unsigned TILE_STEP = GROUPED ? 2u : 1u;   // distance to this warp's next tile
         unsigned long long t_full = 0;
         const long long t_begin = tracing ? clock64() : 0;
         EpiCtx<TOPK> cx;
@@ -1127,9 +1172,9 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
         cx.n_trig = 0;
         cx.n_chunks = 0;
         if constexpr (TOPK) cx.hist = smem + Cfg::OPERAND_BYTES + TC_BAR_BYTES + half * TC_BM + row_in_tile;
-        unsigned int* s_logcnt = reinterpret_cast<unsigned int*>(bars + 20) + (warp - 2);   // spare bytes of the barrier block
-        uint16_t* thr_buf = reinterpret_cast<uint16_t*>(smem + Cfg::OPERAND_BYTES + TC_BAR_BYTES);   // SYM: float16 [2 parities][2 halves][128]
-        unsigned tile_seq = 0;
+        unsigned int* s_logcnt = reinterpret_cast<unsigned int*>(bars + 24) + (warp - 2);   // slots 24-27 of the barrier block
+        uint16_t* thr_buf = reinterpret_cast<uint16_t*>(smem + Cfg::OPERAND_BYTES + TC_BAR_BYTES);   // SYM: float16 column thresholds
+        unsigned tile_seq = 0;   // SYM: column-role tiles this warp has taken (wide: of all tiles; narrow: of its group's)
         const int64_t log_region_id = (int64_t)blockIdx.x * TC_EPI_WARPS + (warp - 2);
         if constexpr (SYM) {
             if (lane == 0) *s_logcnt = 0u;
@@ -1182,21 +1227,26 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
             cx.st.flags = 0;
             uint32_t va[32], vb[32];
             bool prefetched = false;   // va holds an in-flight load of the coming tile's first chunk
-            for (int kt = 0; kt < ui.count; ++kt) {
+            bool first = true;         // no tile of this unit taken yet
+            for (int kt = 0; kt < ui.count; ++kt, ++seq_all) {
+                if (GROUPED && (int)(seq_all & 1u) != half) continue;   // the other group's tile
+                const int acc = (int)(seq_all % (unsigned)ACCS);
+                const uint32_t acc_phase = (seq_all / (unsigned)ACCS) & 1u;
                 const int64_t ct = ui.ct0 + (int64_t)kt * ui.stride;
-                const int64_t col0 = ct * TC_BN + half * 128;
+                const int64_t col0 = GROUPED ? ct * BN : ct * BN + half * 128;
                 // SYM: tiles strictly right of the diagonal also serve their columns as queries; their thresholds come from
                 // the threshold warp through shared memory
                 bool cdir = false;
                 uint32_t thr_tile = 0u;   // shared-memory address of this tile's 128 column thresholds
                 uint32_t thr_done_bar = 0u;
                 if constexpr (SYM) {
-                    cdir = ui.coldir && ct != ui.row_unit;
+                    cdir = ui.coldir && ct / (TC_ROW_UNIT / BN) != ui.row_unit;
                     if (cdir) {   // the threshold warp runs two tiles ahead: this wait is normally a single poll
                         const uint32_t buf = tile_seq & 1u, ph = (tile_seq >> 1) & 1u;
-                        thr_tile = smem_u32(thr_buf + (buf * 2 + half) * 128);
-                        thr_done_bar = bar_thr_empty + 8 * buf;
-                        mbar_wait(bar_thr_full + 8 * buf, ph, p.error_flag);
+                        const uint32_t bi = GROUPED ? (uint32_t)half * 2u + buf : buf;   // barrier index (see the threshold warp)
+                        thr_tile = smem_u32(thr_buf + (GROUPED ? bi : buf * 2 + half) * 128);
+                        thr_done_bar = bar_thr_empty + 8 * bi;
+                        mbar_wait(bar_thr_full + 8 * bi, ph, p.error_flag);
                         ++tile_seq;
                     }
                 }
@@ -1206,10 +1256,10 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
                     mbar_wait_traced(bar_acc_full + 8 * acc, acc_phase, p.error_flag, t_full, tracing);
                     tc_fence_after();
                 }
-                const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_BN + half * 128);
+                const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + (GROUPED ? 0 : half * 128));
                 if constexpr (TOPK) {
-                    cx.count = kt != 0;
-                    if (kt == 0) {
+                    cx.count = !first;
+                    if (first) {
                         // bootstrap: count every column of the stream's first 128 (uniform control flow, nothing is
                         // listed), which yields the first threshold; the columns are then read again below
 #pragma unroll 1
@@ -1250,8 +1300,6 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
                                 if constexpr (NCTA == 2) mbar_arrive_leader(bar_acc_empty + 8 * acc);
                                 else mbar_arrive(bar_acc_empty + 8 * acc);
                             }
-                            acc ^= 1;
-                            if (acc == 0) acc_phase ^= 1;
                         }
                         epi_chunk<TOPK, false>(cx, va, col0 + 32 * c, plain);
                     }
@@ -1275,17 +1323,18 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
                                 if constexpr (NCTA == 2) mbar_arrive_leader(bar_acc_empty + 8 * acc);
                                 else mbar_arrive(bar_acc_empty + 8 * acc);
                             }
-                            acc ^= 1;
-                            if (acc == 0) acc_phase ^= 1;
-                            // Cross-tile prefetch: if the unit's NEXT tile is already complete in the other accumulator, start
-                            // reading its first chunk now, so that the load's latency (queueing behind the other seven warps on
+                            // Cross-tile prefetch: if this warp's NEXT tile of the unit is already complete in its accumulator,
+                            // start reading its first chunk now, so that the load's latency (queueing behind the other warps on
                             // the TMEM read port) hides behind the filter of this tile's last chunk instead of being exposed at
                             // every tile boundary.  One poll, warp-uniform decision; a miss falls back to the blocking wait.
-                            if (kt + 1 < ui.count) {
-                                const bool ready = __all_sync(0xffffffffu, mbar_test(bar_acc_full + 8 * acc, acc_phase));
+                            if (kt + (int)TILE_STEP < ui.count) {
+                                const unsigned nxt = seq_all + TILE_STEP;
+                                const int acc_n = (int)(nxt % (unsigned)ACCS);
+                                const bool ready = __all_sync(0xffffffffu, mbar_test(bar_acc_full + 8 * acc_n, (nxt / (unsigned)ACCS) & 1u));
                                 if (ready) {
                                     tc_fence_after();
-                                    tmem_ld_issue(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_BN + half * 128), va);
+                                    tmem_ld_issue(tmem_base + ((uint32_t)(quad * 32) << 16) +
+                                                      (uint32_t)(acc_n * BN + (GROUPED ? 0 : half * 128)), va);
                                     prefetched = true;
                                 }
                             }
@@ -1301,8 +1350,9 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
                 }
                 if constexpr (TOPK) {
                     // parked columns of the first tile must be listed before columns start being counted
-                    if (kt == 0) pend_flush(cx.pd, cx.st, p.eps, p.cap, p.topk, false, cx.hist, cx.li, cx.ls);
+                    if (first) pend_flush(cx.pd, cx.st, p.eps, p.cap, p.topk, false, cx.hist, cx.li, cx.ls);
                 }
+                first = false;
             }
             if constexpr (TOPK) pend_flush(cx.pd, cx.st, p.eps, p.cap, p.topk, true, cx.hist, cx.li, cx.ls);
             if constexpr (SYM) {
@@ -1634,13 +1684,20 @@ static bool screen_ares_allowed() {
     return cached != 0;
 }
 
-static ScreenPlan plan_screen(int64_t nq, int64_t n) {
+// column-tile width of the kernel a search with this operand width runs on (TcCfg::BN: narrow for the A-resident kernels)
+static int screen_bn(int d_pad) {
+    return (TC_NARROW_ARES && screen_ncta() == 2 && d_pad / TC_BK <= TC_ARES_MAX_SLABS && screen_ares_allowed()) ? TC_BN_NARROW
+                                                                                                                  : TC_BN_WIDE;
+}
+
+static ScreenPlan plan_screen(int64_t nq, int64_t n, int bn) {
     const int ncta = screen_ncta();
-    const int64_t row_blocks = ceil_div(nq, TC_BM * ncta), col_tiles = ceil_div(n, TC_BN);
+    const int64_t row_blocks = ceil_div(nq, TC_BM * ncta), col_tiles = ceil_div(n, bn);
     const int64_t sms = num_sms() / ncta;
-    // enough units for >= ~6 waves when the problem allows it, but keep >= 8 tiles per unit
+    // enough units for >= ~6 waves when the problem allows it, but keep >= 2048 columns (8 wide tiles) per unit
     int64_t want = ceil_div(6 * sms, row_blocks);
-    int64_t max_splits = col_tiles / 8 > 0 ? col_tiles / 8 : 1;
+    const int64_t min_tiles = 8 * (TC_BN_WIDE / bn);
+    int64_t max_splits = col_tiles / min_tiles > 0 ? col_tiles / min_tiles : 1;
     int64_t splits = want < 1 ? 1 : (want > max_splits ? max_splits : want);
     ScreenPlan pl;
     pl.tiles_per_split = (int)ceil_div(col_tiles, splits);
@@ -1652,14 +1709,14 @@ static ScreenPlan plan_screen(int64_t nq, int64_t n) {
 // Top-k variant: every unit restarts with an empty threshold (its first tile is listed in full and the
 // threshold then tightens like k / columns seen), so units should be as long as the wave structure allows:
 // minimise waves x (tiles per unit + start-up cost in tile times).
-static ScreenPlan plan_screen_topk(int64_t nq, int64_t n, int k) {
+static ScreenPlan plan_screen_topk(int64_t nq, int64_t n, int k, int bn) {
     const int ncta = screen_ncta();
-    const int64_t row_blocks = ceil_div(nq, TC_BM * ncta), col_tiles = ceil_div(n, TC_BN);
+    const int64_t row_blocks = ceil_div(nq, TC_BM * ncta), col_tiles = ceil_div(n, bn);
     const int64_t sms = num_sms() / ncta;
-    const int64_t startup = 6;   // bootstrap pass + threshold ramp of a unit, in tile times
+    const int64_t startup = 6 * (TC_BN_WIDE / bn);   // bootstrap pass + threshold ramp of a unit, in tile times
     int64_t best_s = 1, best_cost = INT64_MAX;
     // a stream (half of a unit's tiles) should see >= ~32 k columns, or its own k-th best says little about the row's
-    const int64_t min_tps = ceil_div((int64_t)32 * k, TC_BN / 2);
+    const int64_t min_tps = ceil_div((int64_t)32 * k, bn / 2);
     // (two passes: the cheapest plan, then the FEWEST splits within 2 % of it - every split is one more pair of candidate
     //  streams per row, each restarting from an empty threshold: measured on 100 000 x 1 000 000 x 1 024, k = 50, 7 splits
     //  of 559 tiles against 3 of 1 303 - equal in this model - run the screen at 0.56 against 0.70 of the tensor peak)
@@ -1751,7 +1808,8 @@ static int launch_screen(const uint16_t* q_f16, int64_t nq, const uint16_t* x_f1
     if (gates) SLIC_PROPAGATE(arm_timeout_record());
     CUtensorMap tq, tx;
     SLIC_PROPAGATE(make_tmap(&tq, q_f16, nq, d_pad, TC_BM));
-    SLIC_PROPAGATE(make_tmap(&tx, x_f16, n, d_pad, TC_BN / ncta));
+    const int bn = screen_bn(d_pad);
+    SLIC_PROPAGATE(make_tmap(&tx, x_f16, n, d_pad, bn / ncta));
     ScreenParams p;
     p.nq = nq;
     p.n = n;
@@ -1846,7 +1904,7 @@ static int launch_screen(const uint16_t* q_f16, int64_t nq, const uint16_t* x_f1
     if (g_profile) {
         SLIC_CUDA_OK(cudaEventRecord(g_ev_stop, st));
         g_last_flop = 2.0 * (double)nq * (double)n * (double)d_pad;
-        g_last_exec_flop = exec_tiles > 0 ? 2.0 * (double)exec_tiles * TC_BN * TC_BN * (double)d_pad : g_last_flop;
+        g_last_exec_flop = exec_tiles > 0 ? 2.0 * (double)exec_tiles * (TC_BM * ncta) * bn * (double)d_pad : g_last_flop;
         g_have_sample = true;
     }
     return SLIC_OK;
@@ -1922,18 +1980,23 @@ constexpr int SYM_SAMPLE_TILES = 16;
 //                     arrivals of ALL ranks (*prepass_units_all = their number over all parts)
 enum SymMode { SYM_FULL = 0, SYM_BESTS = 1, SYM_TRIANGLE = 2, SYM_FUSED = 3 };
 constexpr int SYM_FUSED_PRE_TILES = 16;   // fused pre-pass: a row unit's sample is cut into units of this many tiles (balance)
-static int plan_screen_sym(int64_t n, int part, int parts, const GateSpec* g, ScreenPlan* pl, std::vector<int4>* table,
-                           SymMode mode = SYM_FULL, int64_t* prepass_units_all = nullptr) {
+static int plan_screen_sym(int64_t n, int bn, int part, int parts, const GateSpec* g, ScreenPlan* pl,
+                           std::vector<int4>* table, SymMode mode = SYM_FULL, int64_t* prepass_units_all = nullptr) {
     const bool own_rows_prepass = mode == SYM_BESTS || mode == SYM_FUSED;
-    const int64_t T = ceil_div(n, TC_BN);
-    SLIC_REQUIRE(T < 65536, "symmetric screen: more than 16.7 M rows");
+    // R row units of 256 rows (a CTA pair's rows), T column tiles of bn columns, tpr = column tiles per row unit: the
+    // diagonal block of row unit r is made of column tiles [r * tpr, (r + 1) * tpr) and is filtered along rows only
+    const int tpr = TC_ROW_UNIT / bn;
+    const int64_t R = ceil_div(n, TC_ROW_UNIT), T = ceil_div(n, bn);
+    SLIC_REQUIRE(T < 65536, "symmetric screen: too many column tiles");
     SLIC_REQUIRE(parts >= 1 && part >= 0 && part < parts, "symmetric screen: bad partition");
-    int64_t chunk_tiles_gate = 0;
+    int64_t chunk_tiles_gate = 0, chunk_units_gate = 0;
     if (g) {
-        SLIC_REQUIRE(g->gates && g->num_chunks >= 1 && g->num_chunks < 4095 && g->chunk_rows > 0 && g->chunk_rows % TC_BN == 0,
+        SLIC_REQUIRE(g->gates && g->num_chunks >= 1 && g->num_chunks < 4095 && g->chunk_rows > 0 &&
+                         g->chunk_rows % TC_ROW_UNIT == 0,
                      "gated screen: chunk_rows must be a positive multiple of 256");
         SLIC_REQUIRE(ceil_div(n, g->chunk_rows) == g->num_chunks, "gated screen: chunks do not tile the database");
-        chunk_tiles_gate = g->chunk_rows / TC_BN;
+        chunk_tiles_gate = g->chunk_rows / bn;
+        chunk_units_gate = g->chunk_rows / TC_ROW_UNIT;
     }
     static int nocol = -1;   // experiments: SLIC_SYM_NOCOL=1 (wrong results, timing only)
     if (nocol < 0) {
@@ -1941,28 +2004,31 @@ static int plan_screen_sym(int64_t n, int part, int parts, const GateSpec* g, Sc
         nocol = f && atoi(f) == 1 ? 1 : 0;
     }
     table->clear();
-    // pre-pass sample: tiles spread over the whole matrix, or over the first upload chunk when the rest is in flight
+    // pre-pass sample: tiles spread over the whole matrix, or over the first upload chunk when the rest is in flight.
+    // Sample sizes are stated in 256-column blocks (the numbers below were measured with wide tiles) and converted.
     const int64_t span = g ? (chunk_tiles_gate < T ? chunk_tiles_gate : T) : T;
-    // SYM_BESTS: every part pays a warm-up of loose thresholds at the start of its (short) share of the triangle, so a
-    // stronger sample pays off from 4 parts on (measured at 8 parts, C3: 16 / 32 / 64 tiles -> 3.96 / 3.64 / 3.30 ms for
-    // the triangle share against +0.1 ms per 16 tiles here)
-    int samples = own_rows_prepass ? (parts >= 4 ? 4 * SYM_SAMPLE_TILES : SYM_SAMPLE_TILES) : SYM_SAMPLE_TILES / parts;
-    if (own_rows_prepass && samples > span / 4) samples = (int)(span / 4);   // small inputs: a sample, not the whole square
+    const int64_t span_w = span / tpr > 0 ? span / tpr : 1;
+    // SYM_BESTS / SYM_FUSED: every part pays a warm-up of loose thresholds at the start of its (short) share of the
+    // triangle, so a stronger sample pays off from 4 parts on (measured at 8 parts, C3: 16 / 32 / 64 blocks -> 3.96 / 3.64
+    // / 3.30 ms for the triangle share against +0.1 ms per 16 blocks here)
+    int samples_w = own_rows_prepass ? (parts >= 4 ? 4 * SYM_SAMPLE_TILES : SYM_SAMPLE_TILES) : SYM_SAMPLE_TILES / parts;
+    if (own_rows_prepass && samples_w > span_w / 4) samples_w = (int)(span_w / 4);   // small inputs: a sample, not the whole square
     // small inputs (a hierarchy's level 1): the pre-pass must stay a sample - measured at 21 436 x 512 float64 centroids:
-    // 16 / 10 / 4 sample tiles -> 0.88 / 0.79 / 0.72 ms for the whole search
-    if (mode == SYM_FULL && T < 128 && samples > T / 16) samples = (int)(T / 16);
-    if (samples < 4) samples = 4;
+    // 16 / 10 / 4 sample blocks -> 0.88 / 0.79 / 0.72 ms for the whole search
+    if (mode == SYM_FULL && R < 128 && samples_w > R / 16) samples_w = (int)(R / 16);
+    if (samples_w < 4) samples_w = 4;
     if (const char* e = getenv("SLIC_SYM_SAMPLES")) {   // experiments only
         const int v = atoi(e);
-        if (v >= 1 && v <= 64) samples = v;
+        if (v >= 1 && v <= 64) samples_w = v;
     }
+    int samples = samples_w * tpr;
     if (samples > span) samples = (int)span;
     const int stride = (int)(span / samples);
-    const int64_t pre0 = own_rows_prepass ? T * part / parts : 0, pre1 = own_rows_prepass ? T * (part + 1) / parts : T;
-    const int pre_len = mode == SYM_FUSED ? SYM_FUSED_PRE_TILES : samples;
-    if (prepass_units_all) *prepass_units_all = T * ceil_div(samples, pre_len);
+    const int64_t pre0 = own_rows_prepass ? R * part / parts : 0, pre1 = own_rows_prepass ? R * (part + 1) / parts : R;
+    const int pre_len = mode == SYM_FUSED ? SYM_FUSED_PRE_TILES * tpr : samples;
+    if (prepass_units_all) *prepass_units_all = R * ceil_div(samples, pre_len);
     for (int64_t r = pre0; r < pre1 && mode != SYM_TRIANGLE; ++r) {
-        const int gate = g ? (int)(r / chunk_tiles_gate) : -1;
+        const int gate = g ? (int)(r / chunk_units_gate) : -1;
         for (int s0 = 0; s0 < samples; s0 += pre_len)
             table->push_back(unit_entry(r, (int64_t)s0 * stride, samples - s0 < pre_len ? samples - s0 : pre_len, stride, gate, 0,
                                         false));
@@ -1970,27 +2036,28 @@ static int plan_screen_sym(int64_t n, int part, int parts, const GateSpec* g, Sc
     // part / parts: a CONTIGUOUS range of the chunk-major unit list holding 1 / parts of the triangle's tiles.  (Dealing
     // the units round-robin was measured at 8 ranks: a rank's 74 concurrent CTA pairs then span ~9 column chunks, the B
     // tiles are no longer shared through L2 and the kernel runs at half speed.)
+    const int64_t chunk_tiles = (int64_t)SYM_CHUNK_TILES * tpr;   // 16 384 columns = 16 MB of f16 B rows at d_pad 512
     int64_t total_tiles = 0;
-    for (int64_t c0 = 0; c0 < T; c0 += SYM_CHUNK_TILES) {
-        const int64_t c1 = c0 + SYM_CHUNK_TILES < T ? c0 + SYM_CHUNK_TILES : T;
-        for (int64_t r = 0; r < c1; ++r) total_tiles += c1 - (r > c0 ? r : c0);
+    for (int64_t c0 = 0; c0 < T; c0 += chunk_tiles) {
+        const int64_t c1 = c0 + chunk_tiles < T ? c0 + chunk_tiles : T;
+        for (int64_t r = 0; r * tpr < c1; ++r) total_tiles += c1 - (r * tpr > c0 ? r * tpr : c0);
     }
     // Unit length: units are handed out dynamically (p.queue), so the last ones to finish leave at most one unit of
-    // idle time per CTA pair - keep a unit well below a pair's share of the work (level 1 of a hierarchy has ~60 tiles per
-    // pair in total), but long enough to amortise the reload of the resident A rows (one tile's worth of traffic).
+    // idle time per CTA pair - keep a unit well below a pair's share of the work (level 1 of a hierarchy has ~60 blocks per
+    // pair in total), but long enough to amortise the reload of the resident A rows (one block's worth of traffic).
     const int64_t pairs = num_sms() / 2 > 0 ? num_sms() / 2 : 1;
     int64_t unit_len = total_tiles / parts / (pairs * 12);
-    unit_len = unit_len < 8 ? 8 : (unit_len > SYM_CHUNK_TILES ? SYM_CHUNK_TILES : unit_len);
-    if (const char* e = getenv("SLIC_SYM_UNIT_TILES")) {   // experiments only
+    unit_len = unit_len < 8 * tpr ? 8 * tpr : (unit_len > chunk_tiles ? chunk_tiles : unit_len);
+    if (const char* e = getenv("SLIC_SYM_UNIT_TILES")) {   // experiments only (in 256-column blocks)
         const int v = atoi(e);
-        if (v >= 1 && v <= SYM_CHUNK_TILES) unit_len = v;
+        if (v >= 1 && v <= SYM_CHUNK_TILES) unit_len = (int64_t)v * tpr;
     }
     int64_t seen_tiles = 0;
-    for (int64_t c0 = 0; c0 < T && mode != SYM_BESTS; c0 += SYM_CHUNK_TILES) {
-        const int64_t c1 = c0 + SYM_CHUNK_TILES < T ? c0 + SYM_CHUNK_TILES : T;
-        for (int64_t r = 0; r < c1; ++r) {
+    for (int64_t c0 = 0; c0 < T && mode != SYM_BESTS; c0 += chunk_tiles) {
+        const int64_t c1 = c0 + chunk_tiles < T ? c0 + chunk_tiles : T;
+        for (int64_t r = 0; r * tpr < c1; ++r) {
             const int gate = g ? (int)((c1 - 1) / chunk_tiles_gate) : -1;   // column chunk >= row chunk
-            for (int64_t ct0 = r > c0 ? r : c0; ct0 < c1; ct0 += unit_len) {
+            for (int64_t ct0 = r * tpr > c0 ? r * tpr : c0; ct0 < c1; ct0 += unit_len) {
                 const int64_t cnt = c1 - ct0 < unit_len ? c1 - ct0 : unit_len;
                 const int64_t owner = seen_tiles * parts / total_tiles;   // < parts: seen_tiles < total_tiles here
                 seen_tiles += cnt;
@@ -2007,16 +2074,16 @@ static int plan_screen_sym(int64_t n, int part, int parts, const GateSpec* g, Sc
     return SLIC_OK;
 }
 
-static int plan_screen_gated(int64_t nq, int64_t n, int64_t self_offset, const GateSpec& g, ScreenPlan* pl,
+static int plan_screen_gated(int64_t nq, int64_t n, int bn, int64_t self_offset, const GateSpec& g, ScreenPlan* pl,
                              std::vector<int4>* table) {
     const int ncta = screen_ncta();
     const int64_t rows_per_unit = (int64_t)TC_BM * ncta;
-    SLIC_REQUIRE(g.gates && g.num_chunks >= 1 && g.num_chunks < 32768 && g.chunk_rows > 0 && g.chunk_rows % TC_BN == 0,
+    SLIC_REQUIRE(g.gates && g.num_chunks >= 1 && g.num_chunks < 32768 && g.chunk_rows > 0 && g.chunk_rows % TC_ROW_UNIT == 0,
                  "gated screen: chunk_rows must be a positive multiple of 256");
     SLIC_REQUIRE(ceil_div(n, g.chunk_rows) == g.num_chunks, "gated screen: chunks do not tile the database");
     SLIC_REQUIRE(self_offset >= 0 && self_offset + nq <= n, "gated screen: queries must be database rows");
     const int64_t row_units = ceil_div(nq, rows_per_unit);
-    pl->tiles_per_split = (int)(g.chunk_rows / TC_BN);
+    pl->tiles_per_split = (int)(g.chunk_rows / bn);
     pl->splits = g.num_chunks;
     pl->units = row_units * pl->splits;
     table->clear();
@@ -2030,7 +2097,7 @@ static int plan_screen_gated(int64_t nq, int64_t n, int64_t self_offset, const G
                 const int need = rc > s ? rc : s;
                 if (need != gate) continue;
                 const int64_t ct0 = (int64_t)s * pl->tiles_per_split;
-                int64_t cnt = ceil_div(n, TC_BN) - ct0;
+                int64_t cnt = ceil_div(n, bn) - ct0;
                 if (cnt > pl->tiles_per_split) cnt = pl->tiles_per_split;
                 table->push_back(unit_entry(r, ct0, (int)cnt, 1, gate, s, false));
             }
@@ -2064,11 +2131,11 @@ static int nn_top1_impl(const T* q_unit, const uint16_t* q_f16, int64_t nq, cons
         gate = nullptr;
         after = nullptr;
     }
-    ScreenPlan pl = plan_screen(nq, n);
+    ScreenPlan pl = plan_screen(nq, n, screen_bn(d_pad));
     std::vector<int4> table;
     Scratch table_dev;
     if (gate) {
-        SLIC_PROPAGATE(plan_screen_gated(nq, n, self_offset, *gate, &pl, &table));
+        SLIC_PROPAGATE(plan_screen_gated(nq, n, screen_bn(d_pad), self_offset, *gate, &pl, &table));
         SLIC_CUDA_OK(table_dev.alloc(table.size() * sizeof(int4), st));
         SLIC_PROPAGATE(stage_to_device(table_dev.ptr, table.data(), table.size() * sizeof(int4), st));
     }
@@ -2122,8 +2189,8 @@ template <typename T>
 static int topk_tc_impl(const T* q_unit, const uint16_t* q_f16, int64_t nq, const T* x_unit, const uint16_t* x_f16,
                         int64_t n, int d, int d_pad, int k, int64_t self_offset, float eps, int* idx_out, T* dist_out,
                         int* stats_out, cudaStream_t st) {
-    const ScreenPlan pl = plan_screen_topk(nq, n, k);
-    const int TC_CAP_TOPK = topk_cap(k, (int64_t)pl.tiles_per_split * (TC_BN / 2));
+    const ScreenPlan pl = plan_screen_topk(nq, n, k, screen_bn(d_pad));
+    const int TC_CAP_TOPK = topk_cap(k, (int64_t)pl.tiles_per_split * (screen_bn(d_pad) / 2));
     const int64_t slots = (int64_t)pl.splits * 2 * nq;   // one list per (split, 128-column half of the tiles, row)
     Scratch ci, cs, cc, cf, ck, ovr, stats;
     SLIC_CUDA_OK(ci.alloc(slots * TC_CAP_TOPK * sizeof(int), st));
@@ -2314,7 +2381,7 @@ static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d,
     ScreenPlan pl;
     std::vector<int4> table;
     int64_t prepass_units_all = 0;
-    SLIC_PROPAGATE(plan_screen_sym(n, part, parts, gate, &pl, &table, (SymMode)mode, &prepass_units_all));
+    SLIC_PROPAGATE(plan_screen_sym(n, screen_bn(d_pad), part, parts, gate, &pl, &table, (SymMode)mode, &prepass_units_all));
     SLIC_REQUIRE((mode == SYM_FUSED) == (peers != nullptr), "symmetric screen: the fused mode needs peer windows (and only it)");
     SLIC_REQUIRE(mode != SYM_FUSED || (stats_ext && !gate), "symmetric screen: the fused mode is asynchronous and ungated");
     int64_t exec_tiles = 0;
@@ -2627,11 +2694,12 @@ int slic_nn_top1_sym_part(const float* unit_dev, const uint16_t* f16_dev, int64_
     return SLIC_OK;
 }
 
-int slic_debug_sym_plan(int64_t n, int32_t part, int32_t parts, int32_t mode, int32_t gated_chunks, int32_t* units_out_host,
-                        int64_t capacity, int64_t* num_units_out_host) {
+int slic_debug_sym_plan(int64_t n, int32_t part, int32_t parts, int32_t mode, int32_t gated_chunks, int32_t col_tile,
+                        int32_t* units_out_host, int64_t capacity, int64_t* num_units_out_host) {
     using namespace slic;
     SLIC_REQUIRE(n > 1 && n < ((int64_t)1 << 31) && num_units_out_host, "debug_sym_plan: bad arguments");
-    SLIC_REQUIRE(mode >= 0 && mode <= 2, "debug_sym_plan: mode must be 0 (full), 1 (row bests) or 2 (triangle)");
+    SLIC_REQUIRE(col_tile == TC_BN_NARROW || col_tile == TC_BN_WIDE, "debug_sym_plan: col_tile must be 128 or 256");
+    SLIC_REQUIRE(mode >= 0 && mode <= 3, "debug_sym_plan: mode must be 0 (full), 1 (row bests), 2 (triangle) or 3 (fused)");
     SLIC_REQUIRE(gated_chunks >= 0 && gated_chunks < 4095, "debug_sym_plan: bad chunk count");
     GateSpec gs = {reinterpret_cast<const int*>(num_units_out_host) /* never dereferenced by the planner */, 0, 0};
     if (gated_chunks > 0) {
@@ -2640,7 +2708,7 @@ int slic_debug_sym_plan(int64_t n, int32_t part, int32_t parts, int32_t mode, in
     }
     ScreenPlan pl;
     std::vector<int4> table;
-    SLIC_PROPAGATE(plan_screen_sym(n, part, parts, gated_chunks > 0 ? &gs : nullptr, &pl, &table, (SymMode)mode));
+    SLIC_PROPAGATE(plan_screen_sym(n, col_tile, part, parts, gated_chunks > 0 ? &gs : nullptr, &pl, &table, (SymMode)mode));
     *num_units_out_host = (int64_t)table.size();
     if (units_out_host) {
         SLIC_REQUIRE(capacity >= (int64_t)table.size(), "debug_sym_plan: unit buffer too small");
@@ -2744,8 +2812,8 @@ int slic_screen_scores_debug(const uint16_t* q_f16_dev, int64_t nq, const uint16
     SLIC_REQUIRE(q_f16_dev && x_f16_dev && out_dev, "screen_scores_debug: null pointer");
     SLIC_PROPAGATE(slic_require_device());
     cudaStream_t st = as_stream(stream);
-    const ScreenPlan pl = plan_screen(nq, n);
-    const int64_t slots = (int64_t)pl.splits * 2 * nq;   // one list per (split, 128-column half of the tiles, row)
+    const ScreenPlan pl = plan_screen(nq, n, screen_bn(d_pad));
+    const int64_t slots = (int64_t)pl.splits * 2 * nq;   // one list per (split, stream of the row: column half / tile group)
     Scratch ci, cs, cc, cf, err;
     SLIC_CUDA_OK(ci.alloc(slots * TC_CAP * sizeof(int), st));
     SLIC_CUDA_OK(cs.alloc(slots * TC_CAP * sizeof(float), st));
