@@ -331,6 +331,12 @@ int slic_finch_host(const float* x_host, int64_t n, int32_t d, const int64_t* in
                     int32_t* num_clust_out_host, int32_t* num_levels_out_host,
                     float* min_sim_out_host /* or NULL */, int32_t* has_min_sim_out_host /* or NULL */);
 
+/* Host -> device copy on `stream` for callers that hold their device memory themselves: a pinned source goes straight to
+ * cudaMemcpyAsync; a pageable one (a plain numpy array, what clustering/cluster_masks.py:80 produces) is staged in 32 MB
+ * pieces through pinned buffers filled by 8 host threads, the DMA of one piece overlapping the staging of the next
+ * (about 3x the rate of the driver's own single-threaded staging).  Returns once the last piece has been enqueued. */
+int slic_copy_to_device(void* dst_dev, const void* src_host, int64_t bytes, slic_stream_t stream);
+
 /* Upload / search overlap of slic_finch_host.  The pipelined path launches the persistent screen kernel BEFORE the
  * embeddings have arrived and needs the upload stream's small kernels to become resident next to it - true on an
  * otherwise idle B200, not promised by CUDA in general.  enable = 0: always upload first, then search (use this under

@@ -53,6 +53,7 @@ SIGNATURES = {
     "slic_set_flann_threshold": [_i64],
     "slic_host_trace": [_i32, _ptr],
     "slic_set_upload_overlap": [_i32],
+    "slic_copy_to_device": [_ptr, _ptr, _i64, _ptr],
     "slic_comm_create": [_ptr, _i32, _i64, _ptr],
     "slic_finch_multi": [_ptr, _ptr, _i64, _i32, _ptr, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr],
     "slic_comm_last_timeline": [_ptr, _ptr],

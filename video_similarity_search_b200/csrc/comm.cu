@@ -280,7 +280,7 @@ static int worker_call(Comm* c, int r, MultiJob* job, int epoch) {
     if (r == 0) CUDA_STEP(cudaEventRecord(c->t0, st));
     if (r1 > r0) {
         const size_t bytes = (size_t)(r1 - r0) * d * sizeof(float);
-        CUDA_STEP(cudaMemcpyAsync(data.as<float>() + r0 * d, job->x_host + r0 * d, bytes, cudaMemcpyHostToDevice, st));
+        STEP(copy_to_device_staged(data.as<float>() + r0 * d, job->x_host + r0 * d, bytes, st));   // (pageable: staged by threads)
         for (int k = 1; k < world; ++k) {
             const int g = (r + k) % world;   // every worker starts with a different peer
             if (job->data[g])

@@ -128,6 +128,20 @@ int finch_host_single(const float* x_host, int64_t n, int d, const int64_t* init
 // per-row key of the multi-GPU merge: (float32 distance bits << 32) | neighbour; MIN over the ranks = np.argmin's rule
 constexpr unsigned long long SYM_KEY_NONE = 0x7fffffff7fffffffull;
 
+// host_entry.cu: host -> device copies of pageable memory through pinned staging buffers filled by several host threads
+constexpr int STAGE_SLOTS = 3;
+struct StagePool {
+    void* buf[STAGE_SLOTS] = {nullptr, nullptr, nullptr};
+    cudaEvent_t done[STAGE_SLOTS] = {nullptr, nullptr, nullptr};
+    bool busy[STAGE_SLOTS] = {false, false, false};
+    size_t cap = 0;
+    int ensure(size_t bytes);   // three pinned buffers of at least `bytes` each
+};
+StagePool& stage_pool();        // the calling thread's pool
+bool host_is_pageable(const void* p);
+void parallel_host_copy(void* dst, const void* src, size_t bytes);
+int copy_to_device_staged(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t st);
+
 __host__ __device__ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- driver-internal forms of K2 / K3 (finch_driver.cu): counts stay on the device --------------------------------

@@ -14,9 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include <atomic>
 #include <memory>
-#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -416,65 +414,15 @@ struct Upload {
     cudaEvent_t done;
 };
 
-// Pageable source (what clustering/cluster_masks.py:80 hands over: `.cpu().numpy()`): a cudaMemcpyAsync from pageable
-// memory is staged by the driver through a small pinned bounce buffer on ONE thread (~10 GB/s measured: 492 MB in ~45 ms,
-// twice the level-0 screen it should hide behind).  Here STAGE_THREADS host threads copy each chunk slice by slice into
-// one of STAGE_SLOTS pinned staging buffers (kept for the life of the thread: cudaHostAlloc costs milliseconds) and the
-// DMA of chunk c runs while chunk c + 1 is being staged.
-constexpr int STAGE_SLOTS = 3, STAGE_THREADS = 8;
-struct StagePool {
-    void* buf[STAGE_SLOTS] = {nullptr, nullptr, nullptr};
-    cudaEvent_t done[STAGE_SLOTS] = {nullptr, nullptr, nullptr};
-    bool busy[STAGE_SLOTS] = {false, false, false};
-    size_t cap = 0;
-    int ensure(size_t bytes) {
-        if (cap >= bytes) return SLIC_OK;
-        for (int i = 0; i < STAGE_SLOTS; ++i) {
-            if (busy[i]) SLIC_CUDA_OK(cudaEventSynchronize(done[i]));
-            busy[i] = false;
-            if (buf[i]) SLIC_CUDA_OK(cudaFreeHost(buf[i]));
-            buf[i] = nullptr;
-            SLIC_CUDA_OK(cudaHostAlloc(&buf[i], bytes, cudaHostAllocDefault));
-            if (!done[i]) SLIC_CUDA_OK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
-        }
-        cap = bytes;
-        return SLIC_OK;
-    }
-};
-static bool is_pageable(const void* p) {
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-        cudaGetLastError();
-        return true;
-    }
-    return a.type == cudaMemoryTypeUnregistered;
-}
-static void parallel_copy(void* dst, const void* src, size_t bytes) {
-    if (bytes < ((size_t)4 << 20)) {
-        memcpy(dst, src, bytes);
-        return;
-    }
-    std::thread workers[STAGE_THREADS - 1];
-    const size_t per = (bytes / STAGE_THREADS + 4095) / 4096 * 4096;
-    for (int t = 1; t < STAGE_THREADS; ++t) {
-        const size_t o = per * t, len = o < bytes ? (bytes - o < per ? bytes - o : per) : 0;
-        workers[t - 1] = std::thread([=] {
-            if (len) memcpy(static_cast<char*>(dst) + o, static_cast<const char*>(src) + o, len);
-        });
-    }
-    memcpy(dst, src, per < bytes ? per : bytes);
-    for (int t = 1; t < STAGE_THREADS; ++t) workers[t - 1].join();
-}
-
 // Runs on the host right after the gated screen kernel has been launched on main_stream: enqueue, chunk by chunk,
 // copy -> normalise -> open the gate on the copy stream, then make the main stream wait for the last chunk (the
 // exact re-rank reads float32 unit rows of every chunk).
 static int run_upload(void* ctx) {
     Upload* up = static_cast<Upload*>(ctx);
     if (g_host_trace) SLIC_CUDA_OK(cudaEventRecord(g_up0, up->copy_stream));
-    static thread_local StagePool pool;
+    StagePool& pool = stage_pool();
     const bool staged = up->num_chunks > 1 && (size_t)up->chunk_rows * up->d * sizeof(float) <= ((size_t)256 << 20) &&
-                        is_pageable(up->x_host);   // (3 pinned staging buffers of one chunk each: bounded)
+                        host_is_pageable(up->x_host);   // (3 pinned staging buffers of one chunk each: bounded)
     if (staged) SLIC_PROPAGATE(pool.ensure((size_t)up->chunk_rows * up->d * sizeof(float)));
     for (int c = 0; c < up->num_chunks; ++c) {
         const int64_t r0 = (int64_t)c * up->chunk_rows;
@@ -483,7 +431,7 @@ static int run_upload(void* ctx) {
         if (staged) {
             const int slot = c % STAGE_SLOTS;
             if (pool.busy[slot]) SLIC_CUDA_OK(cudaEventSynchronize(pool.done[slot]));   // its previous DMA has drained
-            parallel_copy(pool.buf[slot], src, (size_t)rows * up->d * sizeof(float));
+            parallel_host_copy(pool.buf[slot], src, (size_t)rows * up->d * sizeof(float));
             src = static_cast<const float*>(pool.buf[slot]);
         }
         SLIC_CUDA_OK(cudaMemcpyAsync(up->data + r0 * up->d, src, (size_t)rows * up->d * sizeof(float),

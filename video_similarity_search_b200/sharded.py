@@ -169,7 +169,11 @@ def upload_replicated(data, group=None, backend=None):
         ctx = torch.cuda.stream(copier) if copier is not None else _nullcontext()
         with ctx:
             if rows > 0:
-                mine[:rows].copy_(host[r0 + c0:r0 + c0 + rows], non_blocking=True)
+                piece = host[r0 + c0:r0 + c0 + rows]
+                if on_gpu and hasattr(be, "copy_to_device") and not piece.is_pinned() and piece.is_contiguous():
+                    be.copy_to_device(mine[:rows], piece)      # pageable source: staged by host threads (csrc/host_entry.cu)
+                else:
+                    mine[:rows].copy_(piece, non_blocking=True)
             if rows < c1 - c0:
                 mine[rows:].zero_()                       # padding rows of the ragged last shards
         if copier is not None:
