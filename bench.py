@@ -184,9 +184,32 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 # GPU side
 # --------------------------------------------------------------------------------------------------
+_SAMPLER_SRC = r"""
+import sys, time
+import pynvml as nv
+nv.nvmlInit()
+h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+names = [("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+         ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap),
+         ("hw_power_brake_slowdown", nv.nvmlClocksEventReasonHwPowerBrakeSlowdown)]
+print("MAX", nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM), flush=True)
+while True:
+    try:
+        mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        print("S", time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetPowerUsage(h) / 1000.0,
+              ",".join(n for n, b in names if mask & b), flush=True)
+    except Exception:
+        pass
+    time.sleep(0.005)
+"""
+
+
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region: NVML polled from a thread every ~10 ms
-    (nvidia-smi -lms 100 as the fallback when pynvml cannot initialise)."""
+    """SM clock, power and throttle reasons sampled DURING the timed region by a SEPARATE process (NVML polled every
+    ~5 ms; nvidia-smi -lms 100 as the fallback when pynvml cannot initialise).  Round 1 polled from a thread of the
+    bench process: NVML calls share the driver's locks with the kernel launches of the same process, which costs
+    nothing while a 22 ms kernel hides the launches (1 GPU) but ~1.5 ms per step once the step is 6 ms of short
+    launches (8 GPUs: 7.9 ms per step with the thread, 6.3 ms without)."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -194,9 +217,8 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.gpu_index = gpu_index
         self.proc = None
-        self.thread = None
-        self.stop_flag = False
-        self.sm, self.power, self.reasons, self.max_mhz = [], [], set(), None
+        self.kind = None
+        self.t0 = self.t1 = None
 
     def _physical_index(self):
         vis = os.environ.get("CUDA_VISIBLE_DEVICES")
@@ -206,58 +228,63 @@ class ClockSampler:
                 return int(ids[self.gpu_index])
         return self.gpu_index
 
-    def _poll(self, nv, handle):
-        names = [("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
-                 ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
-                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
-                 ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap),
-                 ("hw_power_brake_slowdown", nv.nvmlClocksEventReasonHwPowerBrakeSlowdown)]
-        while not self.stop_flag:
-            try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)))
-                self.power.append(nv.nvmlDeviceGetPowerUsage(handle) / 1000.0)
-                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(handle)
-                for name, bit in names:
-                    if mask & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            time.sleep(0.01)
-
-    def start(self):
+    def launch(self):
+        """Start the sampling process (call well before the timed region: the interpreter takes a moment to come up)."""
+        env = dict(os.environ)
+        env.pop("CUDA_VISIBLE_DEVICES", None)
         try:
-            import threading
-            import pynvml as nv
-            nv.nvmlInit()
-            handle = nv.nvmlDeviceGetHandleByIndex(self._physical_index())
-            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
-            self.thread = threading.Thread(target=self._poll, args=(nv, handle), daemon=True)
-            self.thread.start()
-            return
+            import pynvml  # noqa: F401  (only to know that the child can import it)
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(self._physical_index())], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True, env=env)
+            self.kind = "nvml"
+            first = self.proc.stdout.readline()          # "MAX <mhz>": the child is up and polling
+            if first.startswith("MAX"):
+                self.max_mhz = float(first.split()[1])
+                return
+            self.proc.kill()                             # (NVML did not initialise in the child)
+            self.proc = None
         except Exception:
-            self.thread = None
+            self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self._physical_index()), "--query-gpu=" + self.QUERY,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.kind = "smi"
         except Exception:
             self.proc = None
 
-    def stop(self):
-        if self.thread is not None:
-            self.stop_flag = True
-            self.thread.join(timeout=2)
-            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
-                    "samples": len(self.sm), "power_w_max": max(self.power) if self.power else None,
-                    "reasons": sorted(self.reasons), "how": "NVML polled every 10 ms during the timed steps"}
+    def start(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            self.launch()
+        self.t0 = time.time()
+
+    def stop(self):
+        self.t1 = time.time()
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no sampler (pynvml and nvidia-smi unavailable)"]}
+        time.sleep(0.02)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
         except Exception:
             self.proc.kill()
             out = ""
+        if self.kind == "nvml":
+            sm, power, reasons = [], [], set()
+            for ln in out.splitlines():
+                f = ln.split()
+                if len(f) < 4 or f[0] != "S":
+                    continue
+                t = float(f[1])
+                if t < self.t0 or t > self.t1:
+                    continue
+                sm.append(float(f[2]))
+                power.append(float(f[3]))
+                if len(f) > 4:
+                    reasons.update(v for v in f[4].split(",") if v)
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "samples": len(sm),
+                    "power_w_max": max(power) if power else None, "reasons": sorted(reasons),
+                    "how": "NVML polled every 5 ms by a separate process during the timed steps"}
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in out.strip().splitlines():
@@ -408,9 +435,11 @@ def run_b200(args):
         return (search(x_dev) if search else be.first_neighbors(x_dev))
 
     warmup = max(args.warmup, 3)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.launch()             # (separate process; comes up during the warm-up steps)
     for _ in range(warmup):          # (also builds the stream-ordered memory pool)
         step_resident()
-    sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = lib.slic_launch_count()

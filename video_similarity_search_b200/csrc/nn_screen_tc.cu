@@ -141,6 +141,13 @@ struct ScreenParams {
     int* cand_flags;       // [2 * splits][nq]  bit0 = overflow, bit1 = compacted
     int topk;              // TOPK kernel: k (<= TC_TOPK_MAX); the candidate rule is "within eps of the k-th best"
     float* cand_kth;       // TOPK kernel: [splits][nq] lower bound of the split's k-th best screened score
+    // TOPK kernel: [2 * splits][nq] the same bound as a histogram bin, ZEROED before the launch.  A stream (row, split,
+    // half) publishes its final bin here and every stream STARTS from the highest bin any other stream of its row has
+    // published: the k-th best over a subset of the columns is a lower bound of the k-th best over all of them, so the
+    // seeded threshold is as valid as the stream's own - and with split-major units the streams of split s - 1 have
+    // finished when those of split s start, which spares them the listing of their first tile and the whole threshold
+    // ramp (~k ln(columns / 128) listings per stream).
+    int* cand_tb;
     float* dump;           // debug: raw scores [nq][n] or nullptr
     int* error_flag;       // set when a barrier wait times out
     unsigned long long* trace;  // optional [8] cycle counters summed over CTAs (diagnostic, see slic_screen_trace)
@@ -1217,10 +1224,13 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
             cx.ls = p.cand_score + slot * p.cap;
             if constexpr (TOPK) {
                 for (int i = 0; i < TC_HIST_BINS; ++i) cx.hist[i * TC_HIST_STRIDE] = 0;
-                cx.st.tb = 0;
+                int seed = 0;
+                if (p.cand_tb && cx.row_ok)
+                    for (int s2 = 0; s2 < 2 * p.splits; ++s2) seed = max(seed, __ldcg(p.cand_tb + (int64_t)s2 * p.nq + cx.row));
+                cx.st.tb = seed;
                 cx.st.cge = 0;
                 cx.st.ctb = 0;
-                cx.st.thr = bin_edge(0) - p.eps;
+                cx.st.thr = bin_edge(seed) - p.eps;
                 cx.pd.n = 0;
             } else if constexpr (SYM) {
                 // start from the best score any CTA has published for this row (pre-pass, earlier units, column roles)
@@ -1382,7 +1392,10 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
             } else if (cx.row_ok) {
                 p.cand_cnt[slot] = cx.st.cnt;
                 p.cand_flags[slot] = cx.st.flags;
-                if constexpr (TOPK) p.cand_kth[slot] = bin_edge(cx.st.tb);
+                if constexpr (TOPK) {
+                    p.cand_kth[slot] = bin_edge(cx.st.tb);
+                    if (p.cand_tb) p.cand_tb[slot] = cx.st.tb;
+                }
             }
         }
         if constexpr (SYM) {
@@ -1810,7 +1823,7 @@ static int launch_screen(const uint16_t* q_f16, int64_t nq, const uint16_t* x_f1
                          float* cand_kth = nullptr, const int4* unit_table = nullptr, const int* gates = nullptr,
                          unsigned int* best_enc = nullptr, int64_t exec_tiles = 0, int* log_q = nullptr,
                          int log_region = 0, int* sync_counter = nullptr, const int* sync_targets = nullptr,
-                         const ScreenPeers* peers = nullptr) {
+                         const ScreenPeers* peers = nullptr, int* cand_tb = nullptr) {
     const int ncta = screen_ncta();
     if (gates) SLIC_PROPAGATE(arm_timeout_record());
     CUtensorMap tq, tx;
@@ -1833,6 +1846,7 @@ static int launch_screen(const uint16_t* q_f16, int64_t nq, const uint16_t* x_f1
     p.cand_flags = cand_flags;
     p.topk = topk;
     p.cand_kth = cand_kth;
+    p.cand_tb = cand_tb;
     p.dump = dump;
     p.error_flag = error_flag;
     p.trace = g_trace;
@@ -2199,7 +2213,9 @@ static int topk_tc_impl(const T* q_unit, const uint16_t* q_f16, int64_t nq, cons
     const ScreenPlan pl = plan_screen_topk(nq, n, k, screen_bn(d_pad));
     const int TC_CAP_TOPK = topk_cap(k, (int64_t)pl.tiles_per_split * (screen_bn(d_pad) / 2));
     const int64_t slots = (int64_t)pl.splits * 2 * nq;   // one list per (split, 128-column half of the tiles, row)
-    Scratch ci, cs, cc, cf, ck, ovr, stats;
+    Scratch ci, cs, cc, cf, ck, ctb, ovr, stats;
+    SLIC_CUDA_OK(ctb.alloc(slots * sizeof(int), st));
+    SLIC_CUDA_OK(cudaMemsetAsync(ctb.ptr, 0, slots * sizeof(int), st));
     SLIC_CUDA_OK(ci.alloc(slots * TC_CAP_TOPK * sizeof(int), st));
     SLIC_CUDA_OK(cs.alloc(slots * TC_CAP_TOPK * sizeof(float), st));
     SLIC_CUDA_OK(cc.alloc(slots * sizeof(int), st));
@@ -2210,7 +2226,8 @@ static int topk_tc_impl(const T* q_unit, const uint16_t* q_f16, int64_t nq, cons
     SLIC_CUDA_OK(cudaMemsetAsync(stats.ptr, 0, 8 * sizeof(int), st));
     SLIC_PROPAGATE(launch_screen(q_f16, nq, x_f16, n, d_pad, self_offset, eps, TC_CAP_TOPK, pl, ci.as<int>(),
                                  cs.as<float>(), cc.as<int>(), cf.as<int>(), nullptr, stats.as<int>() + 4, st, k,
-                                 ck.as<float>()));
+                                 ck.as<float>(), nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr,
+                                 ctb.as<int>()));
     rerank_topk_kernel<T><<<(unsigned)nq, RK_THREADS, 0, st>>>(q_unit, x_unit, nq, d, eps, TC_CAP_TOPK, 2 * pl.splits, k,
                                                                ci.as<int>(), cs.as<float>(), cc.as<int>(), cf.as<int>(),
                                                                ck.as<float>(), idx_out, dist_out, ovr.as<int>(),
