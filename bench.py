@@ -329,7 +329,8 @@ def retrieval_record(torch, be, lib, peaks, q, x, k, steps, world, label, check_
             return topk_neighbors_sharded(q, x, k, backend=be)
         return be.topk_neighbors(q, x, k)
 
-    call()
+    for _ in range(3):
+        call()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -337,8 +338,11 @@ def retrieval_record(torch, be, lib, peaks, q, x, k, steps, world, label, check_
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     out = None
+    per_call = []
     for _ in range(steps):
-        out = call()
+        t0 = time.perf_counter()
+        out = call()                 # (synchronises internally: the candidate counters are read back)
+        per_call.append((time.perf_counter() - t0) * 1e3)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
@@ -356,7 +360,8 @@ def retrieval_record(torch, be, lib, peaks, q, x, k, steps, world, label, check_
     tf = fl.value / (kernel_ms * 1e-3) / 1e12          # this rank's share of 2 Q N d over its kernel time
     rec = {"shape": "%d queries x %d database x %d, k=%d" % (nq, n, d, k), "ms": ms, "queries_per_s": nq / (ms * 1e-3),
            "screen_kernel_ms": kernel_ms, "screen_tflops_per_gpu": tf, "frac_of_peak": tf / peaks["bf16_tflops"],
-           "flop_per_launch": fl.value, "d_pad": d_pad, "n_gpus": world, "data": label}
+           "flop_per_launch": fl.value, "d_pad": d_pad, "n_gpus": world, "data": label,
+           "host_ms_per_call_min_median_max": [min(per_call), statistics.median(per_call), max(per_call)]}
     if check_exact and world == 1:
         # identical indices from the exact float64-accumulating kernels (no screen): the parity of the top-k path
         ux, _ = be.normalize_rows(x, want_f16=False)

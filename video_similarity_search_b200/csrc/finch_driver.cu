@@ -530,6 +530,12 @@ static int finch_host_impl(const float* x_host, int64_t n, int d, const int64_t*
             up.num_chunks = gated_chunks();
             up.chunk_rows = ceil_div(ceil_div(n, up.num_chunks), 256) * 256;
             up.num_chunks = (int)ceil_div(n, up.chunk_rows);
+            // A pageable source is staged through pinned buffers: size them NOW.  cudaFreeHost / cudaHostAlloc synchronise
+            // the device - issued while the gated kernel is already waiting for its first chunk they would wait for a
+            // kernel that waits for them (measured: the 2 s gate time-out, then the whole process falls back to
+            // upload-then-search, 70 ms per call instead of 33).
+            if ((size_t)up.chunk_rows * d * sizeof(float) <= ((size_t)256 << 20) && host_is_pageable(x_host))
+                SLIC_PROPAGATE(stage_pool().ensure((size_t)up.chunk_rows * d * sizeof(float)));
             SLIC_CUDA_OK(gates.alloc((up.num_chunks + 1) * sizeof(int), st));
             SLIC_CUDA_OK(cudaMemsetAsync(gates.ptr, 0, (up.num_chunks + 1) * sizeof(int), st));
             up.gates = gates.as<int>();
