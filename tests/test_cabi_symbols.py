@@ -67,6 +67,26 @@ def test_argument_validation_of_the_multi_gpu_and_widening_entries_needs_no_gpu(
     assert b"contingency" in lib.slic_last_error()
 
 
+def test_argument_validation_of_the_peer_window_entries_needs_no_gpu():
+    """csrc/comm.cu: bad arguments are refused before any device work (status -1, message naming the entry)."""
+    lib = _lib.load()
+    assert lib.slic_comm_create(None, 2, 1000, None) == -1 and b"comm_create" in lib.slic_last_error()
+    devs = (ctypes.c_int32 * 9)(*range(9))
+    out = ctypes.c_void_p()
+    assert lib.slic_comm_create(devs, 9, 1000, ctypes.addressof(out)) == -1             # more than 8 devices
+    assert lib.slic_comm_create(devs, 2, 0, ctypes.addressof(out)) == -1                 # max_rows
+    assert lib.slic_comm_window_create(0, None, None) == -1
+    assert lib.slic_comm_connect(None, 0, 2, None) == -1 and b"comm_connect" in lib.slic_last_error()
+    assert lib.slic_comm_nn_top1(None, None, None, 20000, 64, 64, None, None, None, None) == -1
+    assert lib.slic_comm_finch(None, None, 20000, 64, 1, 32, None, None, None, None, None, None) == -1
+    assert lib.slic_finch_multi(None, None, 20000, 64, None, 1, 32, None, None, None, None, None) == -1
+    assert b"finch_multi" in lib.slic_last_error()
+    assert lib.slic_comm_last_timeline(None, None) == -1
+    assert lib.slic_copy_to_device(None, None, 10, None) == -1 and b"copy_to_device" in lib.slic_last_error()
+    assert lib.slic_comm_destroy(None) == 0                                              # destroying nothing is fine
+    assert lib.slic_set_upload_overlap(0) == 0 and lib.slic_set_upload_overlap(-1) == 0
+
+
 def test_bench_without_a_gpu_fails_loudly_and_names_the_cpu_arm():
     import subprocess
     import sys

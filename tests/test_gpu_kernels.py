@@ -96,6 +96,24 @@ def test_compose_and_segmented_mean(be):
                                fo.cluster_means(xo, lab), rtol=0, atol=1e-11)
 
 
+def test_copy_to_device_pageable_and_pinned_sources(be):
+    """slic_copy_to_device: a pageable source is staged through pinned buffers by several host threads in 32 MB pieces, a
+    pinned one goes straight to the DMA engine - the bytes on the device must be the source's either way (sizes around
+    the piece and slice boundaries, and a second call that reuses the staging slots)."""
+    rng = np.random.default_rng(11)
+    for nbytes in (8 << 20, (32 << 20) + 4096, (70 << 20) + 12, 1000):
+        src = torch.from_numpy(rng.integers(0, 256, nbytes, dtype=np.uint8))
+        for pinned in (False, True):
+            host = src.pin_memory() if pinned else src
+            dst = torch.empty(nbytes, dtype=torch.uint8, device=be.device)
+            be.copy_to_device(dst, host)
+            be.copy_to_device(dst, host)
+            torch.cuda.synchronize()
+            assert torch.equal(dst.cpu(), src), (nbytes, pinned)
+    x = rng.standard_normal((40000, 96)).astype(np.float32)          # to_device takes the same route for large host arrays
+    assert np.array_equal(be.to_device(x).cpu().numpy(), x)
+
+
 def test_direct_callers_with_sloppy_labels_get_defined_results(be):
     """the C ABI is public.  Empty clusters of slic_cluster_sums get sum 0 / count 0 / mean NaN instead of
     uninitialised rows; labels outside [0, num) in slic_cluster_metrics are refused (no out-of-bounds write)."""

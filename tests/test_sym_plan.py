@@ -63,15 +63,15 @@ def test_full_mode_is_prepass_plus_the_same_triangle_and_row_bests_cover_every_r
         full, tri, pre = plan(n, part, parts, 0, tile=tile), plan(n, part, parts, 2, tile=tile), plan(n, part, parts, 1, tile=tile)
         assert np.array_equal(full[full[:, 5] == 1], tri)                # mode 0 = pre-pass over all rows + this share
         assert sorted(full[full[:, 5] == 0][:, 0].tolist()) == list(range(R))
-        assert (pre[:, 5] == 0).all() and (pre[:, 2] == 64 * tpr).all()  # 64 x 256 sampled columns from 4 parts on
+        assert (pre[:, 5] == 0).all() and (pre[:, 2] == 32 * tpr).all()  # 32 x 256 sampled columns from 4 parts on
         cols = np.array([c for _, c in tiles_of(pre[:1])])
-        assert cols.min() >= 0 and cols.max() < T and len(set(cols.tolist())) == 64 * tpr
+        assert cols.min() >= 0 and cols.max() < T and len(set(cols.tolist())) == 32 * tpr
         rows += pre[:, 0].tolist()
         # fused (multi-GPU kernel): the same rows and the same sample, cut into units of 16 x 256 columns, then the share
         fused = plan(n, part, parts, 3, tile=tile)
         fpre = fused[fused[:, 5] == 0]
         assert np.array_equal(fused[fused[:, 5] == 1], tri) and (np.diff(fused[:, 5]) >= 0).all()
-        assert (fpre[:, 2] == 16 * tpr).all() and len(fpre) == 4 * len(pre)
+        assert (fpre[:, 2] == 16 * tpr).all() and len(fpre) == 2 * len(pre)
         assert sorted(tiles_of(fpre)) == sorted(tiles_of(pre))
         fused_rows += sorted(set(fpre[:, 0].tolist()))
     assert sorted(rows) == list(range(R)) and sorted(fused_rows) == list(range(R))   # every row block on exactly one part

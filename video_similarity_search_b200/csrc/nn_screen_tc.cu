@@ -2030,9 +2030,11 @@ static int plan_screen_sym(int64_t n, int bn, int part, int parts, const GateSpe
     const int64_t span = g ? (chunk_tiles_gate < T ? chunk_tiles_gate : T) : T;
     const int64_t span_w = span / tpr > 0 ? span / tpr : 1;
     // SYM_BESTS / SYM_FUSED: every part pays a warm-up of loose thresholds at the start of its (short) share of the
-    // triangle, so a stronger sample pays off from 4 parts on (measured at 8 parts, C3: 16 / 32 / 64 blocks -> 3.96 / 3.64
-    // / 3.30 ms for the triangle share against +0.1 ms per 16 blocks here)
-    int samples_w = own_rows_prepass ? (parts >= 4 ? 4 * SYM_SAMPLE_TILES : SYM_SAMPLE_TILES) : SYM_SAMPLE_TILES / parts;
+    // triangle, so a stronger sample pays off from 4 parts on.  Round 1 (bfloat16 screen, eps 2^-7), 8 parts, C3: 16 / 32 /
+    // 64 blocks -> 3.96 / 3.64 / 3.30 ms for the triangle share against +0.1 ms per 16 blocks here: 64.  Round 2 (float16,
+    // eps 2^-9 + 2^-10: a loose threshold admits far fewer candidates), 4 parts, whole level-0 stage: 7.35 / 7.17 / 7.37 ms:
+    // flat, 32.
+    int samples_w = own_rows_prepass ? (parts >= 4 ? 2 * SYM_SAMPLE_TILES : SYM_SAMPLE_TILES) : SYM_SAMPLE_TILES / parts;
     if (own_rows_prepass && samples_w > span_w / 4) samples_w = (int)(span_w / 4);   // small inputs: a sample, not the whole square
     // small inputs (a hierarchy's level 1): the pre-pass must stay a sample - measured at 21 436 x 512 float64 centroids:
     // 16 / 10 / 4 sample blocks -> 0.88 / 0.79 / 0.72 ms for the whole search
