@@ -93,6 +93,21 @@ ok &= bool(torch.equal(i1, i2) and torch.equal(v1, v2))
 i1, v1 = be.topk_neighbors(xx, xx, 5, same=True)
 i2, v2 = topk_neighbors_sharded(xx, xx, 5, same=True, backend=be)
 ok &= bool(torch.equal(i1, i2) and torch.equal(v1, v2))
+# a rank that cannot set up its peer window (no IPC in the container, no peer access): EVERY rank must notice, nobody may
+# hang, and the search must fall back to the NCCL scheme with the same result
+close_peer_groups()
+if rank == 1:
+    def broken(max_rows):
+        raise RuntimeError("simulated: CUDA IPC not permitted")
+    be.comm_window_create = broken
+import warnings
+with warnings.catch_warnings():
+    warnings.simplefilter("ignore")
+    search = sharded_first_neighbors(be)
+    nn, dd, _ = search(x)
+    ok &= bool(torch.equal(nn, nn1) and torch.equal(dd, d1))
+    cs, nums, _ = FINCH_sharded(x, backend=be, verbose=False)
+    ok &= nums == num1 and bool(np.array_equal(cs, c1))
 t = torch.tensor([int(ok)], device=be.device)
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:

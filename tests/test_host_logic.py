@@ -134,6 +134,11 @@ def test_evaluate_wrappers_match_oracle():
     dme = ev.get_distance_matrix(q.astype(np.float64), x.astype(np.float64), "euclidean", backend=be)
     np.testing.assert_allclose(np.asarray(dme), ro.distance_matrix(q.astype(np.float64), x.astype(np.float64), "euclidean"),
                                rtol=1e-9, atol=1e-9)
+    # lazy=False: the ndarray itself, as the reference returns it
+    dense = ev.get_distance_matrix(q, x, backend=be, lazy=False)
+    assert isinstance(dense, np.ndarray) and dense.dtype == ref.dtype
+    np.testing.assert_allclose(dense, ref, rtol=0, atol=2e-6)
+    np.testing.assert_array_equal(ev.get_topk_acc(dense, ql.tolist(), xl.tolist(), backend=be), ro.topk_acc(ref, ql.tolist(), xl.tolist()))
     with pytest.raises(AssertionError):
         ev.get_distance_matrix(q, x, "manhattan", backend=be)
 

@@ -83,8 +83,11 @@ class DistanceMatrix:
         return self._be.rows_topk(self.device_matrix(), k)
 
 
-def get_distance_matrix(x_embeddings, y_embeddings=None, dist_metric='cosine', backend=None):
-    """evaluate.py:208-223.  Returns a DistanceMatrix (see module docstring)."""
+def get_distance_matrix(x_embeddings, y_embeddings=None, dist_metric='cosine', backend=None, lazy=True):
+    """evaluate.py:208-223.  Returns a DistanceMatrix (see module docstring): every caller in the reference
+    (evaluate.py:367-384, validation.py:81-82, :130-131) hands the result to get_topk_acc / get_closest_data(_mat) or
+    reads .shape / indexes rows, all of which the lazy object serves.  lazy=False returns the materialised
+    np.ndarray itself (what the reference returns), for code that checks isinstance(..., np.ndarray)."""
     assert(dist_metric in ['cosine', 'euclidean'])                  # evaluate.py:211
     be = backend or _backend.default_backend()
     x = _as_float_array(x_embeddings)
@@ -93,7 +96,8 @@ def get_distance_matrix(x_embeddings, y_embeddings=None, dist_metric='cosine', b
     tdt = torch.float32 if dt == np.float32 else torch.float64
     xd = be.to_device(x.astype(dt, copy=False), tdt)
     yd = xd if y is None else be.to_device(y.astype(dt, copy=False), tdt)
-    return DistanceMatrix(be, xd, yd, dist_metric, same=y is None)
+    dm = DistanceMatrix(be, xd, yd, dist_metric, same=y is None)
+    return dm if lazy else dm.numpy()
 
 
 def _topk_from_any(distance_matrix, top_k, backend=None):

@@ -19,6 +19,10 @@ from . import backend as _backend
 from .clustering.finch import FINCH
 
 
+class PeerWindowsUnavailable(RuntimeError):
+    """Raised on EVERY rank when some rank could not set up its peer window; callers fall back to the NCCL scheme."""
+
+
 class PeerGroup:
     """NVLink peer windows of the ranks of a process group (one process per GPU; csrc/comm.cu).  The 64-byte CUDA IPC
     handles travel through the process group once, at construction; after that the level-0 search of the group needs
@@ -27,12 +31,30 @@ class PeerGroup:
     def __init__(self, be, group=None, max_rows=1 << 20):
         self.be, self.group, self.max_rows = be, group, int(max_rows)
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.comm, handle = be.comm_window_create(self.max_rows)
+        # Every step is collective-safe: a rank that cannot create, export or map a window (no peer access between the
+        # devices, CUDA IPC not permitted in this container, ...) still takes part in the exchanges below, and ALL ranks
+        # learn of the failure from one all-reduce - nobody is left waiting in a barrier.
+        self.comm, error = None, None
+        try:
+            self.comm, handle = be.comm_window_create(self.max_rows)
+        except Exception as e:             # noqa: BLE001 - reported below, on every rank
+            handle, error = bytes(64), e
         mine = torch.tensor(list(handle), dtype=torch.uint8, device=be.device)
         everyone = torch.empty(64 * self.world, dtype=torch.uint8, device=be.device)
         dist.all_gather_into_tensor(everyone, mine, group=group)
-        be.comm_connect(self.comm, self.rank, self.world, bytes(everyone.cpu().tolist()))
-        dist.barrier(group=group)          # every rank has mapped every window before anyone publishes into one
+        if error is None:
+            try:
+                be.comm_connect(self.comm, self.rank, self.world, bytes(everyone.cpu().tolist()))
+            except Exception as e:         # noqa: BLE001
+                error = e
+        ok = torch.tensor([0 if error is not None else 1], dtype=torch.int32, device=be.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)   # (also: every rank has mapped every window before anyone publishes)
+        if int(ok.item()) == 0:
+            if self.comm is not None:
+                be.comm_destroy(self.comm)
+                self.comm = None
+            raise PeerWindowsUnavailable("NVLink peer windows could not be set up on every rank%s"
+                                         % ("" if error is None else ": %s" % error))
 
     def first_neighbors(self, mat):
         """-> (nn, dist, unit, status): status is a device int32[2], non-zero = repeat the search another way."""
@@ -60,14 +82,24 @@ def sharded_first_neighbors(be, group=None, timings=None, triangle=True, peer=Tr
         between them and an all-reduce MIN of the keys after (the round-1 scheme, also used by the CPU stand-in tests);
     otherwise (and for small inputs) query rows are sharded and the ids all-gathered."""
     def peer_group(n):
-        # one set of windows per (backend, process group), shared by every search built on them and grown on demand
+        # one set of windows per (backend, process group), shared by every search built on them and grown on demand;
+        # None when the windows cannot be had on this box (decided once, identically on every rank)
         key = (id(be), id(group))
+        if key in _PEER_UNAVAILABLE:
+            return None
         pg = _PEER_GROUPS.get(key)
         if pg is not None and pg.max_rows < n:
             pg.close()
+            _PEER_GROUPS.pop(key, None)
             pg = None
         if pg is None:
-            pg = _PEER_GROUPS[key] = PeerGroup(be, group, max_rows=max(n, 1 << 18))
+            try:
+                pg = _PEER_GROUPS[key] = PeerGroup(be, group, max_rows=max(n, 1 << 18))
+            except PeerWindowsUnavailable as e:
+                import warnings
+                warnings.warn("%s - falling back to the NCCL all-reduce scheme" % e)
+                _PEER_UNAVAILABLE.add(key)
+                return None
         return pg
 
     def search(mat):
@@ -75,8 +107,9 @@ def sharded_first_neighbors(be, group=None, timings=None, triangle=True, peer=Tr
         rank = dist.get_rank(group)
         n = mat.shape[0]
         use_triangle = world > 1 and triangle and hasattr(be, "first_neighbors_part") and be.supports_triangle_parts(mat)
-        if use_triangle and peer and world <= 8 and hasattr(be, "comm_first_neighbors"):
-            nn, d, unit, status = peer_group(n).first_neighbors(mat)
+        pg = peer_group(n) if (use_triangle and peer and world <= 8 and hasattr(be, "comm_first_neighbors")) else None
+        if pg is not None:
+            nn, d, unit, status = pg.first_neighbors(mat)
             if not status.any().item():      # (the one host read-back of the stage; identical on every rank)
                 return nn, d, unit
             use_triangle = False             # degenerate input (candidate log overflow): row-sharded full square below
@@ -116,7 +149,8 @@ def sharded_first_neighbors(be, group=None, timings=None, triangle=True, peer=Tr
         world = dist.get_world_size(group)
         if (world > 1 and world <= 8 and triangle and peer and hasattr(be, "finch_native_comm")
                 and be.supports_triangle_parts(mat)):
-            return peer_group(mat.shape[0]).comm
+            pg = peer_group(mat.shape[0])
+            return None if pg is None else pg.comm
         return None
 
     search.native_comm = native_comm
@@ -124,6 +158,7 @@ def sharded_first_neighbors(be, group=None, timings=None, triangle=True, peer=Tr
 
 
 _PEER_GROUPS = {}
+_PEER_UNAVAILABLE = set()
 
 
 def close_peer_groups():
