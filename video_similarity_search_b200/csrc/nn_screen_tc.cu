@@ -148,6 +148,10 @@ struct ScreenParams {
     // finished when those of split s start, which spares them the listing of their first tile and the whole threshold
     // ramp (~k ln(columns / 128) listings per stream).
     int* cand_tb;
+    // experiment (SLIC_SCREEN_L2PF, default 0 = off): tiles ahead of the ring whose B slabs the producer prefetches into L2.
+    // Measured at C3 with 1 / 2 / 4 tiles: operand wait of the MMA issuer 14.4 % -> 13.8 %, kernel 23.3 -> 24.3 ms - the wait is
+    // L2 -> SM delivery, not DRAM latency (profiles/r2_screen_pipeline_trace.txt).
+    int l2_prefetch;
     float* dump;           // debug: raw scores [nq][n] or nullptr
     int* error_flag;       // set when a barrier wait times out
     unsigned long long* trace;  // optional [8] cycle counters summed over CTAs (diagnostic, see slic_screen_trace)
@@ -366,6 +370,10 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t dst
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
+}
+// L2 prefetch of one TMA box (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 // shared::cluster address of the same smem offset in the pair's leader CTA (rank 0): clear the peer bit
 constexpr uint32_t TC_PEER_BIT_MASK = 0xFEFFFFFFu;
@@ -1009,6 +1017,11 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
                 }
                 for (int kt = 0; kt < ui.count; ++kt) {
                     const int64_t ct = ui.ct0 + (int64_t)kt * ui.stride;
+                    if (p.l2_prefetch > 0 && kt + p.l2_prefetch < ui.count) {
+                        const int64_t ctp = ui.ct0 + (int64_t)(kt + p.l2_prefetch) * ui.stride;
+                        for (int ks = 0; ks < p.num_k_slabs; ++ks)
+                            tma_prefetch_l2_2d(&tmap_x, ks * TC_BK, (int)(ctp * BN + cta_rank * Cfg::B_ROWS));
+                    }
                     for (int ks = 0; ks < p.num_k_slabs; ks += Cfg::SPS) {
                         mbar_wait_traced(bar_empty + 8 * stage, phase ^ 1, p.error_flag, t_wait, tracing);
                         const uint32_t a_dst = ring_base + stage * Cfg::STAGE_BYTES;
@@ -1847,6 +1860,15 @@ static int launch_screen(const uint16_t* q_f16, int64_t nq, const uint16_t* x_f1
     p.topk = topk;
     p.cand_kth = cand_kth;
     p.cand_tb = cand_tb;
+    {
+        static int l2pf = -1;   // experiments: SLIC_SCREEN_L2PF=<tiles ahead> (default 0 = off)
+        if (l2pf < 0) {
+            const char* e = getenv("SLIC_SCREEN_L2PF");
+            l2pf = e ? atoi(e) : 0;
+            if (l2pf < 0 || l2pf > 16) l2pf = 0;
+        }
+        p.l2_prefetch = l2pf;
+    }
     p.dump = dump;
     p.error_flag = error_flag;
     p.trace = g_trace;
