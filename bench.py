@@ -65,7 +65,7 @@ def parse_args():
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from a committed `ncu --set full`
 # capture; keyed by (workload, ranks).  A constant taken from that capture, not re-measured per run (a number taken under
 # the profiler's replay is evidence of traffic, never of time) - the line says so in `traffic_source`.
-NCU_TRAFFIC = {("C3", 1): (2.115234e9 + 102.021376e6, "profiles/r1_sym_screen_kernel_ncu_full.txt (round-1 kernel, bf16 operands)")}
+NCU_TRAFFIC = {("C3", 1): (2.087769e9 + 82.432768e6, "profiles/r2_sym_screen_kernel_ncu_full.txt (round-2 kernel, float16 operands)")}
 
 
 def load_peaks():
