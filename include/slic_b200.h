@@ -204,7 +204,9 @@ int slic_hit_at_k(const int32_t* topk_idx_dev, int64_t nq, int32_t k_stride,
  *   use_filter != 0: a link survives iff weight * distance <= min_sim, weight 2 for mutual first
  *     neighbours, 1 otherwise; rows sharing a first neighbour are linked iff their own distance
  *     <= min_sim (needs unit rows + dist_nn in `dtype`).
- * num_clust_out_dev receives the component count (device int32). */
+ * num_clust_out_dev receives the component count (device int32).  Entries of nn_dev outside [0, n) are
+ * never followed; if there are any, num_clust_out_dev[0] comes back as MINUS their number (the
+ * reference raises on such an index, finch.py:41-43). */
 int slic_finch_components(const int32_t* nn_dev, int64_t n, int32_t use_filter, double min_sim,
                           const void* unit_dev, int32_t d, int32_t dtype, const void* dist_nn_dev,
                           int32_t* labels_out_dev, int32_t* num_clust_out_dev,

@@ -127,6 +127,10 @@ def test_direct_callers_with_sloppy_labels_get_defined_results(be):
     t = torch.tensor([0, 1, 2, 3], dtype=torch.int32, device=be.device)
     with pytest.raises(ValueError, match="outside"):
         be.cluster_metrics(t, t, 3, 4)                                    # label 3 >= num_true 3
+    with pytest.raises(ValueError, match="2 first-neighbour indices"):
+        be.components(torch.tensor([1, 0, 7, -1, 3], dtype=torch.int32, device=be.device))
+    lab, cnt = be.components(torch.tensor([1, 0, 3, 2, 3], dtype=torch.int32, device=be.device))
+    assert cnt == 2 and lab.cpu().tolist() == [0, 0, 1, 1, 1]
     assert be.cluster_metrics(t, t, 4, 4)[0] > 0
 
 

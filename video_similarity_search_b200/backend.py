@@ -314,7 +314,10 @@ class CudaBackend:
         _lib.call("slic_finch_components", _p(nn), n, int(use_filter), float(min_sim) if use_filter else 0.0,
                   _p(unit) if use_filter else None, d, dt, _p(dist) if use_filter else None, _p(labels), _p(count),
                   self._stream())
-        return labels, int(count.item())
+        c = int(count.item())
+        if c < 0:      # the reference's sparse-matrix constructor raises on such indices (finch.py:41-43)
+            raise ValueError("components: %d first-neighbour indices lie outside [0, n)" % -c)
+        return labels, c
 
     def min_sim(self, nn, unit, dist):
         out = torch.empty(1, dtype=torch.float32, device=nn.device)

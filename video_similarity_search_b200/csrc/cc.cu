@@ -208,6 +208,10 @@ __global__ void cc_relabel_kernel(const int* __restrict__ root, const int* __res
     }
 }
 
+__global__ void negate_count_if_bad_kernel(const int* __restrict__ bad, int* __restrict__ count) {
+    if (*bad > 0) *count = -*bad;
+}
+
 __global__ void compose_kernel(const int* __restrict__ prev, const int* __restrict__ u, int64_t n,
                                int* __restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -362,13 +366,24 @@ int slic_finch_components(const int32_t* nn_dev, int64_t n, int32_t use_filter, 
         SLIC_CUDA_OK(cudaMemsetAsync(num_clust_out_dev, 0, sizeof(int), st));
         return SLIC_OK;
     }
+    // neighbour indices outside [0, n) are never followed (no out-of-bounds access); the reference's sparse-matrix
+    // constructor raises on them (finch.py:41-43) - here the count comes back NEGATED (-number of such rows)
+    slic::Scratch bad;
+    SLIC_CUDA_OK(bad.alloc(sizeof(int), st));
+    SLIC_CUDA_OK(cudaMemsetAsync(bad.ptr, 0, sizeof(int), st));
+    int status;
     if (use_filter && dtype == SLIC_F64)
-        return slic::components_impl<double>(nn_dev, n, 1, min_sim, nullptr, (const double*)unit_dev, d,
-                                             (const double*)dist_nn_dev, labels_out_dev, num_clust_out_dev, nullptr,
-                                             nullptr, st);
-    return slic::components_impl<float>(nn_dev, n, use_filter, min_sim, nullptr, (const float*)unit_dev, d,
-                                        (const float*)dist_nn_dev, labels_out_dev, num_clust_out_dev, nullptr, nullptr,
-                                        st);
+        status = slic::components_impl<double>(nn_dev, n, 1, min_sim, nullptr, (const double*)unit_dev, d,
+                                               (const double*)dist_nn_dev, labels_out_dev, num_clust_out_dev, nullptr,
+                                               nullptr, st, bad.as<int>());
+    else
+        status = slic::components_impl<float>(nn_dev, n, use_filter, min_sim, nullptr, (const float*)unit_dev, d,
+                                              (const float*)dist_nn_dev, labels_out_dev, num_clust_out_dev, nullptr,
+                                              nullptr, st, bad.as<int>());
+    SLIC_PROPAGATE(status);
+    slic::negate_count_if_bad_kernel<<<1, 1, 0, st>>>(bad.as<int>(), num_clust_out_dev);
+    SLIC_LAUNCH_OK();
+    return SLIC_OK;
 }
 
 int slic_finch_min_sim(const int32_t* nn_dev, int64_t n, const void* unit_dev, int32_t d, int32_t dtype,
