@@ -454,19 +454,27 @@ def run_b200(args):
     def step_nn_only():
         return (search(x_dev) if search else be.first_neighbors(x_dev))
 
+    def warm(fn, k):
+        """k untimed calls with the holding pattern of timed(): the previous result stays alive while the next is computed.
+        FINCH delivers its label matrix in page-locked buffers that are reused once the caller has dropped the result
+        (backend.PinnedResultPool), so the steady state of such a loop needs two of them - a buffer allocated inside a
+        timed region (cudaHostAlloc of 31 MB: 14 ms) would be start-up cost booked as step time."""
+        out = None
+        for _ in range(k):
+            out = fn()
+        return out
+
     warmup = max(args.warmup, 3)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.launch()             # (separate process; comes up during the warm-up steps)
-    for _ in range(warmup):          # (also builds the stream-ordered memory pool)
-        step_resident()
+    warm(step_resident, warmup)      # (also builds the stream-ordered memory pool)
     # Multi-GPU: the first steps after start-up run slower than the steady state whatever is timed - measured at 8 GPUs
     # (scripts/sampler_probe.py): 7.75 ms per step for steps 4-8 of the process, 6.4-6.6 for the next 25, 6.35 from then on
     # (peer mappings, NVLink links and eight processes' allocator pools settling; the clock sampler was ruled out by the
     # same probe).  Extra UNTIMED settling steps at N > 1, reported in the line; the K timed steps are unchanged.
     settle = 12 if world > 1 else 0
-    for _ in range(settle):
-        step_resident()
+    warm(step_resident, settle)
     if rank == 0:
         sampler.start()
     launches0 = lib.slic_launch_count()
@@ -500,17 +508,17 @@ def run_b200(args):
     # with the level-0 neighbours handed in
     cached = step_nn_only()
     tail_step = lambda: FINCH(x_dev, verbose=False, backend=be, first_neighbors=lambda m: cached)   # noqa: E731
-    tail_step()        # (warm-up: with caller-supplied neighbours the driver sizes its buffers for n clusters - pool growth)
+    warm(tail_step, 3)   # (with caller-supplied neighbours the driver sizes its buffers for n clusters - pool growth)
     ms_tail, _ = timed(tail_step, args.steps)
-    del cached
+    del cached, _
     ms_e2e = ms_e2e_pageable = None
     if not big:
-        for _ in range(2):
-            host_step(x_pinned)()
+        warm(host_step(x_pinned), 3)
         ms_e2e, _ = timed(host_step(x_pinned), args.steps)
-        for _ in range(2):
-            host_step(x_host)()
+        del _
+        warm(host_step(x_host), 3)
         ms_e2e_pageable, _ = timed(host_step(x_host), args.steps)
+        del _
 
     sharded_equal = None
     if world > 1:

@@ -302,8 +302,12 @@ int slic_group_by_label(const int32_t* labels_dev, int64_t n, int32_t num_labels
  *                     level0_dense 0) or an external search such as the row-sharded multi-GPU one
  *                     (dist0_dev [n] float32, unit0_dev [n, d] float32, level0_dense as above).
  * labels_out_dev: room for [n, capacity] int32; on return its first n * P entries are the [n, P]
- * C-contiguous matrix `c` of the reference (column l = partition l).  num_clust_out_host [capacity],
- * *num_levels_out_host = P.  SLIC_ERR_OVERFLOW if the hierarchy has more than `capacity` levels. */
+ * C-contiguous matrix `c` of the reference (column l = partition l).  It may also be the device view
+ * of page-locked host memory (cudaHostAlloc / a pinned torch tensor: the same address under unified
+ * addressing): the matrix is then written over PCIe by the last kernel of the hierarchy and is on
+ * the host when the call returns - no copy after the level count is known.  num_clust_out_host
+ * [capacity], *num_levels_out_host = P.  SLIC_ERR_OVERFLOW if the hierarchy has more than
+ * `capacity` levels. */
 /* clustering/finch.py:19 (FLANN_THRESHOLD = 70000, a module constant): the row count above which the
  * reference holds no dense distances (no min_sim filter at that level).  Default 70000. */
 int slic_set_flann_threshold(int64_t rows);
@@ -326,8 +330,9 @@ int slic_first_neighbors_host(const void* x_host, int64_t n, int32_t d, int32_t 
  * The host -> device copy is cut into row chunks that are normalised as they land while the
  * level-0 tensor-core screen, launched first, consumes them (see csrc/finch_driver.cu), so the
  * PCIe transfer is hidden behind the O(N^2 D) stage.  initial_rank_host: NULL or [n] int64.
- * labels_out_host: room for [n, capacity] int32 (capacity <= 64); filled as [n, P] C-contiguous.
- * Blocks until the labels are in place. */
+ * labels_out_host: room for [n, capacity] int32 (capacity <= 64); filled as [n, P] C-contiguous
+ * (page-locked memory is written by the device directly, pageable memory through a device buffer
+ * and a copy).  Blocks until the labels are in place. */
 int slic_finch_host(const float* x_host, int64_t n, int32_t d, const int64_t* initial_rank_host,
                     int32_t ensure_early_exit, int32_t capacity, int32_t* labels_out_host,
                     int32_t* num_clust_out_host, int32_t* num_levels_out_host,

@@ -141,6 +141,42 @@ def test_native_driver_equals_python_level_loop(be):
         assert np.array_equal(c_loop, c_dev.cpu().numpy()) and np.array_equal(c_loop, c_host)
 
 
+def test_labels_delivered_in_pinned_memory_are_not_aliased_between_calls(be):
+    """FINCH returns a numpy matrix that the DEVICE wrote into a page-locked buffer of the result pool (no staging copy):
+    equal to the device-resident result, writable, C-contiguous int32 - and a result the caller still holds is never
+    overwritten by later calls (resident input, host input, pinned and pageable destinations of slic_finch_host)."""
+    import ctypes
+    from video_similarity_search_b200 import _lib
+    from video_similarity_search_b200.clustering.finch import FINCH
+    held = []
+    for n, d, k, seed in ((20000, 64, 40, 31), (20000, 64, 25, 32), (5000, 32, 10, 33), (20000, 64, 40, 34)):
+        x = synth.gaussian_mixture(n, d, k, seed)
+        dev = be.to_device(x)
+        c_dev, num_dev, _ = be.finch_native(dev)
+        want = c_dev.cpu().numpy()
+        c_res, num_res, _ = FINCH(dev, backend=be, verbose=False)           # slic_finch, pinned sink
+        c_host, num_host, _ = FINCH(x, backend=be, verbose=False)           # slic_finch_host, pinned sink
+        for c in (c_res, c_host):
+            assert isinstance(c, np.ndarray) and c.dtype == np.int32 and c.flags.c_contiguous and c.flags.writeable
+            assert np.array_equal(c, want)
+        assert num_res == num_dev == num_host
+        held.append((want, c_res, c_host))
+    for want, c_res, c_host in held:                                        # nothing was overwritten meanwhile
+        assert np.array_equal(c_res, want) and np.array_equal(c_host, want)
+    # pageable destination through the C ABI: device buffer + copy, same matrix
+    want, _, _ = held[0]
+    x = synth.gaussian_mixture(20000, 64, 40, 31)
+    n, d, cap = x.shape[0], x.shape[1], 32
+    out = np.full(n * cap, -1, dtype=np.int32)
+    num = (ctypes.c_int32 * cap)()
+    levels, has = ctypes.c_int32(0), ctypes.c_int32(0)
+    ms = ctypes.c_float(0)
+    _lib.call("slic_finch_host", x.ctypes.data, n, d, None, 1, cap, out.ctypes.data, ctypes.addressof(num),
+              ctypes.addressof(levels), ctypes.addressof(ms), ctypes.addressof(has))
+    p = levels.value
+    assert np.array_equal(out[: n * p].reshape(n, p), want) and (out[n * p:] == -1).all()
+
+
 def test_host_entry_pipelined_upload_matches_resident_path(be):
     """slic_finch_host above 32 768 rows launches the level-0 screen BEFORE the embeddings have arrived and feeds it
     chunk by chunk (gates).  Result must equal the resident path bit for bit - pageable and pinned source, a row count

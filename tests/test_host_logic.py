@@ -162,3 +162,45 @@ def test_iic_topk_retrieval_files(tmp_path):
     assert json.load(open(tmp_path / "topk_correct.json")) == {str(k): v for k, v in exp.items()}
     assert buf.getvalue().splitlines()[0] == "Load local .npy files."
     assert "Top-50, correct = " in buf.getvalue()
+
+
+def test_pinned_result_pool_never_reuses_a_buffer_the_caller_still_holds():
+    """backend.PinnedResultPool (results are delivered in page-locked buffers without a host-side copy): a buffer goes
+    back into circulation only after the array handed out AND every view of it are gone."""
+    import gc
+    from video_similarity_search_b200.backend import PinnedResultPool
+    allocated = []
+
+    def alloc(nbytes):
+        allocated.append(nbytes)
+        return torch.empty(nbytes, dtype=torch.uint8)          # (pageable stand-in: no CUDA on this box)
+
+    pool = PinnedResultPool(keep=2, alloc=alloc)
+    raw, addr_a = pool.take(800)
+    c = raw[:800].view(np.int32).reshape(100, 2)               # what finch_host returns: a view of the buffer
+    c[:] = 7
+    del raw
+    other, addr_b = pool.take(800)                             # the first result is still alive: another buffer
+    assert addr_b != addr_a and len(allocated) == 2
+    other[:] = 0
+    assert (c == 7).all()
+    column = c[:, 0]                                           # a view of a view keeps the buffer out of circulation
+    del c
+    gc.collect()
+    third, addr_c = pool.take(400)
+    assert addr_c not in (addr_a, addr_b) and len(allocated) == 3
+    assert (column == 7).all()
+    del column, other
+    gc.collect()
+    again, addr_d = pool.take(400)                             # both early buffers are idle now: one of them is reused
+    assert addr_d in (addr_a, addr_b) and len(allocated) == 3
+    big, _ = pool.take(1 << 23)                                # larger than anything kept: a new buffer, idle small ones go
+    assert len(allocated) == 4 and big.nbytes == 1 << 23
+    assert len(pool._entries) <= 4
+    del third, again, big
+    gc.collect()
+    for size in (1 << 23) + 1, (1 << 23) + 2, (1 << 23) + 3:  # ever larger requests with everything idle: the pool stays small
+        held, _ = pool.take(size)
+        del held
+        gc.collect()
+    assert len(pool._entries) <= 2

@@ -7,6 +7,7 @@ host logic in clustering/finch.py can be exercised on a box without a GPU; it is
 infrastructure and is never selected by the product code.)
 """
 import ctypes
+import weakref
 
 import numpy as np
 import torch
@@ -29,6 +30,33 @@ def d_pad_of(d):
     return (d + 63) // 64 * 64
 
 
+class PinnedResultPool:
+    """Page-locked host buffers that results are DELIVERED in (no staging copy on the host side): take() hands out a
+    numpy byte array backed by a pinned buffer; the buffer is reused only after that array - and every view of it,
+    i.e. whatever the caller still holds of the result - has been garbage-collected (weak reference).  cudaHostAlloc
+    costs ~1 ms, so buffers are kept; at most `keep` idle ones.  `alloc` is injectable for tests without a GPU."""
+
+    def __init__(self, keep=4, alloc=None):
+        self._entries = []      # [buffer (uint8 tensor), weakref to the numpy array handed out | None]
+        self._keep = keep
+        self._alloc = alloc or (lambda nbytes: torch.empty(nbytes, dtype=torch.uint8, pin_memory=True))
+
+    def take(self, nbytes):
+        """-> (numpy uint8 [nbytes] in page-locked memory, its address)."""
+        free = [e for e in self._entries if e[1] is None or e[1]() is None]
+        fit = [e for e in free if e[0].numel() >= nbytes]
+        if fit:
+            entry = min(fit, key=lambda e: e[0].numel())
+        else:
+            drop = free[max(self._keep - 1, 0):]             # idle buffers that are too small: let them go
+            self._entries = [e for e in self._entries if not any(e is x for x in drop)]
+            entry = [self._alloc(max(int(nbytes), 1 << 22)), None]
+            self._entries.append(entry)
+        arr = entry[0].numpy()
+        entry[1] = weakref.ref(arr)
+        return arr[:nbytes], entry[0].data_ptr()
+
+
 class CudaBackend:
     name = "cuda"
 
@@ -41,6 +69,7 @@ class CudaBackend:
             _lib.check(self.lib.slic_require_device(), "slic_require_device")
         self.last_stats = None
         self._stage = None
+        self._results = PinnedResultPool()
         self._multi = None
 
     # -- plumbing ------------------------------------------------------------------------------
@@ -196,19 +225,29 @@ class CudaBackend:
         _lib.call("slic_comm_nn_top1", comm, _p(unit), _p(ub), n, d, ub.shape[1], _p(nn), _p(dist), _p(status), self._stream())
         return nn, dist, unit, status
 
-    def finch_native_comm(self, comm, data, ensure_early_exit=True):
+    def _labels_sink(self, n, cap, device, host_labels):
+        """Destination of a hierarchy's [N, P] label matrix: device memory, or (host_labels) a page-locked host buffer
+        that the last kernel of the hierarchy writes over PCIe - the labels are then on the host when the call returns.
+        -> (address for the C ABI, finish(p) -> the [N, P] matrix, keep-alive)."""
+        if host_labels:
+            arr, addr = self._results.take(n * cap * 4)
+            return addr, (lambda p: arr[: n * p * 4].view(np.int32).reshape(n, p)), arr
+        labels = torch.empty(n * cap, dtype=torch.int32, device=device)
+        return _p(labels), (lambda p: labels[: n * p].view(n, p)), labels
+
+    def finch_native_comm(self, comm, data, ensure_early_exit=True, host_labels=False):
         """slic_comm_finch: the whole hierarchy with the level-0 search shared by the ranks connected through `comm`
         (every rank calls it with the same device matrix).  -> as finch_native."""
         n, d = data.shape
         cap = self.FINCH_CAPACITY
-        labels = torch.empty(n * cap, dtype=torch.int32, device=data.device)
+        sink, finish, _keep = self._labels_sink(n, cap, data.device, host_labels)
         num = (ctypes.c_int32 * cap)()
         levels, has = ctypes.c_int32(0), ctypes.c_int32(0)
         ms = ctypes.c_float(0)
-        _lib.call("slic_comm_finch", comm, _p(data), n, d, int(bool(ensure_early_exit)), cap, _p(labels),
+        _lib.call("slic_comm_finch", comm, _p(data), n, d, int(bool(ensure_early_exit)), cap, sink,
                   ctypes.addressof(num), ctypes.addressof(levels), ctypes.addressof(ms), ctypes.addressof(has), self._stream())
         p = levels.value
-        return labels[: n * p].view(n, p), [int(v) for v in num[:p]], (np.float32(ms.value) if has.value else None)
+        return finish(p), [int(v) for v in num[:p]], (np.float32(ms.value) if has.value else None)
 
     # -- rank-0-driven multi-GPU FINCH (csrc/comm.cu): one process, all GPUs of the box -------------------
     def enable_multi_gpu(self, devices=None, max_rows=1 << 21):
@@ -369,31 +408,30 @@ class CudaBackend:
     FINCH_CAPACITY = 32   # label columns provided to the native driver (a FINCH level at least halves the clusters
                           # unless the min_sim cut intervenes; more levels -> SlicError status -5, see FINCH())
 
-    def finch_native(self, data, nn0=None, dist0=None, unit0=None, dense0=False, ensure_early_exit=True):
-        """slic_finch on a device-resident float32 matrix.  -> (c int32 [N, P] device, num_clust list, min_sim or None)."""
+    def finch_native(self, data, nn0=None, dist0=None, unit0=None, dense0=False, ensure_early_exit=True, host_labels=False):
+        """slic_finch on a device-resident float32 matrix.  -> (c int32 [N, P], num_clust list, min_sim or None); c is a
+        device tensor, or with host_labels a numpy array in page-locked memory written by the device (see _labels_sink)."""
         n, d = data.shape
         cap = self.FINCH_CAPACITY
-        labels = torch.empty(n * cap, dtype=torch.int32, device=data.device)
+        sink, finish, _keep = self._labels_sink(n, cap, data.device, host_labels)
         num = (ctypes.c_int32 * cap)()
         levels, has = ctypes.c_int32(0), ctypes.c_int32(0)
         ms = ctypes.c_float(0)
         _lib.call("slic_finch", _p(data), n, d, _p(nn0), _p(dist0), _p(unit0), int(bool(dense0)), int(bool(ensure_early_exit)),
-                  cap, _p(labels), ctypes.addressof(num), ctypes.addressof(levels), ctypes.addressof(ms),
+                  cap, sink, ctypes.addressof(num), ctypes.addressof(levels), ctypes.addressof(ms),
                   ctypes.addressof(has), self._stream())
         p = levels.value
-        return labels[: n * p].view(n, p), [int(v) for v in num[:p]], (np.float32(ms.value) if has.value else None)
+        return finish(p), [int(v) for v in num[:p]], (np.float32(ms.value) if has.value else None)
 
     def finch_host(self, x, initial_rank=None, ensure_early_exit=True):
         """slic_finch_host on a C-contiguous float32 numpy matrix (pageable or pinned): chunked upload hidden behind the
         level-0 screen.  -> (c int32 [N, P] numpy, num_clust list, min_sim or None)."""
         n, d = x.shape
         cap = self.FINCH_CAPACITY
-        # labels come back into the cached pinned staging buffer (a pageable destination makes the runtime stage the copy
-        # itself, at a fraction of the PCIe rate); only the [N, P] prefix that was written is copied out
-        nbytes = n * cap * 4
-        if self._stage is None or self._stage.numel() < nbytes:
-            self._stage = torch.empty(max(nbytes, 1 << 22), dtype=torch.uint8, pin_memory=True)
-        out = self._stage[:nbytes].view(torch.int32).numpy()
+        # the labels are delivered in a page-locked buffer of the result pool: the device writes the [N, P] matrix into it
+        # directly and the caller receives a view of it - no staging copy on either side
+        raw, _ = self._results.take(n * cap * 4)
+        out = raw.view(np.int32)
         num = (ctypes.c_int32 * cap)()
         levels, has = ctypes.c_int32(0), ctypes.c_int32(0)
         ms = ctypes.c_float(0)
@@ -413,7 +451,7 @@ class CudaBackend:
                           int(bool(ensure_early_exit)), cap, out.ctypes.data, ctypes.addressof(num), ctypes.addressof(levels),
                           ctypes.addressof(ms), ctypes.addressof(has))
         p = levels.value
-        return out[: n * p].reshape(n, p).copy(), [int(v) for v in num[:p]], (np.float32(ms.value) if has.value else None)
+        return out[: n * p].reshape(n, p), [int(v) for v in num[:p]], (np.float32(ms.value) if has.value else None)
 
     # -- K4 --------------------------------------------------------------------------------------
     def label_mask(self, a, b, prepend_ones=False, negate=False):

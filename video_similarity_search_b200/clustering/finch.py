@@ -164,12 +164,13 @@ def _finch_native(be, data, initial_rank, ensure_early_exit, first_neighbors):
         if comm is not None:
             # multi-GPU, one process per GPU: normalise + shared level-0 search + the rest of the hierarchy behind ONE
             # call on every rank (csrc/comm.cu), no host synchronisation between the stages
-            c_dev, num_clust, _ = be.finch_native_comm(comm, dev, ensure_early_exit)
-            return be.to_host(c_dev), num_clust, dev
+            c, num_clust, _ = be.finch_native_comm(comm, dev, ensure_early_exit, host_labels=True)
+            return c, num_clust, dev
         nn0, dist0, unit0 = first_neighbors(dev)
         dense0 = n <= FLANN_THRESHOLD
-    c_dev, num_clust, _ = be.finch_native(dev, nn0, dist0, unit0, dense0, ensure_early_exit)
-    return be.to_host(c_dev), num_clust, dev
+    # (host_labels: the device writes the label matrix straight into page-locked host memory - FINCH returns numpy)
+    c, num_clust, _ = be.finch_native(dev, nn0, dist0, unit0, dense0, ensure_early_exit, host_labels=True)
+    return c, num_clust, dev
 
 
 def FINCH(data, initial_rank=None, req_clust=None, distance='cosine', ensure_early_exit=True, verbose=True,

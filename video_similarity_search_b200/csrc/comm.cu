@@ -24,6 +24,7 @@
 //      (= np.argmin's rule: smallest distance, then lowest index) straight into nn / dist.  (Round 1: NCCL all-reduce MIN
 //      + unpack kernel.)
 // Bytes over NVLink per rank: 4 N (G-1)/G of published bests (+ one counter add per pre-pass warp) + 8 N (G-1) of keys read.
+#include <stdlib.h>
 #include <string.h>
 
 #include <condition_variable>
@@ -44,6 +45,7 @@ constexpr size_t WIN_HEADER_BYTES = 1024;
 struct WindowHeader {
     int flags[COMM_PHASES][COMM_MAX_RANKS];   // flags[phase][src] = epoch of the last barrier rank `src` has entered
     int sync_counter;                         // pre-pass arrivals of all ranks' screen kernels (this search)
+    int unit_queue;                           // rank 0's window only: the box-wide unit counter of the fused screen kernels
 };
 static_assert(sizeof(WindowHeader) <= WIN_HEADER_BYTES, "window header");
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -189,6 +191,16 @@ static WindowPtrs window_ptrs(const Comm* c) {
     return wp;
 }
 
+// SLIC_COMM_SHARED_QUEUE=1 (experiment, off by default): ONE unit queue for the whole box instead of a fixed 1/G share of
+// the triangle per rank - every rank holds the complete unit list and draws from a counter in rank 0's window (an NVLink
+// atomic per unit).  Measured at C3 on 8 GPUs (scripts/exp_shared_queue.py, gpurun_out/exp_sq8.log): the ranks' screen
+// kernels become equal (4.14-4.15 ms each) but slower than the slowest fixed share (3.56-3.82 ms): level-0 stage 4.77-4.85 ms
+// against 4.40-4.57 ms; at 2 GPUs 13.37 against 13.22 ms.  Shorter units (32 / 16 blocks) do not change that.
+static bool shared_unit_queue() {
+    const char* e = getenv("SLIC_COMM_SHARED_QUEUE");   // (read per call: the A/B script flips it inside one process group)
+    return e && atoi(e) == 1;
+}
+
 struct BarrierCtx {
     const Comm* c;
     int rank, phase, epoch;
@@ -218,6 +230,10 @@ static int comm_nn_top1_rank(const Comm* c, int rank, int epoch, const float* un
         sp.peer_best[sp.num_peers] = reinterpret_cast<unsigned int*>(c->win[g] + win_best_off());
         sp.peer_sync[sp.num_peers] = &reinterpret_cast<WindowHeader*>(c->win[g])->sync_counter;
         ++sp.num_peers;
+    }
+    if (shared_unit_queue()) {
+        sp.shared_queue = &reinterpret_cast<WindowHeader*>(c->win[0])->unit_queue;
+        sp.queue_to_zero = rank == 0 ? sp.shared_queue : nullptr;
     }
     Scratch lidx, ldist, lstats;
     SLIC_CUDA_OK(lidx.alloc((size_t)n * sizeof(int), st));

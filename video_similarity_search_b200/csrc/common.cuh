@@ -89,6 +89,9 @@ struct ScreenPeers {
     int* own_sync;                             // this rank's pre-pass arrival counter (its window)
     unsigned int* peer_best[SLIC_MAX_PEERS];   // the same two of every other rank
     int* peer_sync[SLIC_MAX_PEERS];
+    int* shared_queue;    // optional: ONE unit counter for all ranks (in rank 0's window); every rank then runs the same
+                          // complete unit list and the GPUs balance each other dynamically
+    int* queue_to_zero;   // rank 0: the counter it resets together with its window; other ranks: nullptr
 };
 // can CTAs of the given shape co-reside with the persistent screen kernel of a gated self-search (see nn_screen_tc.cu)
 bool screen_can_overlap_upload(int64_t n, int d_pad, int guest_threads, int guest_regs);
@@ -139,6 +142,7 @@ struct StagePool {
 };
 StagePool& stage_pool();        // the calling thread's pool
 bool host_is_pageable(const void* p);
+void* pinned_device_view(void* p);   // device-writable view of page-locked host memory, or nullptr
 void parallel_host_copy(void* dst, const void* src, size_t bytes);
 int copy_to_device_staged(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t st);
 

@@ -412,11 +412,16 @@ struct Upload {
     int64_t chunk_rows;
     cudaStream_t copy_stream, main_stream;
     cudaEvent_t done;
+    cudaStream_t prep_stream;       // normalise + gate of chunk c run here while chunk c + 1 is being copied
+    cudaEvent_t* chunk_landed;      // [num_chunks] (pipelined upload only)
 };
 
 // Runs on the host right after the gated screen kernel has been launched on main_stream: enqueue, chunk by chunk,
-// copy -> normalise -> open the gate on the copy stream, then make the main stream wait for the last chunk (the
-// exact re-rank reads float32 unit rows of every chunk).
+// copy (copy stream) -> normalise -> open the gate (preparation stream, behind an event per chunk), then make the main
+// stream wait for the last chunk (the exact re-rank reads float32 unit rows of every chunk).  The copies run back to
+// back: with copy and normalise on ONE stream the copy engine idled while each chunk was normalised by guest CTAs
+// squeezed in next to the persistent screen kernel - the upload of C3 lasted 12 ms against 9.3 ms for the bare copy,
+// and the screen, whose available work grows with the square of the rows that have arrived, starved that much longer.
 static int run_upload(void* ctx) {
     Upload* up = static_cast<Upload*>(ctx);
     if (g_host_trace) SLIC_CUDA_OK(cudaEventRecord(g_up0, up->copy_stream));
@@ -441,34 +446,54 @@ static int run_upload(void* ctx) {
             SLIC_CUDA_OK(cudaEventRecord(pool.done[slot], up->copy_stream));
             pool.busy[slot] = true;
         }
+        cudaStream_t prep = up->copy_stream;
+        if (up->chunk_landed) {
+            prep = up->prep_stream;
+            SLIC_CUDA_OK(cudaEventRecord(up->chunk_landed[c], up->copy_stream));
+            SLIC_CUDA_OK(cudaStreamWaitEvent(prep, up->chunk_landed[c], 0));
+        }
         SLIC_PROPAGATE(slic_normalize_rows(up->data + r0 * up->d, rows, up->d, SLIC_F32, up->unit + r0 * up->d, nullptr,
-                                           up->ub + r0 * up->d_pad, up->d_pad, up->copy_stream));
+                                           up->ub + r0 * up->d_pad, up->d_pad, prep));
         if (up->gates) {
-            open_gate_kernel<<<1, 32, 0, up->copy_stream>>>(up->gates + c);
+            open_gate_kernel<<<1, 32, 0, prep>>>(up->gates + c);
             SLIC_LAUNCH_OK();
         }
     }
-    if (g_host_trace) SLIC_CUDA_OK(cudaEventRecord(g_up1, up->copy_stream));
-    SLIC_CUDA_OK(cudaEventRecord(up->done, up->copy_stream));
+    cudaStream_t last = up->chunk_landed ? up->prep_stream : up->copy_stream;
+    if (g_host_trace) SLIC_CUDA_OK(cudaEventRecord(g_up1, last));
+    SLIC_CUDA_OK(cudaEventRecord(up->done, last));
     SLIC_CUDA_OK(cudaStreamWaitEvent(up->main_stream, up->done, 0));
     return SLIC_OK;
 }
 
 struct HostStreams {
-    cudaStream_t main = nullptr, copy = nullptr;
+    cudaStream_t main = nullptr, copy = nullptr, prep = nullptr;
     cudaEvent_t ready = nullptr, done = nullptr;
+    std::vector<cudaEvent_t> landed;   // one per upload chunk
     int init() {
         SLIC_CUDA_OK(cudaStreamCreateWithFlags(&main, cudaStreamNonBlocking));
         SLIC_CUDA_OK(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+        SLIC_CUDA_OK(cudaStreamCreateWithFlags(&prep, cudaStreamNonBlocking));
         SLIC_CUDA_OK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
         SLIC_CUDA_OK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+        return SLIC_OK;
+    }
+    int chunk_events(int count) {
+        while ((int)landed.size() < count) {
+            cudaEvent_t e = nullptr;
+            SLIC_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            landed.push_back(e);
+        }
         return SLIC_OK;
     }
     ~HostStreams() {
         if (main) cudaStreamSynchronize(main);
         if (copy) cudaStreamSynchronize(copy);
+        if (prep) cudaStreamSynchronize(prep);
+        for (cudaEvent_t e : landed) cudaEventDestroy(e);
         if (ready) cudaEventDestroy(ready);
         if (done) cudaEventDestroy(done);
+        if (prep) cudaStreamDestroy(prep);
         if (copy) cudaStreamDestroy(copy);
         if (main) cudaStreamDestroy(main);
     }
@@ -487,12 +512,16 @@ static int finch_host_impl(const float* x_host, int64_t n, int d, const int64_t*
         HostStreams& h;
         ~Drain() {
             cudaStreamSynchronize(h.copy);
+            cudaStreamSynchronize(h.prep);
             cudaStreamSynchronize(h.main);
         }
     } drain{hs};
     SLIC_CUDA_OK(data.alloc((size_t)n * d * sizeof(float), st));
     SLIC_CUDA_OK(nn.alloc((size_t)n * sizeof(int), st));
-    SLIC_CUDA_OK(labels.alloc((size_t)n * capacity * sizeof(int), st));
+    // page-locked destination: the stacking kernel writes the [N, P] matrix into it directly (one synchronisation, no
+    // copy after the level count is known); pageable destination: device buffer + copy
+    int* labels_direct = static_cast<int*>(pinned_device_view(labels_out_host));
+    if (!labels_direct) SLIC_CUDA_OK(labels.alloc((size_t)n * capacity * sizeof(int), st));
     SLIC_CUDA_OK(blk.alloc(16 * sizeof(int), st));
     SLIC_CUDA_OK(cudaMemsetAsync(blk.ptr, 0, 16 * sizeof(int), st));
     Level0 l0;
@@ -520,7 +549,7 @@ static int finch_host_impl(const float* x_host, int64_t n, int d, const int64_t*
         const bool screen = n >= SCREEN_MIN_ROWS;
         if (screen) SLIC_CUDA_OK(ub.alloc((size_t)n * dp * 2, st));
         Upload up = {x_host, n, d, dp, data.as<float>(), unit.as<float>(), ub.as<uint16_t>(), nullptr, 1, n, hs.copy, st,
-                     hs.done};
+                     hs.done, hs.prep, nullptr};
         if (g_host_trace) SLIC_CUDA_OK(cudaEventRecord(g_t0, st));
         int guest_threads = 0, guest_regs = 0;
         SLIC_PROPAGATE(normalize_kernel_shape(&guest_threads, &guest_regs));
@@ -539,6 +568,8 @@ static int finch_host_impl(const float* x_host, int64_t n, int d, const int64_t*
             SLIC_CUDA_OK(gates.alloc((up.num_chunks + 1) * sizeof(int), st));
             SLIC_CUDA_OK(cudaMemsetAsync(gates.ptr, 0, (up.num_chunks + 1) * sizeof(int), st));
             up.gates = gates.as<int>();
+            SLIC_PROPAGATE(hs.chunk_events(up.num_chunks));
+            up.chunk_landed = hs.landed.data();
             // Every kernel the copy stream will run must be LOADED before the screen kernel starts to wait for it: with
             // lazy module loading the first launch of a function may synchronise the context - behind the very kernel
             // that is waiting.  normalize_kernel_shape() above loaded the normalise kernel; open a spare gate here.
@@ -579,10 +610,12 @@ static int finch_host_impl(const float* x_host, int64_t n, int d, const int64_t*
         if (g_host_trace) SLIC_CUDA_OK(cudaEventRecord(g_t_search, st));
     }
     int levels = 0;
-    SLIC_PROPAGATE(finch_levels(data.as<float>(), n, d, l0, ensure_early_exit, capacity, labels.as<int>(), num_clust_host,
-                                &levels, min_sim_host, has_min_sim_host, st));
+    SLIC_PROPAGATE(finch_levels(data.as<float>(), n, d, l0, ensure_early_exit, capacity,
+                                labels_direct ? labels_direct : labels.as<int>(), num_clust_host, &levels, min_sim_host,
+                                has_min_sim_host, st));
     *num_levels_host = levels;
-    SLIC_CUDA_OK(cudaMemcpyAsync(labels_out_host, labels.ptr, (size_t)n * levels * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (!labels_direct)
+        SLIC_CUDA_OK(cudaMemcpyAsync(labels_out_host, labels.ptr, (size_t)n * levels * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (g_host_trace) SLIC_CUDA_OK(cudaEventRecord(g_t_end, st));
     SLIC_CUDA_OK(cudaStreamSynchronize(st));
     return SLIC_OK;
@@ -613,7 +646,8 @@ int finch_tail_to_host(const float* data, int64_t n, int d, int* nn, float* dist
                        int* blk16, bool ensure_early_exit, int capacity, int* labels_out_host, int* num_clust_host,
                        int* num_levels_host, float* min_sim_host, int* has_min_sim_host, cudaStream_t st) {
     Scratch labels;
-    SLIC_CUDA_OK(labels.alloc((size_t)n * capacity * sizeof(int), st));
+    int* labels_direct = static_cast<int*>(pinned_device_view(labels_out_host));   // (see finch_host_impl)
+    if (!labels_direct) SLIC_CUDA_OK(labels.alloc((size_t)n * capacity * sizeof(int), st));
     Level0 l0;
     l0.nn = nn;
     l0.dist = dist;
@@ -625,11 +659,13 @@ int finch_tail_to_host(const float* data, int64_t n, int d, int* nn, float* dist
     l0.retry_dist = dist;
     l0.no_self_links = true;
     int levels = 0;
-    SLIC_PROPAGATE(finch_levels(data, n, d, l0, ensure_early_exit, capacity, labels.as<int>(), num_clust_host, &levels,
-                                min_sim_host, has_min_sim_host, st));
+    SLIC_PROPAGATE(finch_levels(data, n, d, l0, ensure_early_exit, capacity, labels_direct ? labels_direct : labels.as<int>(),
+                                num_clust_host, &levels, min_sim_host, has_min_sim_host, st));
     *num_levels_host = levels;
-    SLIC_CUDA_OK(cudaMemcpyAsync(labels_out_host, labels.ptr, (size_t)n * levels * sizeof(int), cudaMemcpyDeviceToHost, st));
-    SLIC_CUDA_OK(cudaStreamSynchronize(st));
+    if (!labels_direct) {
+        SLIC_CUDA_OK(cudaMemcpyAsync(labels_out_host, labels.ptr, (size_t)n * levels * sizeof(int), cudaMemcpyDeviceToHost, st));
+        SLIC_CUDA_OK(cudaStreamSynchronize(st));
+    }
     return SLIC_OK;
 }
 

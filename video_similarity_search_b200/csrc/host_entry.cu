@@ -41,6 +41,17 @@ bool host_is_pageable(const void* p) {
     }
     return a.type == cudaMemoryTypeUnregistered;
 }
+// Page-locked host memory that kernels of the current device can write (cudaHostAlloc / torch pin_memory under unified
+// addressing): its device view, else nullptr.  The label matrix of a hierarchy is then written by the stacking kernel
+// straight over PCIe - no staging copy in device memory, no second transfer after the level count has reached the host.
+void* pinned_device_view(void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
 void parallel_host_copy(void* dst, const void* src, size_t bytes) {
     constexpr int STAGE_THREADS = 8;
     if (bytes < ((size_t)4 << 20)) {

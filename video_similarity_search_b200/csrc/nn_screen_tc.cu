@@ -175,6 +175,7 @@ struct ScreenParams {
     // Dynamic scheduling: units are handed out in list order from this global counter (zeroed before the launch) to
     // whichever CTA pair becomes free - no pair idles while another still holds a queue of long units.
     int* queue;
+    int queue_on_peer;   // the counter lives in another GPU's window (box-wide queue experiment): system-scope draws
     // Multi-GPU fused search (comm.cu): the pre-pass units of this rank publish their rows' bests into the best arrays
     // of the OTHER ranks as well (red.max over NVLink peer mappings) and count their arrivals on every rank's
     // sync_counter, so the triangle units of every rank start from thresholds for ALL rows - the exchange that used to
@@ -978,7 +979,9 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
             const bool scheduler = cta_rank == 0;
             // (p.queue == nullptr: static striding over the CTA pairs - kept for A/B measurements, SLIC_SCREEN_STATIC=1)
             const int stride_groups = (int)(gridDim.x / NCTA);
-            int u_next = scheduler ? (p.queue ? atomicAdd(p.queue, 1) : (int)(blockIdx.x / NCTA)) : 0;
+            // (a queue shared by the GPUs of a box lives in one rank's peer-mapped window: the draw is an NVLink atomic)
+            auto draw = [&]() -> int { return p.queue_on_peer ? atomicAdd_system(p.queue, 1) : atomicAdd(p.queue, 1); };
+            int u_next = scheduler ? (p.queue ? draw() : (int)(blockIdx.x / NCTA)) : 0;
             while (true) {
                 int u;
                 if (scheduler) {
@@ -994,7 +997,7 @@ __global__ void __maxnreg__(TOPK ? 168 : TC_TOP1_MAX_REGS) nn_screen_kernel(cons
                         ring.slot = 0;
                         ring.phase ^= 1u;
                     }
-                    if (u >= 0) u_next = p.queue ? atomicAdd(p.queue, 1) : u_next + stride_groups;   // (the round trip overlaps this unit's loads)
+                    if (u >= 0) u_next = p.queue ? draw() : u_next + stride_groups;   // (the round trip overlaps this unit's loads)
                 } else {
                     u = ring_take(ring, false, p.error_flag);
                 }
@@ -1836,7 +1839,7 @@ static int launch_screen(const uint16_t* q_f16, int64_t nq, const uint16_t* x_f1
                          float* cand_kth = nullptr, const int4* unit_table = nullptr, const int* gates = nullptr,
                          unsigned int* best_enc = nullptr, int64_t exec_tiles = 0, int* log_q = nullptr,
                          int log_region = 0, int* sync_counter = nullptr, const int* sync_targets = nullptr,
-                         const ScreenPeers* peers = nullptr, int* cand_tb = nullptr) {
+                         const ScreenPeers* peers = nullptr, int* cand_tb = nullptr, int* shared_queue = nullptr) {
     const int ncta = screen_ncta();
     if (gates) SLIC_PROPAGATE(arm_timeout_record());
     CUtensorMap tq, tx;
@@ -1892,16 +1895,21 @@ static int launch_screen(const uint16_t* q_f16, int64_t nq, const uint16_t* x_f1
         }
     }
     Scratch queue;   // (freed in stream order, i.e. after the kernel)
-    SLIC_CUDA_OK(queue.alloc(sizeof(int), st));
-    SLIC_CUDA_OK(cudaMemsetAsync(queue.ptr, 0, sizeof(int), st));
-    p.queue = queue.as<int>();
+    p.queue_on_peer = shared_queue ? 1 : 0;
+    if (shared_queue) {
+        p.queue = shared_queue;   // one queue for all GPUs of the box (zeroed by its owner before the cross-rank barrier)
+    } else {
+        SLIC_CUDA_OK(queue.alloc(sizeof(int), st));
+        SLIC_CUDA_OK(cudaMemsetAsync(queue.ptr, 0, sizeof(int), st));
+        p.queue = queue.as<int>();
+    }
     {
         static int static_sched = -1;
         if (static_sched < 0) {
             const char* e = getenv("SLIC_SCREEN_STATIC");
             static_sched = e && atoi(e) == 1 ? 1 : 0;
         }
-        if (static_sched) p.queue = nullptr;
+        if (static_sched && !shared_queue) p.queue = nullptr;
     }
     const bool sym = best_enc != nullptr;
     const bool is_topk = topk > 0;
@@ -2024,7 +2032,8 @@ constexpr int SYM_SAMPLE_TILES = 16;
 enum SymMode { SYM_FULL = 0, SYM_BESTS = 1, SYM_TRIANGLE = 2, SYM_FUSED = 3 };
 constexpr int SYM_FUSED_PRE_TILES = 16;   // fused pre-pass: a row unit's sample is cut into units of this many tiles (balance)
 static int plan_screen_sym(int64_t n, int bn, int part, int parts, const GateSpec* g, ScreenPlan* pl,
-                           std::vector<int4>* table, SymMode mode = SYM_FULL, int64_t* prepass_units_all = nullptr) {
+                           std::vector<int4>* table, SymMode mode = SYM_FULL, int64_t* prepass_units_all = nullptr,
+                           bool whole_list = false /* SYM_FUSED: the units of ALL parts (shared queue) */) {
     const bool own_rows_prepass = mode == SYM_BESTS || mode == SYM_FUSED;
     // R row units of 256 rows (a CTA pair's rows), T column tiles of bn columns, tpr = column tiles per row unit: the
     // diagonal block of row unit r is made of column tiles [r * tpr, (r + 1) * tpr) and is filtered along rows only
@@ -2069,8 +2078,13 @@ static int plan_screen_sym(int64_t n, int bn, int part, int parts, const GateSpe
     int samples = samples_w * tpr;
     if (samples > span) samples = (int)span;
     const int stride = (int)(span / samples);
-    const int64_t pre0 = own_rows_prepass ? R * part / parts : 0, pre1 = own_rows_prepass ? R * (part + 1) / parts : R;
-    const int pre_len = mode == SYM_FUSED ? SYM_FUSED_PRE_TILES * tpr : samples;
+    const int64_t pre0 = (own_rows_prepass && !whole_list) ? R * part / parts : 0;
+    const int64_t pre1 = (own_rows_prepass && !whole_list) ? R * (part + 1) / parts : R;
+    int pre_len = mode == SYM_FUSED ? SYM_FUSED_PRE_TILES * tpr : samples;
+    if (const char* e = getenv("SLIC_SYM_PRE_TILES")) {   // experiments only (fused pre-pass unit, in 256-column blocks)
+        const int v = atoi(e);
+        if (mode == SYM_FUSED && v >= 1 && v <= 64) pre_len = v * tpr;
+    }
     if (prepass_units_all) *prepass_units_all = R * ceil_div(samples, pre_len);
     for (int64_t r = pre0; r < pre1 && mode != SYM_TRIANGLE; ++r) {
         const int gate = g ? (int)(r / chunk_units_gate) : -1;
@@ -2081,7 +2095,11 @@ static int plan_screen_sym(int64_t n, int bn, int part, int parts, const GateSpe
     // part / parts: a CONTIGUOUS range of the chunk-major unit list holding 1 / parts of the triangle's tiles.  (Dealing
     // the units round-robin was measured at 8 ranks: a rank's 74 concurrent CTA pairs then span ~9 column chunks, the B
     // tiles are no longer shared through L2 and the kernel runs at half speed.)
-    const int64_t chunk_tiles = (int64_t)SYM_CHUNK_TILES * tpr;   // 16 384 columns = 16 MB of f16 B rows at d_pad 512
+    int64_t chunk_tiles = (int64_t)SYM_CHUNK_TILES * tpr;   // 16 384 columns = 16 MB of f16 B rows at d_pad 512
+    if (const char* e = getenv("SLIC_SYM_CHUNK_TILES")) {   // experiments only (in 256-column blocks)
+        const int v = atoi(e);
+        if (v >= 8 && v <= 1024) chunk_tiles = (int64_t)v * tpr;
+    }
     int64_t total_tiles = 0;
     for (int64_t c0 = 0; c0 < T; c0 += chunk_tiles) {
         const int64_t c1 = c0 + chunk_tiles < T ? c0 + chunk_tiles : T;
@@ -2095,7 +2113,7 @@ static int plan_screen_sym(int64_t n, int bn, int part, int parts, const GateSpe
     unit_len = unit_len < 8 * tpr ? 8 * tpr : (unit_len > chunk_tiles ? chunk_tiles : unit_len);
     if (const char* e = getenv("SLIC_SYM_UNIT_TILES")) {   // experiments only (in 256-column blocks)
         const int v = atoi(e);
-        if (v >= 1 && v <= SYM_CHUNK_TILES) unit_len = (int64_t)v * tpr;
+        if (v >= 1 && v <= SYM_CHUNK_TILES && (int64_t)v * tpr <= chunk_tiles) unit_len = (int64_t)v * tpr;
     }
     int64_t seen_tiles = 0;
     for (int64_t c0 = 0; c0 < T && mode != SYM_BESTS; c0 += chunk_tiles) {
@@ -2106,7 +2124,7 @@ static int plan_screen_sym(int64_t n, int bn, int part, int parts, const GateSpe
                 const int64_t cnt = c1 - ct0 < unit_len ? c1 - ct0 : unit_len;
                 const int64_t owner = seen_tiles * parts / total_tiles;   // < parts: seen_tiles < total_tiles here
                 seen_tiles += cnt;
-                if (owner != part) continue;
+                if (owner != part && !whole_list) continue;
                 table->push_back(unit_entry(r, ct0, (int)cnt, 1, gate, 0, nocol == 0));
             }
         }
@@ -2306,10 +2324,11 @@ __global__ void flip_sign_bit_kernel(const unsigned int* __restrict__ in, int64_
 __global__ void sym_init_kernel(int* __restrict__ stats8, int* __restrict__ lcnt, int64_t regions,
                                 unsigned char* __restrict__ rmin_bytes, int64_t rmin_n_bytes, int* __restrict__ sync_counter,
                                 unsigned int* __restrict__ best, const unsigned int* __restrict__ bests_in, int64_t n,
-                                unsigned int* __restrict__ idx_out) {
+                                unsigned int* __restrict__ idx_out, int* __restrict__ queue_to_zero) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < 8) stats8[i] = 0;
     if (i == 0) *sync_counter = 0;
+    if (i == 0 && queue_to_zero) *queue_to_zero = 0;
     if (i < regions) lcnt[i] = 0;
     if (i < n) {
         best[i] = bests_in ? (bests_in[i] ^ 0x80000000u) : ENC_NEG_INF;   // exchanged bests arrive in signed-comparable form
@@ -2429,7 +2448,11 @@ static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d,
     ScreenPlan pl;
     std::vector<int4> table;
     int64_t prepass_units_all = 0;
-    SLIC_PROPAGATE(plan_screen_sym(n, screen_bn(d_pad), part, parts, gate, &pl, &table, (SymMode)mode, &prepass_units_all));
+    // fused multi-GPU search with ONE unit queue for the box: every rank holds the same complete list (all rows' pre-pass,
+    // the whole triangle) and draws from the shared counter - the GPUs balance each other as the CTA pairs of one GPU do
+    const bool shared_list = peers && peers->shared_queue;
+    SLIC_PROPAGATE(plan_screen_sym(n, screen_bn(d_pad), part, parts, gate, &pl, &table, (SymMode)mode, &prepass_units_all,
+                                   shared_list));
     SLIC_REQUIRE((mode == SYM_FUSED) == (peers != nullptr), "symmetric screen: the fused mode needs peer windows (and only it)");
     SLIC_REQUIRE(mode != SYM_FUSED || (stats_ext && !gate), "symmetric screen: the fused mode is asynchronous and ungated");
     int64_t exec_tiles = 0;
@@ -2488,7 +2511,8 @@ static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d,
         sym_init_kernel<<<(unsigned)ceil_div(threads, 256), 256, 0, st>>>(stats_dev, lcnt.as<int>(), regions,
                                                                          static_cast<unsigned char*>(rmin.ptr), rmin_bytes,
                                                                          sync_counter_dev, best_dev,
-                                                                         (const unsigned int*)bests_in, n, (unsigned int*)idx_out);
+                                                                         (const unsigned int*)bests_in, n, (unsigned int*)idx_out,
+                                                                         peers ? peers->queue_to_zero : nullptr);
         SLIC_LAUNCH_OK();
     }
     if (before_screen) SLIC_PROPAGATE(before_screen(before_ctx));
@@ -2500,7 +2524,8 @@ static int nn_top1_sym_impl(const T* unit, const uint16_t* ub, int64_t n, int d,
     SLIC_PROPAGATE(launch_screen(ub, n, ub, n, d_pad, 0, eps, 0, pl, lnb.as<int>(), ls.as<float>(), lcnt.as<int>(),
                                  flag_dev, nullptr, stats_dev + 4, st, 0, nullptr, table_dev.as<int4>(),
                                  gate ? gate->gates : nullptr, best_dev, exec_tiles, lq.as<int>(),
-                                 (int)region, nowait ? nullptr : sync_counter_dev, sync_dev + 1, peers));
+                                 (int)region, nowait ? nullptr : sync_counter_dev, sync_dev + 1, peers, nullptr,
+                                 shared_list ? peers->shared_queue : nullptr));
     if (g_profile && parts > 1) g_last_flop /= (double)parts;   // this process's share of the algorithmic 2 n^2 d
     if (after) SLIC_PROPAGATE(after(after_ctx));
     if (mode == SYM_BESTS) {   // phase 1 of the multi-GPU search: the row bests are the result, the log is discarded
