@@ -7,6 +7,9 @@ host logic in clustering/finch.py can be exercised on a box without a GPU; it is
 infrastructure and is never selected by the product code.)
 """
 import ctypes
+import os
+import sys
+import time
 import weakref
 
 import numpy as np
@@ -50,8 +53,13 @@ class PinnedResultPool:
         else:
             drop = free[max(self._keep - 1, 0):]             # idle buffers that are too small: let them go
             self._entries = [e for e in self._entries if not any(e is x for x in drop)]
+            t0 = time.perf_counter()
             entry = [self._alloc(max(int(nbytes), 1 << 22)), None]
             self._entries.append(entry)
+            if os.environ.get("SLIC_POOL_TRACE"):
+                print("[slic] result pool: new page-locked buffer of %.1f MB in %.2f ms (%d buffers, %d busy)"
+                      % (entry[0].numel() / 1e6, (time.perf_counter() - t0) * 1e3, len(self._entries),
+                         sum(1 for e in self._entries if e[1] is not None and e[1]() is not None)), file=sys.stderr, flush=True)
         arr = entry[0].numpy()
         entry[1] = weakref.ref(arr)
         return arr[:nbytes], entry[0].data_ptr()
