@@ -482,24 +482,34 @@ def run_b200(args):
     warm(step_resident, settle)
     if rank == 0:
         sampler.start()
-    launches0 = lib.slic_launch_count()
-    ms_step, result = timed(step_resident, args.steps)
+    # One stalled call (a host hiccup: page reclaim under an allocation, a descheduled rank the peers then wait for - seen
+    # in this harness as 0.1-0.9 s inside single calls of every one of the timed loops, before and after any change to
+    # the library) turns K x 27 ms into a second.  Like the driver's own rule for clock anomalies such a measurement is
+    # repeated ONCE and the first attempt stays in the line (`remeasured`); every rank takes the same decision.
+    remeasured = {}
+
+    def timed_checked(name, fn, steps, before=None):
+        if before:
+            before()
+        ms, out = timed(fn, steps)
+        stall = torch.tensor([1 if max(walls) > 2.5 * statistics.median(walls) else 0], dtype=torch.int32, device=be.device)
+        if world > 1:
+            dist.all_reduce(stall, op=dist.ReduceOp.MAX)
+        if int(stall.item()):
+            remeasured[name] = {"first_attempt_ms_per_step": ms, "first_attempt_host_ms_per_call_rank0": [round(v, 3) for v in walls],
+                                "rule": "a call took more than 2.5 x the median call on some rank: measured again, once"}
+            del out
+            warm(fn, 2)
+            if before:
+                before()
+            ms, out = timed(fn, steps)
+        return ms, out
+
+    mark = {}
+    ms_step, result = timed_checked("resident", step_resident, args.steps,
+                                    before=lambda: mark.__setitem__("launches0", lib.slic_launch_count()))
+    launches0 = mark["launches0"]
     step_walls = [round(v, 3) for v in walls]
-    # One stalled call (a host hiccup: page reclaim under a pinned allocation, a descheduled rank the peers then wait for)
-    # turns K x 27 ms into a second.  Like the driver's own rule for clock anomalies the measurement is then repeated ONCE
-    # and the first attempt stays in the line (`stalled_attempt`); every rank takes the same decision.
-    stalled_attempt = None
-    stall = torch.tensor([1 if max(walls) > 2.5 * statistics.median(walls) else 0], dtype=torch.int32, device=be.device)
-    if world > 1:
-        dist.all_reduce(stall, op=dist.ReduceOp.MAX)
-    if int(stall.item()):
-        stalled_attempt = {"ms_per_step": ms_step, "step_host_ms_rank0": step_walls,
-                           "rule": "a call took more than 2.5 x the median call on some rank: re-measured once"}
-        del result
-        warm(step_resident, 2)
-        launches0 = lib.slic_launch_count()
-        ms_step, result = timed(step_resident, args.steps)
-        step_walls = [round(v, 3) for v in walls]
     launches = (lib.slic_launch_count() - launches0)
     clocks = sampler.stop() if rank == 0 else None
     c, num_clust, _ = result
@@ -530,21 +540,21 @@ def run_b200(args):
 
     for _ in range(2):
         nn_only_dropped()
-    ms_nn, _ = timed(nn_only_dropped, args.steps)
+    ms_nn, _ = timed_checked("nn_stage", nn_only_dropped, args.steps)
     # everything after the level-0 search (components, means, all further levels, labels to the host): one FINCH call
     # with the level-0 neighbours handed in
     cached = step_nn_only()
     tail_step = lambda: FINCH(x_dev, verbose=False, backend=be, first_neighbors=lambda m: cached)   # noqa: E731
     warm(tail_step, 3)   # (with caller-supplied neighbours the driver sizes its buffers for n clusters - pool growth)
-    ms_tail, _ = timed(tail_step, args.steps)
+    ms_tail, _ = timed_checked("tail", tail_step, args.steps)
     del cached, _
     ms_e2e = ms_e2e_pageable = None
     if not big:
         warm(host_step(x_pinned), 3)
-        ms_e2e, _ = timed(host_step(x_pinned), args.steps)
+        ms_e2e, _ = timed_checked("e2e", host_step(x_pinned), args.steps)
         del _
         warm(host_step(x_host), 3)
-        ms_e2e_pageable, _ = timed(host_step(x_host), args.steps)
+        ms_e2e_pageable, _ = timed_checked("e2e_pageable", host_step(x_host), args.steps)
         del _
 
     sharded_equal = None
@@ -605,7 +615,7 @@ def run_b200(args):
     line = {
         "metric": METRIC, "value": n / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": warmup, "settle_steps_untimed": settle, "ms_per_step": ms_step, "step_host_ms_rank0": step_walls,
-        "stalled_attempt": stalled_attempt, "higher_is_better": True, "scaling": "strong",
+        "remeasured": remeasured or None, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f16 screen (f32 accumulate) + f32/f64 exact re-rank", "data": "synthetic",
         "config": {"workload": workload_string(n, d, k, seed),
                    "l2": "inputs exceed L2 (%.0f MB fp32 + %.0f MB fp16 per step)" % (n * d * 4 / 1e6, n * d_pad * 2 / 1e6),
