@@ -199,6 +199,17 @@ def test_pinned_result_pool_never_reuses_a_buffer_the_caller_still_holds():
     assert len(pool._entries) <= 4
     del third, again, big
     gc.collect()
+    hoard = []                                                 # a caller that keeps every result: page-locked memory stays
+    for i in range(5):                                         # bounded - from `keep` + 1 results on, ordinary copies
+        raw, _ = pool.take(64)
+        raw[:] = i
+        hoard.append(pool.deliver(raw[:64].view(np.int32)))
+        del raw
+    gc.collect()
+    assert len(pool._entries) <= 4 and all((h == i * 0x01010101).all() for i, h in enumerate(hoard))
+    assert sum(1 for h in hoard if h.flags.owndata) >= 2
+    del hoard
+    gc.collect()
     for size in (1 << 23) + 1, (1 << 23) + 2, (1 << 23) + 3:  # ever larger requests with everything idle: the pool stays small
         held, _ = pool.take(size)
         del held

@@ -37,7 +37,9 @@ class PinnedResultPool:
     """Page-locked host buffers that results are DELIVERED in (no staging copy on the host side): take() hands out a
     numpy byte array backed by a pinned buffer; the buffer is reused only after that array - and every view of it,
     i.e. whatever the caller still holds of the result - has been garbage-collected (weak reference).  cudaHostAlloc
-    costs ~1 ms, so buffers are kept; at most `keep` idle ones.  `alloc` is injectable for tests without a GPU."""
+    costs 12-80 ms for the 31 MB of a 240 000-row hierarchy (measured), so buffers are kept: at most `keep` idle ones,
+    and a caller who holds on to more than `keep` results gets ordinary right-sized copies from then on (deliver()),
+    so that page-locked memory stays bounded.  `alloc` is injectable for tests without a GPU."""
 
     def __init__(self, keep=4, alloc=None):
         self._entries = []      # [buffer (uint8 tensor), weakref to the numpy array handed out | None]
@@ -63,6 +65,12 @@ class PinnedResultPool:
         arr = entry[0].numpy()
         entry[1] = weakref.ref(arr)
         return arr[:nbytes], entry[0].data_ptr()
+
+    def deliver(self, view):
+        """The result as the caller receives it: the view of the page-locked buffer itself, or - when more than `keep`
+        buffers are out with callers - a copy in ordinary memory (the buffer is free again once `view` is dropped)."""
+        busy = sum(1 for e in self._entries if e[1] is not None and e[1]() is not None)
+        return view.copy() if busy > self._keep else view
 
 
 class CudaBackend:
@@ -239,7 +247,7 @@ class CudaBackend:
         -> (address for the C ABI, finish(p) -> the [N, P] matrix, keep-alive)."""
         if host_labels:
             arr, addr = self._results.take(n * cap * 4)
-            return addr, (lambda p: arr[: n * p * 4].view(np.int32).reshape(n, p)), arr
+            return addr, (lambda p: self._results.deliver(arr[: n * p * 4].view(np.int32).reshape(n, p))), arr
         labels = torch.empty(n * cap, dtype=torch.int32, device=device)
         return _p(labels), (lambda p: labels[: n * p].view(n, p)), labels
 
@@ -459,7 +467,8 @@ class CudaBackend:
                           int(bool(ensure_early_exit)), cap, out.ctypes.data, ctypes.addressof(num), ctypes.addressof(levels),
                           ctypes.addressof(ms), ctypes.addressof(has))
         p = levels.value
-        return out[: n * p].reshape(n, p), [int(v) for v in num[:p]], (np.float32(ms.value) if has.value else None)
+        return (self._results.deliver(out[: n * p].reshape(n, p)), [int(v) for v in num[:p]],
+                (np.float32(ms.value) if has.value else None))
 
     # -- K4 --------------------------------------------------------------------------------------
     def label_mask(self, a, b, prepend_ones=False, negate=False):
