@@ -467,7 +467,8 @@ def run_b200(args):
         out = None
         for _ in range(k):
             out = fn()
-        return out
+        barrier()      # (N > 1: the first barrier of a process has start-up work of its own - seen as a 55 ms first timed call
+        return out     #  at 2 GPUs when timed() was the first to issue one)
 
     warmup = max(args.warmup, 3)
     sampler = ClockSampler(local_rank)
