@@ -246,9 +246,14 @@ class CudaBackend:
         that the last kernel of the hierarchy writes over PCIe - the labels are then on the host when the call returns.
         -> (address for the C ABI, finish(p) -> the [N, P] matrix, keep-alive)."""
         if host_labels:
-            arr, addr = self._results.take(n * cap * 4)
-            return addr, (lambda p: self._results.deliver(arr[: n * p * 4].view(np.int32).reshape(n, p))), arr
+            try:
+                arr, addr = self._results.take(n * cap * 4)
+                return addr, (lambda p: self._results.deliver(arr[: n * p * 4].view(np.int32).reshape(n, p))), arr
+            except RuntimeError:      # no page-locked memory to be had: device buffer, then the staged copy of to_host()
+                pass
         labels = torch.empty(n * cap, dtype=torch.int32, device=device)
+        if host_labels:
+            return _p(labels), (lambda p: self.to_host(labels[: n * p].view(n, p))), labels
         return _p(labels), (lambda p: labels[: n * p].view(n, p)), labels
 
     def finch_native_comm(self, comm, data, ensure_early_exit=True, host_labels=False):
