@@ -451,8 +451,11 @@ class CudaBackend:
         cap = self.FINCH_CAPACITY
         # the labels are delivered in a page-locked buffer of the result pool: the device writes the [N, P] matrix into it
         # directly and the caller receives a view of it - no staging copy on either side
-        raw, _ = self._results.take(n * cap * 4)
-        out = raw.view(np.int32)
+        try:
+            raw, _ = self._results.take(n * cap * 4)
+            out = raw.view(np.int32)
+        except RuntimeError:          # no page-locked memory to be had: pageable destination (device buffer + copy inside)
+            out = np.empty(n * cap, dtype=np.int32)
         num = (ctypes.c_int32 * cap)()
         levels, has = ctypes.c_int32(0), ctypes.c_int32(0)
         ms = ctypes.c_float(0)
