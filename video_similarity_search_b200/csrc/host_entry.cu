@@ -1,6 +1,7 @@
 // Host-buffer entry points of the C ABI: the call a reference-side binding makes with numpy arrays.
 // They own their transfers (pageable or pinned host memory both work) and block until the result is
 // in the caller's buffers.
+#include <stdlib.h>
 #include <string.h>
 
 #include <thread>
@@ -13,9 +14,9 @@ static int d_pad_of(int d) { return (d + 63) / 64 * 64; }
 
 // Pageable source (what clustering/cluster_masks.py:80 hands over: `.cpu().numpy()`): a cudaMemcpyAsync from pageable
 // memory is staged by the driver through a small pinned bounce buffer on ONE thread (~10 GB/s measured: 492 MB in ~45 ms,
-// twice the level-0 screen it should hide behind).  Here STAGE_THREADS host threads copy a piece slice by slice into one
+// twice the level-0 screen it should hide behind).  Here several host threads (3/4 of the cores, at most 12) copy a piece slice by slice into one
 // of STAGE_SLOTS pinned staging buffers (kept for the life of the calling thread: cudaHostAlloc costs milliseconds) and
-// the DMA of piece c runs while piece c + 1 is being staged.  (Measured at C3: FINCH from a plain numpy array 56 -> 34 ms.)
+// the DMA of piece c runs while piece c + 1 is being staged.  (Measured at C3: FINCH from a plain numpy array 56 -> 31-32 ms.)
 int StagePool::ensure(size_t bytes) {
     if (cap >= bytes) return SLIC_OK;
     for (int i = 0; i < STAGE_SLOTS; ++i) {
@@ -53,12 +54,24 @@ void* pinned_device_view(void* p) {
     return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
 }
 void parallel_host_copy(void* dst, const void* src, size_t bytes) {
-    constexpr int STAGE_THREADS = 8;
-    if (bytes < ((size_t)4 << 20)) {
+    constexpr int STAGE_THREADS_MAX = 32;
+    // measured at C3 on a 16-core host (scripts/exp_stage_threads.py): 4 / 8 / 12 / 16 / 24 threads -> 34.9 / 32.3 / 31.2 / 31.4 /
+    // 31.9 ms for FINCH(plain numpy array) against 29.8 ms from pinned memory - the host copies 492 MB at ~33 GB/s at best
+    static const int default_threads = [] {
+        const int hw = (int)std::thread::hardware_concurrency();
+        const int v = hw > 0 ? hw * 3 / 4 : 8;
+        return v < 4 ? 4 : (v > 12 ? 12 : v);
+    }();
+    int STAGE_THREADS = default_threads;
+    if (const char* e = getenv("SLIC_STAGE_THREADS")) {   // experiments (scripts/exp_stage_threads.py)
+        const int v = atoi(e);
+        if (v >= 1 && v <= STAGE_THREADS_MAX) STAGE_THREADS = v;
+    }
+    if (bytes < ((size_t)4 << 20) || STAGE_THREADS == 1) {
         memcpy(dst, src, bytes);
         return;
     }
-    std::thread workers[STAGE_THREADS - 1];
+    std::thread workers[STAGE_THREADS_MAX - 1];
     const size_t per = (bytes / STAGE_THREADS + 4095) / 4096 * 4096;
     for (int t = 1; t < STAGE_THREADS; ++t) {
         const size_t o = per * t, len = o < bytes ? (bytes - o < per ? bytes - o : per) : 0;
