@@ -42,6 +42,7 @@ namespace slic {
 constexpr int COMM_MAX_RANKS = SLIC_MAX_PEERS + 1;
 constexpr int COMM_PHASES = 4;
 constexpr size_t WIN_HEADER_BYTES = 1024;
+constexpr int COMM_UPLOAD_PIECES = 4;   // rank-0-driven upload: a worker's share crosses PCIe in pieces, forwarded as they land
 struct WindowHeader {
     int flags[COMM_PHASES][COMM_MAX_RANKS];   // flags[phase][src] = epoch of the last barrier rank `src` has entered
     int sync_counter;                         // pre-pass arrivals of all ranks' screen kernels (this search)
@@ -172,6 +173,8 @@ struct Comm : slic_comm {
     // single process
     int devices[COMM_MAX_RANKS] = {};
     cudaStream_t streams[COMM_MAX_RANKS] = {};
+    cudaStream_t forward[COMM_MAX_RANKS] = {};                     // device -> peers copies of the pieces already uploaded
+    cudaEvent_t piece_up[COMM_MAX_RANKS][COMM_UPLOAD_PIECES] = {};   // piece p of worker r's share has reached its device
     cudaEvent_t uploaded[COMM_MAX_RANKS] = {};
     cudaEvent_t t0 = nullptr, t1 = nullptr, t2 = nullptr, t3 = nullptr;
     std::vector<std::thread> threads;
@@ -295,16 +298,31 @@ static int worker_call(Comm* c, int r, MultiJob* job, int epoch) {
     const int64_t r0 = per * r < n ? per * r : n, r1 = r0 + per < n ? r0 + per : n;
     if (r == 0) CUDA_STEP(cudaEventRecord(c->t0, st));
     if (r1 > r0) {
-        const size_t bytes = (size_t)(r1 - r0) * d * sizeof(float);
-        STEP(copy_to_device_staged(data.as<float>() + r0 * d, job->x_host + r0 * d, bytes, st));   // (pageable: staged by threads)
-        for (int k = 1; k < world; ++k) {
-            const int g = (r + k) % world;   // every worker starts with a different peer
-            if (job->data[g])
-                CUDA_STEP(cudaMemcpyPeerAsync(job->data[g] + r0 * d, c->devices[g], data.as<float>() + r0 * d, c->devices[r],
-                                              bytes, st));
+        // piece p + 1 crosses PCIe (host -> this device, stream st) while piece p travels on to the peers over NVLink
+        // (copy engines, stream forward[r]): the forwards of all but the last piece are hidden behind the upload
+        // (a pageable source is staged through pinned buffers by host threads, which is the slower leg anyway: one piece -
+        // measured with pieces at 2 GPUs: upload + forward 12.8 -> 15 ms)
+        const int pieces = ((size_t)(r1 - r0) * d * sizeof(float) >= ((size_t)32 << 20) && !host_is_pageable(job->x_host))
+                               ? COMM_UPLOAD_PIECES
+                               : 1;
+        const int64_t step = ceil_div(r1 - r0, pieces);
+        for (int p = 0; p < pieces; ++p) {
+            const int64_t a = r0 + step * p < r1 ? r0 + step * p : r1, b = a + step < r1 ? a + step : r1;
+            if (b <= a) continue;
+            const size_t bytes = (size_t)(b - a) * d * sizeof(float);
+            STEP(copy_to_device_staged(data.as<float>() + a * d, job->x_host + a * d, bytes, st));   // (pageable: staged by threads)
+            CUDA_STEP(cudaEventRecord(c->piece_up[r][p], st));
+            CUDA_STEP(cudaStreamWaitEvent(c->forward[r], c->piece_up[r][p], 0));
+            for (int k = 1; k < world; ++k) {
+                const int g = (r + k) % world;   // every worker starts with a different peer
+                if (job->data[g])
+                    CUDA_STEP(cudaMemcpyPeerAsync(job->data[g] + a * d, c->devices[g], data.as<float>() + a * d, c->devices[r],
+                                                  bytes, c->forward[r]));
+            }
         }
     }
-    CUDA_STEP(cudaEventRecord(c->uploaded[r], st));
+    CUDA_STEP(cudaEventRecord(c->uploaded[r], c->forward[r]));   // (forward[r] has waited for the last piece: upload AND forwards)
+    CUDA_STEP(cudaStreamWaitEvent(st, c->uploaded[r], 0));       // this worker's buffers are not reused before its forwards end
     c->bar->wait();
     for (int g = 0; g < world; ++g)
         if (g != r) CUDA_STEP(cudaStreamWaitEvent(st, c->uploaded[g], 0));
@@ -339,6 +357,7 @@ static int worker_call(Comm* c, int r, MultiJob* job, int epoch) {
 
 static void worker_main(Comm* c, int r) {
     cudaSetDevice(c->devices[r]);
+    stage_threads_shared();
     unsigned seen = 0;
     int epoch = 0;
     while (true) {
@@ -378,6 +397,9 @@ static void destroy_comm(Comm* c) {
         for (int g = 0; g < c->world; ++g) {
             cudaSetDevice(c->devices[g]);
             if (c->streams[g]) cudaStreamDestroy(c->streams[g]);
+            if (c->forward[g]) cudaStreamDestroy(c->forward[g]);
+            for (int p = 0; p < COMM_UPLOAD_PIECES; ++p)
+                if (c->piece_up[g][p]) cudaEventDestroy(c->piece_up[g][p]);
             if (c->uploaded[g]) cudaEventDestroy(c->uploaded[g]);
             if (c->win[g]) cudaFree(c->win[g]);
         }
@@ -557,6 +579,9 @@ int slic_comm_create(const int32_t* devices, int32_t num_devices, int64_t max_ro
             c->win[g] = static_cast<unsigned char*>(w);
             SLIC_CUDA_OK(cudaMemset(w, 0, win_bytes(max_rows)));
             SLIC_CUDA_OK(cudaStreamCreateWithFlags(&c->streams[g], cudaStreamNonBlocking));
+            SLIC_CUDA_OK(cudaStreamCreateWithFlags(&c->forward[g], cudaStreamNonBlocking));
+            for (int p = 0; p < COMM_UPLOAD_PIECES; ++p)
+                SLIC_CUDA_OK(cudaEventCreateWithFlags(&c->piece_up[g][p], cudaEventDisableTiming));
             SLIC_CUDA_OK(cudaEventCreateWithFlags(&c->uploaded[g], cudaEventDisableTiming));
             if (g == 0) {
                 SLIC_CUDA_OK(cudaEventCreate(&c->t0));

@@ -142,6 +142,7 @@ struct StagePool {
 };
 StagePool& stage_pool();        // the calling thread's pool
 bool host_is_pageable(const void* p);
+void stage_threads_shared();          // the calling thread shares the host with other uploading threads (comm.cu workers)
 void* pinned_device_view(void* p);   // device-writable view of page-locked host memory, or nullptr
 void parallel_host_copy(void* dst, const void* src, size_t bytes);
 int copy_to_device_staged(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t st);

@@ -53,16 +53,23 @@ void* pinned_device_view(void* p) {
     }
     return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
 }
+static thread_local bool g_stage_threads_shared = false;
+void stage_threads_shared() { g_stage_threads_shared = true; }   // this thread is one of several feeding GPUs at the same time
 void parallel_host_copy(void* dst, const void* src, size_t bytes) {
     constexpr int STAGE_THREADS_MAX = 32;
     // measured at C3 on a 16-core host (scripts/exp_stage_threads.py): 4 / 8 / 12 / 16 / 24 threads -> 34.9 / 32.3 / 31.2 / 31.4 /
     // 31.9 ms for FINCH(plain numpy array) against 29.8 ms from pinned memory - the host copies 492 MB at ~33 GB/s at best
+    // Several GPUs fed from one host at once - the worker threads of slic_finch_multi (stage_threads_shared() below), the
+    // ranks of a torchrun job (LOCAL_WORLD_SIZE) - keep 8 threads each, the configuration their numbers were measured with
+    // (2 workers x 12 threads on the 16 cores: upload 12.8 -> 14.8 ms).
     static const int default_threads = [] {
+        const char* lw = getenv("LOCAL_WORLD_SIZE");
+        if (lw && atoi(lw) > 1) return 8;
         const int hw = (int)std::thread::hardware_concurrency();
         const int v = hw > 0 ? hw * 3 / 4 : 8;
         return v < 4 ? 4 : (v > 12 ? 12 : v);
     }();
-    int STAGE_THREADS = default_threads;
+    int STAGE_THREADS = g_stage_threads_shared ? 8 : default_threads;
     if (const char* e = getenv("SLIC_STAGE_THREADS")) {   // experiments (scripts/exp_stage_threads.py)
         const int v = atoi(e);
         if (v >= 1 && v <= STAGE_THREADS_MAX) STAGE_THREADS = v;
