@@ -21,6 +21,8 @@ configs[4] (N = 1 000 000 x D = 1 024 FINCH + top-50 retrieval of 100 000 querie
   retrieval    the second half of BASELINE.json's metric: top-50 retrieval through the same screen (configs[1] and
                the configs[4] retrieval shape), ms / queries per second / fraction of the tensor peak
   cpu_baseline the oracle port of the reference (numpy / scipy / sklearn) on this box's host cores, bounded sample
+  step_host_ms_rank0   host clock of every timed call of the headline loop; `remeasured`: a timed loop in which one call took
+               more than 2.5 x the median call (a host stall) is measured again ONCE - the first attempt stays in the line
 At N > 1 the level-0 nearest-neighbour stage is shared by the ranks (strong scaling: total work fixed).
 
 --impl reference: the reference's CPU implementation (oracle port; the reference itself is pure Python that needs
