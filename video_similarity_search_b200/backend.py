@@ -9,6 +9,7 @@ infrastructure and is never selected by the product code.)
 import ctypes
 import os
 import sys
+import threading
 import time
 import weakref
 
@@ -44,10 +45,15 @@ class PinnedResultPool:
     def __init__(self, keep=4, alloc=None):
         self._entries = []      # [buffer (uint8 tensor), weakref to the numpy array handed out | None]
         self._keep = keep
+        self._lock = threading.Lock()   # (a backend may be called from several host threads)
         self._alloc = alloc or (lambda nbytes: torch.empty(nbytes, dtype=torch.uint8, pin_memory=True))
 
     def take(self, nbytes):
         """-> (numpy uint8 [nbytes] in page-locked memory, its address)."""
+        with self._lock:
+            return self._take(nbytes)
+
+    def _take(self, nbytes):
         free = [e for e in self._entries if e[1] is None or e[1]() is None]
         fit = [e for e in free if e[0].numel() >= nbytes]
         if fit:
