@@ -216,6 +216,11 @@ while True:
 """
 
 
+def has_stalled_call(host_ms_per_call, factor=2.5):
+    """The re-measurement rule of the timed loops: one call took more than `factor` x the median call."""
+    return len(host_ms_per_call) >= 3 and max(host_ms_per_call) > factor * statistics.median(host_ms_per_call)
+
+
 class ClockSampler:
     """SM clock, power and throttle reasons sampled DURING the timed region by a SEPARATE process (NVML polled every
     ~5 ms; nvidia-smi -lms 100 as the fallback when pynvml cannot initialise).  A separate process keeps the polling off
@@ -495,7 +500,7 @@ def run_b200(args):
         if before:
             before()
         ms, out = timed(fn, steps)
-        stall = torch.tensor([1 if max(walls) > 2.5 * statistics.median(walls) else 0], dtype=torch.int32, device=be.device)
+        stall = torch.tensor([1 if has_stalled_call(walls) else 0], dtype=torch.int32, device=be.device)
         if world > 1:
             dist.all_reduce(stall, op=dist.ReduceOp.MAX)
         if int(stall.item()):

@@ -67,3 +67,14 @@ def test_b200_arm_prints_the_contract_line():
     assert line["retrieval"]["C2_top50"]["indices_equal_exact_kernels"] is True
     cb = line["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["unit"] == line["unit"]
+
+
+def test_stall_rule_of_the_timed_loops():
+    """bench.has_stalled_call: a loop is measured again only when a single call stands out (the stalls seen on the GPU
+    boxes: 55 ms and 149 ms calls among 15-19 ms ones), never for ordinary jitter or for uniformly slow calls."""
+    import bench
+    assert bench.has_stalled_call([55.808, 14.104, 14.167, 14.156, 14.568, 14.579, 14.595, 14.975, 15.322, 14.985])
+    assert bench.has_stalled_call([19.078, 19.157, 19.148, 149.498, 77.455, 19.001, 18.962, 18.966, 19.831, 23.916])
+    assert not bench.has_stalled_call([26.677, 25.38, 26.022, 26.867, 26.174, 26.672, 27.257, 27.216, 27.129, 26.526])
+    assert not bench.has_stalled_call([37.8] * 10)          # a slow box is not a stall
+    assert not bench.has_stalled_call([30.0, 90.0])          # too few calls to tell
